@@ -1,0 +1,43 @@
+"""Builds libasc_b200.so (sm_100a only) in-tree with nvcc.  No torch extension machinery: the
+library is a plain C-ABI shared object (include/asc.h)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libasc_b200.so")
+SOURCES = ["asc_api.cu", "sim_generator.cpp"]
+DEPS = SOURCES + ["kernels.cuh", "host_math.h", os.path.join("..", "..", "include", "asc.h")]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False, dof_list=None):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3", "-shared", "-o", LIB]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    if dof_list:
+        cmd += ["-DASC_DOF_LIST(X)=" + " ".join("X(%d)" % n for n in dof_list)]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    dofs = [int(a) for a in sys.argv[1:] if a.isdigit()]
+    build(force=True, verbose="-v" in sys.argv, dof_list=dofs or None)
+    print(LIB)

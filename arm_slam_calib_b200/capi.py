@@ -1,0 +1,295 @@
+"""ctypes binding of include/asc.h plus a small host-side mirror of the reference's optimiser surface.
+
+`BatchOptimizer` plays the role of gtsam::LevenbergMarquardtOptimizer / gtsam::DoglegOptimizer as
+ArmSlamCalib::OptimizeStep uses them (src/ArmSlamCalib.cpp:438-467): construct over (graph, values),
+call optimize(), read error().  The graph is the flattened `Problem`.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _ctypes_defs as D
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libasc_b200.so")
+_lib = None
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); also the list tests/test_abi.py checks against include/asc.h
+SIGNATURES = {
+    "asc_default_params": (None, [C.POINTER(D.AscParams)]),
+    "asc_last_error": (C.c_char_p, []),
+    "asc_version": (C.c_char_p, []),
+    "asc_create": (C.c_int, [C.POINTER(D.AscParams), C.POINTER(_vp)]),
+    "asc_destroy": (C.c_int, [_vp]),
+    "asc_set_chain": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "asc_set_camera": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "asc_set_problem": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "asc_set_values": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "asc_get_values": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "asc_error": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "asc_linearize": (C.c_int, [_vp, C.POINTER(D.AscLinearStats)]),
+    "asc_optimize": (C.c_int, [_vp, C.c_int32, C.POINTER(D.AscIterLog), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    "asc_indeterminate_key": (C.c_int, [_vp, C.POINTER(C.c_char), C.POINTER(C.c_int64)]),
+    "asc_get_projection_blocks": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "asc_get_landmark_blocks": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "asc_get_pose_blocks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "asc_solve_damped": (C.c_int, [_vp, C.c_double, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
+    "asc_comm_id_size": (C.c_int, []),
+    "asc_comm_create_id": (C.c_int, [_vp]),
+    "asc_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp]),
+    "asc_shard_by_landmark": (C.c_int, [C.c_int32, C.c_int64, _vp, C.c_int32, _vp]),
+    "asc_sim_default_config": (None, [C.POINTER(D.AscSimConfig)]),
+    "asc_chain_mico": (C.c_int, [_vp, _vp, _vp]),
+    "asc_chain_generate": (C.c_int, [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "asc_sim_create": (C.c_int, [C.POINTER(D.AscSimConfig), C.c_int32, _vp, _vp, _vp, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, C.POINTER(_vp)]),
+    "asc_sim_destroy": (None, [_vp]),
+    "asc_sim_sizes": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "asc_sim_export": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "asc_chain_fk": (C.c_int, [C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "asc_srand": (None, [C.c_uint]),
+}
+
+
+def lib():
+    """Loads libasc_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError("libasc_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+class AscError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("asc status %d: %s" % (code, msg))
+        self.code = code
+
+
+class IndeterminantLinearSystemException(AscError):
+    """Same name and role as gtsam::IndeterminantLinearSystemException (ArmSlamCalib.cpp:451-455)."""
+
+    def __init__(self, code, msg, kind, index):
+        super().__init__(code, msg)
+        self.kind, self.index = kind, index
+
+    def nearbyVariable(self):
+        return (self.kind, self.index)
+
+
+def default_params():
+    p = D.AscParams()
+    lib().asc_default_params(C.byref(p))
+    return p
+
+
+def optimization_mode_from_string(name, previous=D.ASC_BATCH_DOGLEG):
+    """ArmSlamCalib::Params::InitializeNodehandleParams, src/ArmSlamCalib.cpp:408-422: the code reads
+    "BatchDogLeg" while the README says BatchDogleg; unknown strings silently keep the previous mode.
+    ISAM is out of scope for this library and is reported as such."""
+    if name == "BatchLM":
+        return D.ASC_BATCH_LM
+    if name in ("BatchDogLeg", "BatchDogleg"):
+        return D.ASC_BATCH_DOGLEG
+    if name == "ISAM":
+        raise NotImplementedError("optimization_mode=ISAM is outside the batch path this library accelerates")
+    return previous
+
+
+@dataclass
+class Problem:
+    """The factor graph of ArmSlamCalib (graph + chain + calibration), flattened (include/asc.h)."""
+    n_dof: int
+    t_p2j: np.ndarray
+    axis: np.ndarray
+    t_c2j: np.ndarray
+    fx: float
+    fy: float
+    cx: float
+    cy: float
+    pose_idx: np.ndarray
+    lm_idx: np.ndarray
+    uv: np.ndarray
+    enc: np.ndarray
+    lm_prior: np.ndarray
+    x_prior: np.ndarray
+    continuous: np.ndarray = None
+    has_enc: np.ndarray = None
+    t_base: np.ndarray = None
+    # initial estimate (Values)
+    q0: np.ndarray = None
+    l0: np.ndarray = None
+    x0: np.ndarray = None
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_poses(self):
+        return self.enc.shape[0]
+
+    @property
+    def n_landmarks(self):
+        return self.lm_prior.shape[0]
+
+    @property
+    def n_obs(self):
+        return self.pose_idx.shape[0]
+
+
+def shard_by_landmark(n_landmarks, lm_idx, world_size):
+    out = np.zeros(world_size + 1, dtype=np.int32)
+    lm_idx = np.ascontiguousarray(lm_idx, dtype=np.int32)
+    rc = lib().asc_shard_by_landmark(n_landmarks, lm_idx.shape[0], _ptr(lm_idx), world_size, _ptr(out))
+    if rc:
+        raise AscError(rc, lib().asc_last_error().decode())
+    return out
+
+
+def shard_problem(pb, rank, world_size):
+    """Rank's shard: its landmark range and all their observations; poses/encoders replicated."""
+    bounds = shard_by_landmark(pb.n_landmarks, pb.lm_idx, world_size)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    sel = (pb.lm_idx >= lo) & (pb.lm_idx < hi)
+    import dataclasses
+    return dataclasses.replace(
+        pb, pose_idx=np.ascontiguousarray(pb.pose_idx[sel]), lm_idx=np.ascontiguousarray(pb.lm_idx[sel] - lo),
+        uv=np.ascontiguousarray(pb.uv[sel]), lm_prior=np.ascontiguousarray(pb.lm_prior[lo:hi]),
+        l0=None if pb.l0 is None else np.ascontiguousarray(pb.l0[lo:hi]), meta=dict(pb.meta, lm_range=(lo, hi), obs_sel=sel))
+
+
+class BatchOptimizer:
+    """Device-resident optimiser over one Problem.  Mirrors the GTSAM optimiser objects the reference
+    constructs in OptimizeStep: BatchOptimizer(problem, params).optimize(mode) / .error()."""
+
+    def __init__(self, problem, params=None, comm=None):
+        self.L = lib()
+        self.pb = problem
+        self.params = params if params is not None else default_params()
+        self.h = _vp()
+        self._check(self.L.asc_create(C.byref(self.params), C.byref(self.h)))
+        pb = problem
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        self._keep = dict(t_p2j=f64(pb.t_p2j), axis=f64(pb.axis), t_c2j=f64(pb.t_c2j), t_base=f64(pb.t_base),
+                          cont=None if pb.continuous is None else np.ascontiguousarray(pb.continuous, dtype=np.uint8))
+        k = self._keep
+        self._check(self.L.asc_set_chain(self.h, pb.n_dof, _ptr(k["t_p2j"]), _ptr(k["axis"]), _ptr(k["t_c2j"]), _ptr(k["cont"]), _ptr(k["t_base"])))
+        self._check(self.L.asc_set_camera(self.h, pb.fx, pb.fy, pb.cx, pb.cy))
+        if comm is not None:
+            rank, world, id_bytes = comm
+            buf = np.frombuffer(bytes(id_bytes), dtype=np.uint8).copy()
+            self._check(self.L.asc_comm_init(self.h, rank, world, _ptr(buf)))
+        self.set_problem(pb)
+        if pb.q0 is not None:
+            self.set_values(pb.q0, pb.l0, pb.x0)
+        self.log = []
+        self._error = None
+
+    def _check(self, rc):
+        if rc == D.ASC_OK:
+            return
+        msg = self.L.asc_last_error().decode()
+        if rc == D.ASC_ERR_INDETERMINATE:
+            kind, idx = C.c_char(), C.c_int64()
+            self.L.asc_indeterminate_key(self.h, C.byref(kind), C.byref(idx))
+            raise IndeterminantLinearSystemException(rc, msg, kind.value.decode() if kind.value else "?", idx.value)
+        raise AscError(rc, msg)
+
+    def set_problem(self, pb):
+        pi = np.ascontiguousarray(pb.pose_idx, dtype=np.int32)
+        li = np.ascontiguousarray(pb.lm_idx, dtype=np.int32)
+        uv = np.ascontiguousarray(pb.uv, dtype=np.float64)
+        enc = np.ascontiguousarray(pb.enc, dtype=np.float64)
+        he = None if pb.has_enc is None else np.ascontiguousarray(pb.has_enc, dtype=np.uint8)
+        lp = np.ascontiguousarray(pb.lm_prior, dtype=np.float64)
+        xp = np.ascontiguousarray(pb.x_prior, dtype=np.float64)
+        self._check(self.L.asc_set_problem(self.h, enc.shape[0], lp.shape[0], pi.shape[0], _ptr(pi), _ptr(li), _ptr(uv), _ptr(enc), _ptr(he), _ptr(lp), _ptr(xp)))
+        self.P, self.Lm, self.M, self.N = enc.shape[0], lp.shape[0], pi.shape[0], pb.n_dof
+
+    def set_values(self, q, l, x):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        l = np.ascontiguousarray(l, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self._check(self.L.asc_set_values(self.h, _ptr(q), _ptr(l), _ptr(x)))
+
+    def values(self):
+        q = np.empty((self.P, self.N)); l = np.empty((self.Lm, 3)); x = np.empty(12)
+        self._check(self.L.asc_get_values(self.h, _ptr(q), _ptr(l), _ptr(x)))
+        return q, l, x
+
+    def graph_error(self):
+        e = C.c_double()
+        self._check(self.L.asc_error(self.h, C.byref(e)))
+        return e.value
+
+    def linearize(self):
+        st = D.AscLinearStats()
+        self._check(self.L.asc_linearize(self.h, C.byref(st)))
+        return st
+
+    def projection_blocks(self):
+        b = np.empty((self.M, 2)); jq = np.empty((self.M, 2, self.N)); jl = np.empty((self.M, 2, 3))
+        self._check(self.L.asc_get_projection_blocks(self.h, _ptr(b), _ptr(jq), _ptr(jl)))
+        return b, jq, jl
+
+    def landmark_blocks(self):
+        c = np.empty((self.Lm, 3, 3)); gl = np.empty((self.Lm, 3)); wk = np.empty((self.Lm, 6, 3))
+        self._check(self.L.asc_get_landmark_blocks(self.h, _ptr(c), _ptr(gl), _ptr(wk)))
+        return c, gl, wk
+
+    def pose_blocks(self):
+        bpp = np.empty((self.P, self.N, self.N)); bpk = np.empty((self.P, self.N, 6)); gp = np.empty((self.P, self.N))
+        bkk = np.empty((6, 6)); gk = np.empty(6)
+        self._check(self.L.asc_get_pose_blocks(self.h, _ptr(bpp), _ptr(bpk), _ptr(gp), _ptr(bkk), _ptr(gk)))
+        return bpp, bpk, gp, bkk, gk
+
+    def solve_damped(self, lam):
+        dq = np.empty((self.P, self.N)); dl = np.empty((self.Lm, 3)); dx = np.empty(6)
+        its = C.c_int32()
+        self._check(self.L.asc_solve_damped(self.h, float(lam), _ptr(dq), _ptr(dl), _ptr(dx), C.byref(its)))
+        return dq, dl, dx, its.value
+
+    def optimize(self, mode=D.ASC_BATCH_LM):
+        cap = max(1, int(self.params.max_iterations))
+        log = (D.AscIterLog * cap)()
+        n = C.c_int32()
+        err = C.c_double()
+        rc = self.L.asc_optimize(self.h, mode, log, cap, C.byref(n), C.byref(err))
+        self.log = [log[i] for i in range(min(n.value, cap))]
+        self._error = err.value
+        self._check(rc)
+        return self.values()
+
+    def error(self):
+        return self._error if self._error is not None else self.graph_error()
+
+    def iterations(self):
+        return len(self.log)
+
+    def close(self):
+        if self.h:
+            self.L.asc_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

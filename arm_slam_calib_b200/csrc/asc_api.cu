@@ -1,0 +1,1033 @@
+// Host side of the B200 batch optimiser: the C ABI of include/asc.h, problem packing, the
+// LM / Dogleg controllers and the kernel launch sequences.
+// There is no CPU fallback in this file: every compute entry point needs an sm_100 device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only; the library is dlopen()ed when a communicator is requested
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/asc.h"
+#include "host_math.h"
+#include "kernels.cuh"
+
+using namespace asck;
+
+// DOFs with compiled kernels.  data/dof_experiments.py sweeps 4..19; BASELINE configs use 6..12.
+#ifndef ASC_DOF_LIST
+#define ASC_DOF_LIST(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+#endif
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) return fail(ASC_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- NCCL through dlopen: no link-time dependency, and the already-loaded libnccl (torch's) is reused
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+    if (g_nccl.lib) return ASC_OK;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(ASC_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(ASC_ERR_COMM, "libnccl is missing required symbols");
+    g_nccl.lib = lib;
+    return ASC_OK;
+}
+
+int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+struct asc_handle {
+    asc_params prm;
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int N = 0, P = 0, L = 0;
+    int64_t M = 0;
+    bool chain_set = false, cam_set = false, problem_set = false, values_set = false, linearized = false;
+    double lin_lambda = -1.0;   // lambda the current Cinv/Minv were prepared for (<0: none)
+    // host copies
+    std::vector<double> t_p2j, axis, t_c2j, t_base;
+    std::vector<uint8_t> continuous;
+    Camera cm{};
+    PriorConst pc{};
+    std::vector<int32_t> h_p_orig;
+    // multi-GPU
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    // failure report
+    char fail_kind = 0;
+    int64_t fail_index = -1;
+    // device memory
+    std::vector<void*> allocs;
+    int *pose_ptr = nullptr, *p_lm = nullptr, *p_pose = nullptr, *p_orig = nullptr;
+    int *lm_ptr = nullptr, *l_pose = nullptr, *l_perm = nullptr;
+    double2 *p_uv = nullptr, *l_uv = nullptr, *J = nullptr, *b_dbg = nullptr;
+    double *enc = nullptr, *lm_prior = nullptr;
+    uint8_t* has_enc = nullptr;
+    double *q = nullptr, *lm4 = nullptr, *X = nullptr, *q_try = nullptr, *lm4_try = nullptr, *X_try = nullptr;
+    double *cam = nullptr, *chain = nullptr;
+    double *poseblk = nullptr;   // [Bpp | BpK | BKK(36) | gp | gK(6) | err | pad]   (one all-reduce)
+    double *Bpp = nullptr, *BpK = nullptr, *BKK = nullptr, *gr = nullptr, *err_lin = nullptr;
+    double *C = nullptr, *gl = nullptr, *WK = nullptr, *Cinv = nullptr, *cg4 = nullptr, *u4 = nullptr, *v4 = nullptr, *dl4 = nullptr, *gl4 = nullptr;
+    double *precblk = nullptr;   // [Dloc | rloc | krow(32)]
+    double *Dloc = nullptr, *rloc = nullptr, *krow = nullptr;
+    double *Minv = nullptr, *MinvK = nullptr, *rhs = nullptr;
+    double *vx = nullptr, *vr = nullptr, *vz = nullptr, *vp = nullptr;
+    double *ybuf = nullptr;      // [y (PN) | yK(6) pad to 8 | rowC(32) | rowB(32)]
+    double *partA = nullptr, *partB = nullptr, *partC = nullptr, *partL = nullptr, *errblk = nullptr;
+    int nCtaPose = 0, nBlkLm = 0, nErrBlk = 0;
+    double *scal = nullptr, *status = nullptr;
+    int *flags = nullptr;        // [0] pcg done, [1] landmark fail idx, [2] pose fail idx, [3] K fail
+    unsigned long long* cheir = nullptr;
+    double* h_status = nullptr;  // pinned: status(32) + scal(8)
+    int* h_flags = nullptr;      // pinned
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(asc_handle* h, T** out, size_t count) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    CUDA_TRY(cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), h->stream));
+    h->allocs.push_back(p);
+    *out = (T*)p;
+    return ASC_OK;
+}
+
+void free_device(asc_handle* h) {
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+}
+
+int allreduce(asc_handle* h, double* buf, size_t count) {
+    if (h->world <= 1) return ASC_OK;
+    ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(ASC_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    return ASC_OK;
+}
+
+template <int N>
+ChainConst<N> make_chain_const(const asc_handle* h) {
+    ChainConst<N> cc;
+    asc::Xf base = asc::xf_from12(h->t_base.data());
+    asc::Xf f0 = asc::xf_mul(base, asc::xf_from12(&h->t_p2j[0]));
+    asc::xf_to12(f0, cc.F0);
+    for (int i = 0; i < N; ++i) {
+        asc::Xf li = asc::xf_inv(asc::xf_from12(&h->t_c2j[12 * i]));
+        if (i + 1 < N) li = asc::xf_mul(li, asc::xf_from12(&h->t_p2j[12 * (i + 1)]));
+        asc::xf_to12(li, cc.Lk[i]);
+        for (int k = 0; k < 3; ++k) cc.axis[i][k] = h->axis[3 * i + k];
+    }
+    return cc;
+}
+
+// ------------------------------------------------------------------ launch sequences (templated on DOF)
+template <int N>
+struct Engine {
+    static int fk(asc_handle* h, const double* q, const double* X, bool with_chain) {
+        const ChainConst<N> cc = make_chain_const<N>(h);
+        const int grid = cdiv(h->P, 128);
+        if (with_chain) fk_kernel<N, true><<<grid, 128, 0, h->stream>>>(cc, q, X, h->P, h->cam, h->chain);
+        else fk_kernel<N, false><<<grid, 128, 0, h->stream>>>(cc, q, X, h->P, h->cam, h->chain);
+        CUDA_TRY(cudaGetLastError());
+        return ASC_OK;
+    }
+
+    static int setup_attrs() {
+        static bool done = false;
+        if (done) return ASC_OK;
+        CUDA_TRY(cudaFuncSetAttribute(linearize_pose_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<N>::kBytes));
+        CUDA_TRY(cudaFuncSetAttribute(linearize_pose_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<N>::kBytes));
+        CUDA_TRY(cudaFuncSetAttribute(pose_schur_diag_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PrecSmem<N>::kBytes));
+        done = true;
+        return ASC_OK;
+    }
+
+    // FK + K1/K2b + K2a + finish.  Leaves the undamped blocks and the error on the device.
+    static int linearize(asc_handle* h, bool store_b, float* ms_lin, float* ms_asm) {
+        int rc = setup_attrs();
+        if (rc) return rc;
+        const int add_priors = h->rank == 0 ? 1 : 0;
+        CUDA_TRY(cudaMemsetAsync(h->cheir, 0, sizeof(unsigned long long), h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+        rc = fk(h, h->q, h->X, true);
+        if (rc) return rc;
+        if (store_b)
+            linearize_pose_kernel<N, true><<<h->nCtaPose, kCtaThreads, LinSmem<N>::kBytes, h->stream>>>(
+                h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
+                h->J, h->Bpp, h->BpK, h->gr, h->partA, h->b_dbg, h->cheir);
+        else
+            linearize_pose_kernel<N, false><<<h->nCtaPose, kCtaThreads, LinSmem<N>::kBytes, h->stream>>>(
+                h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
+                h->J, h->Bpp, h->BpK, h->gr, h->partA, nullptr, h->cheir);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+        landmark_blocks_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->cm, h->L, h->lm_ptr, h->l_pose, h->l_uv, h->cam, h->lm4, h->lm_prior, h->C,
+                                                                h->gl, h->WK, h->errblk);
+        CUDA_TRY(cudaGetLastError());
+        linearize_finish_kernel<<<1, 256, 0, h->stream>>>(h->pc, add_priors, h->X, h->partA, h->nCtaPose, h->errblk, h->nBlkLm, h->BKK,
+                                                         h->gr + (size_t)h->P * N, h->err_lin);
+        CUDA_TRY(cudaGetLastError());
+        if (h->world > 1) {
+            const size_t count = (size_t)h->P * (N * N + 6 * N) + 36 + (size_t)h->P * N + 6 + 1;
+            rc = allreduce(h, h->poseblk, count);
+            if (rc) return rc;
+        }
+        pad3to4_kernel<<<cdiv((int64_t)h->L * 4, 256), 256, 0, h->stream>>>(h->L, h->gl, h->gl4);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+        h->linearized = true;
+        h->lin_lambda = -1.0;
+        if (ms_lin || ms_asm) {
+            CUDA_TRY(cudaEventSynchronize(h->ev[2]));
+            if (ms_lin) CUDA_TRY(cudaEventElapsedTime(ms_lin, h->ev[0], h->ev[1]));
+            if (ms_asm) CUDA_TRY(cudaEventElapsedTime(ms_asm, h->ev[1], h->ev[2]));
+        }
+        return ASC_OK;
+    }
+
+    // damped landmark inverses, Schur-diagonal preconditioner, reduced right-hand side
+    static int prepare(asc_handle* h, double lambda) {
+        const int big = 0x7fffffff;
+        int init_flags[4] = {0, big, big, big};
+        CUDA_TRY(cudaMemcpyAsync(h->flags, init_flags, sizeof init_flags, cudaMemcpyHostToDevice, h->stream));
+        landmark_invert_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->L, lambda, h->C, h->gl, h->WK, h->Cinv, h->cg4, h->partL, h->flags + 1);
+        CUDA_TRY(cudaGetLastError());
+        pose_schur_diag_kernel<N><<<h->nCtaPose, kCtaThreads, PrecSmem<N>::kBytes, h->stream>>>(h->P, h->M, h->pose_ptr, h->p_lm, h->J, h->Cinv, h->cg4,
+                                                                                              h->Dloc, h->rloc);
+        CUDA_TRY(cudaGetLastError());
+        const double* kpart = h->partL;
+        int nk = h->nBlkLm;
+        if (h->world > 1) {
+            reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partL, h->nBlkLm, 27, kPartCols, h->nBlkLm, h->krow);
+            CUDA_TRY(cudaGetLastError());
+            int rc = allreduce(h, h->precblk, (size_t)h->P * (N * N + N) + kPartCols);
+            if (rc) return rc;
+            kpart = h->krow;
+            nk = 1;
+        }
+        k_rows_kernel<<<1, 256, 0, h->stream>>>(lambda, kpart, nk, h->BKK, h->gr + (size_t)h->P * N, h->MinvK, h->rhs + (size_t)h->P * N, h->flags + 3);
+        CUDA_TRY(cudaGetLastError());
+        pose_invert_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, lambda, h->Bpp, h->gr, h->Dloc, h->rloc, h->Minv, h->rhs, h->flags + 2);
+        CUDA_TRY(cudaGetLastError());
+        h->lin_lambda = lambda;
+        return ASC_OK;
+    }
+
+    // one application y = S x written into ybuf; K rows handled by the caller's kernels
+    static int schur_apply_launch(asc_handle* h, double lambda, bool update_p, double* x, const int* done) {
+        if (update_p)
+            schur_pass_a_kernel<N, true><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4);
+        else
+            schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4);
+        CUDA_TRY(cudaGetLastError());
+        schur_pass_b_kernel<false><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->l_perm, h->v4, h->WK, h->Cinv, x + (size_t)h->P * N, done,
+                                                                    nullptr, h->u4, h->partB);
+        CUDA_TRY(cudaGetLastError());
+        schur_pass_c_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, h->rank == 0 ? 1 : 0, h->pose_ptr, h->p_lm, h->J, h->u4, x,
+                                                                         h->Bpp, h->BpK, done, h->ybuf, h->partC);
+        CUDA_TRY(cudaGetLastError());
+        return ASC_OK;
+    }
+
+    // block-Jacobi PCG on the reduced system; solution left in vx.  Returns iterations through *iters.
+    static int pcg(asc_handle* h, double lambda, int* iters) {
+        const size_t PN = (size_t)h->P * N;
+        pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
+        CUDA_TRY(cudaGetLastError());
+        pcg_init_end_kernel<<<1, 256, 0, h->stream>>>(h->partA, h->nCtaPose, h->scal, h->flags);
+        CUDA_TRY(cudaGetLastError());
+        const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
+        const int chunk = 8;
+        int launched = 0;
+        for (;;) {
+            for (int c = 0; c < chunk; ++c) {
+                int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags);
+                if (rc) return rc;
+                const double* pc_ = h->partC;
+                const double* pb_ = h->partB;
+                int nC = h->nCtaPose, nB = h->nBlkLm;
+                if (h->world > 1) {
+                    double* rowC = h->ybuf + PN + 8;
+                    double* rowB = rowC + kPartCols;
+                    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPartCols, h->nCtaPose, rowC);
+                    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partB, h->nBlkLm, 6, kPartCols, h->nBlkLm, rowB);
+                    CUDA_TRY(cudaGetLastError());
+                    rc = allreduce(h, h->ybuf, PN + 8 + 2 * kPartCols);
+                    if (rc) return rc;
+                    pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
+                }
+                pcg_mid_kernel<<<1, 256, 0, h->stream>>>(h->P, N, lambda, pc_, nC, pb_, nB, h->BKK, h->MinvK, h->vp, h->vx, h->vr, h->vz,
+                                                        h->ybuf + PN, h->scal, h->flags);
+                CUDA_TRY(cudaGetLastError());
+                pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
+                CUDA_TRY(cudaGetLastError());
+                pcg_end_kernel<<<1, 256, 0, h->stream>>>(h->P, N, h->partA, h->nCtaPose, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags);
+                CUDA_TRY(cudaGetLastError());
+            }
+            launched += chunk;
+            CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(h->h_status + 32, h->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            if (h->h_flags[0] || launched >= h->prm.pcg_max_iters + chunk) break;
+        }
+        if (iters) *iters = (int)h->h_status[32 + 5];
+        return ASC_OK;
+    }
+
+    // delta_l = Cinv (g_l - W^T delta_r) -> dl4
+    static int backsub(asc_handle* h) {
+        schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, h->vx, nullptr, nullptr, nullptr, h->v4);
+        CUDA_TRY(cudaGetLastError());
+        schur_pass_b_kernel<true><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->l_perm, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
+                                                                   h->cg4, h->dl4, nullptr);
+        CUDA_TRY(cudaGetLastError());
+        return ASC_OK;
+    }
+
+    // full damped solve: prepare + PCG + back-substitution.  rc ASC_ERR_INDETERMINATE on breakdown.
+    static int solve(asc_handle* h, double lambda, int* iters) {
+        int rc = prepare(h, lambda);
+        if (rc) return rc;
+        rc = pcg(h, lambda, iters);
+        if (rc) return rc;
+        const int big = 0x7fffffff;
+        if (h->h_flags[1] != big) { h->fail_kind = 'l'; h->fail_index = h->h_flags[1]; return fail(ASC_ERR_INDETERMINATE, "landmark block %d is not positive definite", h->h_flags[1]); }
+        if (h->h_flags[2] != big) { h->fail_kind = 'q'; h->fail_index = h->h_flags[2]; return fail(ASC_ERR_INDETERMINATE, "pose block %d is not positive definite", h->h_flags[2]); }
+        if (h->h_flags[3] != big) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "extrinsic block is not positive definite"); }
+        if (h->h_status[32 + 6] != 0.0) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "PCG breakdown: p^T S p <= 0"); }
+        return backsub(h);
+    }
+
+    // graph.error(values) at (q, lm4, X); synchronises and returns the value
+    static int error(asc_handle* h, const double* q, const double* lm4, const double* X, double* out) {
+        int rc = fk(h, q, X, false);
+        if (rc) return rc;
+        const int nb1 = cdiv(h->M, 256), nb2 = cdiv((int64_t)h->P + h->L, 256);
+        if (nb1) error_proj_kernel<<<nb1, 256, 0, h->stream>>>(h->cm, h->M, h->p_pose, h->p_lm, h->p_uv, h->cam, lm4, h->errblk);
+        CUDA_TRY(cudaGetLastError());
+        error_prior_kernel<<<nb2, 256, 0, h->stream>>>(h->cm, h->pc, N, h->P, h->L, h->rank == 0 ? 1 : 0, q, h->enc, h->has_enc, lm4, h->lm_prior, h->errblk + nb1);
+        CUDA_TRY(cudaGetLastError());
+        error_finish_kernel<<<1, 256, 0, h->stream>>>(h->pc, h->rank == 0 ? 1 : 0, X, h->errblk, nb1 + nb2, h->status + 4);
+        CUDA_TRY(cudaGetLastError());
+        if (h->world > 1) { rc = allreduce(h, h->status + 4, 1); if (rc) return rc; }
+        CUDA_TRY(cudaMemcpyAsync(h->h_status + 4, h->status + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        *out = h->h_status[4];
+        // the FK table now belongs to the trial values; a following linearise recomputes it
+        return ASC_OK;
+    }
+
+    static int unpack(asc_handle* h, double* d_b, double* d_jq, double* d_jl) {
+        unpack_blocks_kernel<N><<<cdiv(h->M, 256), 256, 0, h->stream>>>(h->M, h->p_orig, h->J, h->b_dbg, d_b, d_jq, d_jl);
+        CUDA_TRY(cudaGetLastError());
+        return ASC_OK;
+    }
+};
+
+int dispatch_linearize(asc_handle* h, bool store_b, float* a, float* b) {
+#define X(n) case n: return Engine<n>::linearize(h, store_b, a, b);
+    switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
+#undef X
+}
+int dispatch_solve(asc_handle* h, double lambda, int* iters) {
+#define X(n) case n: return Engine<n>::solve(h, lambda, iters);
+    switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
+#undef X
+}
+int dispatch_error(asc_handle* h, const double* q, const double* lm4, const double* X_, double* out) {
+#define X(n) case n: return Engine<n>::error(h, q, lm4, X_, out);
+    switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
+#undef X
+}
+int dispatch_unpack(asc_handle* h, double* b, double* jq, double* jl) {
+#define X(n) case n: return Engine<n>::unpack(h, b, jq, jl);
+    switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
+#undef X
+}
+int dispatch_schur_c(asc_handle* h, double lambda, double* x, double* u4_in) {
+    // pass C only, with a caller-provided landmark vector (Dogleg cross term)
+#define X(n)                                                                                                                      \
+    case n:                                                                                                                       \
+        schur_pass_c_kernel<n><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, 0, h->pose_ptr, h->p_lm, h->J, u4_in, x, \
+                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC);             \
+        break;
+    switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
+#undef X
+    CUDA_TRY(cudaGetLastError());
+    return ASC_OK;
+}
+bool dof_supported(int n) {
+#define X(k) if (n == k) return true;
+    ASC_DOF_LIST(X)
+#undef X
+    return false;
+}
+
+// ---- step scalars: [x.g_r, x.x, dl.gl, dl.dl] over the reduced vector and the landmark vector
+__global__ void __launch_bounds__(256)
+step_dots_kernel(int64_t nr, const double* __restrict__ x, const double* __restrict__ g, int L, const double* __restrict__ dl4,
+                 const double* __restrict__ gl4, double* __restrict__ blk) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v[4] = {0, 0, 0, 0};
+    if (i < nr) { v[0] = x[i] * g[i]; v[1] = x[i] * x[i]; }
+    if (i < (int64_t)L * 4) { v[2] = dl4[i] * gl4[i]; v[3] = dl4[i] * dl4[i]; }
+    __shared__ double s[8][4];
+    for (int c = 0; c < 4; ++c) {
+        const double t = warp_sum(v[c]);
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5][c] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPartCols) {
+        double t = 0.0;
+        if (threadIdx.x < 4)
+            for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
+        blk[(size_t)blockIdx.x * kPartCols + threadIdx.x] = t;
+    }
+}
+
+// per keyframe g_p^T B_pp g_p + 2 g_p^T B_pK g_K   (Dogleg, |A g|^2)
+__global__ void __launch_bounds__(256)
+dogleg_pose_quad_kernel(int P, int N, const double* __restrict__ Bpp, const double* __restrict__ BpK, const double* __restrict__ g, double* __restrict__ blk) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (p < P) {
+        const double* gp = g + (size_t)p * N;
+        const double* gK = g + (size_t)P * N;
+        for (int r = 0; r < N; ++r) {
+            double t = 0.0;
+            for (int c = 0; c < N; ++c) t += Bpp[(size_t)p * N * N + r * N + c] * gp[c];
+            double k = 0.0;
+            for (int c = 0; c < 6; ++c) k += BpK[(size_t)p * N * 6 + r * 6 + c] * gK[c];
+            v += gp[r] * (t + 2.0 * k);
+        }
+    }
+    __shared__ double s[8];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) blk[blockIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+int step_dots(asc_handle* h, const double* x, const double* dl4, double* out4_host) {
+    const int64_t nr = (int64_t)h->P * h->N + 6;
+    const int64_t n = std::max<int64_t>(nr, (int64_t)h->L * 4);
+    const int nb = cdiv(n, 256);
+    step_dots_kernel<<<nb, 256, 0, h->stream>>>(nr, x, h->gr, h->L, dl4, h->gl4, h->partA);
+    CUDA_TRY(cudaGetLastError());
+    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partA, nb, 4, kPartCols, nb, h->status + 8);
+    CUDA_TRY(cudaGetLastError());
+    // multi-GPU: the reduced-vector parts are replicated, the landmark parts are sharded
+    if (h->world > 1) { int rc = allreduce(h, h->status + 10, 2); if (rc) return rc; }
+    CUDA_TRY(cudaMemcpyAsync(h->h_status + 8, h->status + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 4; ++i) out4_host[i] = h->h_status[8 + i];
+    return ASC_OK;
+}
+
+int retract_to_try(asc_handle* h, double cn, double cu) {
+    const int64_t nq = (int64_t)h->P * h->N;
+    const int64_t n = std::max<int64_t>(nq, (int64_t)h->L * 4);
+    const bool with_u = cu != 0.0;
+    retract_kernel<<<cdiv(std::max<int64_t>(n, 1), 256), 256, 0, h->stream>>>(h->prm.pose3_chart, nq, h->L, h->q, h->lm4, h->X, cn, h->vx, h->dl4,
+                                                                             h->vx + nq, cu, with_u ? h->gr : nullptr, with_u ? h->gl : nullptr,
+                                                                             with_u ? h->gr + nq : nullptr, h->q_try, h->lm4_try, h->X_try);
+    CUDA_TRY(cudaGetLastError());
+    return ASC_OK;
+}
+
+void accept_try(asc_handle* h) {
+    std::swap(h->q, h->q_try);
+    std::swap(h->lm4, h->lm4_try);
+    std::swap(h->X, h->X_try);
+    h->linearized = false;
+}
+
+bool converged(const asc_params& p, double e0, double e1) {
+    if (e1 <= p.error_tol) return true;
+    const double abs_dec = e0 - e1, rel_dec = abs_dec / e0;
+    return (p.relative_error_tol != 0 && rel_dec <= p.relative_error_tol) || abs_dec <= p.absolute_error_tol;
+}
+
+// [DEP] LevenbergMarquardtOptimizer::iterate
+int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
+    const asc_params& p = h->prm;
+    float ms = 0;
+    int rc = dispatch_linearize(h, false, nullptr, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+    for (;;) {
+        int its = 0;
+        rc = dispatch_solve(h, *lambda, &its);
+        lg->inner_steps++;
+        lg->pcg_iterations += its;
+        if (rc != ASC_OK && rc != ASC_ERR_INDETERMINATE) return rc;
+        const bool solved = rc == ASC_OK;
+        bool ok = false, stop = false;
+        double new_error = 0.0;
+        if (solved) {
+            double d[4];
+            rc = step_dots(h, h->vx, h->dl4, d);
+            if (rc) return rc;
+            // linear.error(0) - linear.error(delta) for an exact damped solve: 0.5 d.g + 0.5 lambda |d|^2
+            const double lin_dec = 0.5 * (d[0] + d[2]) + 0.5 * *lambda * (d[1] + d[3]);
+            if (lin_dec >= 0) {
+                rc = retract_to_try(h, 1.0, 0.0);
+                if (rc) return rc;
+                rc = dispatch_error(h, h->q_try, h->lm4_try, h->X_try, &new_error);
+                if (rc) return rc;
+                const double cost_dec = *error - new_error;
+                ok = lin_dec > 1e-15 ? (cost_dec / lin_dec) > p.min_model_fidelity : true;
+                if (std::fabs(cost_dec) < p.relative_error_tol * *error) stop = true;
+            }
+        }
+        if (ok) {
+            accept_try(h);
+            *error = new_error;
+            *lambda = std::max(*lambda / p.lambda_factor, p.lambda_lower_bound);
+            lg->accepted = 1;
+            break;
+        } else if (!stop) {
+            *lambda *= p.lambda_factor;
+            if (*lambda >= p.lambda_upper_bound) break;
+        } else break;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+    CUDA_TRY(cudaEventSynchronize(h->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]));
+    lg->linearize_ms = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[3], h->ev[2]));
+    lg->solve_ms = ms;
+    return ASC_OK;
+}
+
+// |A g|^2 from the assembled blocks and the stored Jacobian planes (K5)
+int dogleg_gHg(asc_handle* h, double* out) {
+    const int N = h->N;
+    const size_t PN = (size_t)h->P * N;
+    int rc = dispatch_schur_c(h, 0.0, h->gr, h->gl4);   // yloc = -W g_l ; partC col 6 = sum g_p . yloc_p
+    if (rc) return rc;
+    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPartCols, h->nCtaPose, h->status + 16);   // [16+6] = T1
+    const int nbp = cdiv(h->P, 256), nbl = cdiv(h->L, 256);
+    dogleg_pose_quad_kernel<<<nbp, 256, 0, h->stream>>>(h->P, N, h->Bpp, h->BpK, h->gr, h->errblk);
+    dogleg_landmark_quad_kernel<<<std::max(nbl, 1), 256, 0, h->stream>>>(h->L, h->C, h->gl, h->WK, h->gr + PN, h->errblk + nbp);
+    CUDA_TRY(cudaGetLastError());
+    sum_kernel<<<1, 256, 0, h->stream>>>(h->errblk, h->rank == 0 ? nbp : 0, h->status + 12);
+    sum_kernel<<<1, 256, 0, h->stream>>>(h->errblk + nbp, std::max(nbl, 1), h->status + 13);
+    CUDA_TRY(cudaGetLastError());
+    if (h->world > 1) {
+        // status[12] pose quad (rank 0 only), [13] landmark quad (sharded), [22] T1 (sharded)
+        rc = allreduce(h, h->status + 12, 2); if (rc) return rc;
+        rc = allreduce(h, h->status + 22, 1); if (rc) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->h_status + 12, h->status + 12, 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    double hb[36 + 6];
+    CUDA_TRY(cudaMemcpyAsync(hb, h->BKK, 36 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(hb + 36, h->gr + PN, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    double kk = 0.0;
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) kk += hb[36 + r] * hb[6 * r + c] * hb[36 + c];
+    *out = h->h_status[12] + h->h_status[13] + kk - 2.0 * h->h_status[22];
+    return ASC_OK;
+}
+
+// [DEP] DoglegOptimizer::iterate + DoglegOptimizerImpl::Iterate(ONE_STEP_PER_ITERATION)
+int dogleg_iterate(asc_handle* h, double* error, double* Delta, asc_iter_log* lg) {
+    float ms = 0;
+    int rc = dispatch_linearize(h, false, nullptr, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+    int its = 0;
+    rc = dispatch_solve(h, 0.0, &its);   // Gauss-Newton point in (vx, dl4)
+    lg->pcg_iterations += its;
+    if (rc) return rc;
+    double d[4], gg4[4], gHg = 0.0;
+    rc = step_dots(h, h->vx, h->dl4, d);           // n.g, n.n
+    if (rc) return rc;
+    rc = step_dots(h, h->gr, h->gl4, gg4);         // g.g
+    if (rc) return rc;
+    rc = dogleg_gHg(h, &gHg);
+    if (rc) return rc;
+    const double ng = d[0] + d[2], nn = d[1] + d[3], gg = gg4[0] + gg4[2];
+    const double step = gg / gHg;                  // steepest-descent point u = step * g
+    const double uu = step * step * gg, un = step * ng;
+    const double f0 = *error;
+    double f_new = f0, cu = 0.0, cn = 1.0;
+    bool stay = true;
+    while (stay) {
+        lg->inner_steps++;
+        const double D2 = *Delta * *Delta;
+        if (D2 < uu) { cu = std::sqrt(D2 / uu); cn = 0.0; }
+        else if (D2 < nn) {   // ComputeBlend
+            const double a = uu - 2. * un + nn, b = 2. * (un - uu), c = uu - D2, sq = std::sqrt(b * b - 4 * a * c);
+            const double tau1 = (-b + sq) / (2. * a), tau2 = (-b - sq) / (2. * a);
+            const double tau = (0.0 <= tau1 && tau1 <= 1.0) ? tau1 : tau2;
+            cu = 1. - tau; cn = tau;
+        } else { cu = 0.0; cn = 1.0; }
+        rc = retract_to_try(h, cn, cu * step);
+        if (rc) return rc;
+        rc = dispatch_error(h, h->q_try, h->lm4_try, h->X_try, &f_new);
+        if (rc) return rc;
+        // M(delta) = f0 - delta.g + 0.5 delta^T H delta with H n = g (undamped Gauss-Newton solve)
+        const double a = cu * step;   // delta = a g + cn n
+        const double dg = a * gg + cn * ng;
+        const double dHd = a * a * gHg + 2.0 * a * cn * gg + cn * cn * ng;   // g^T H n = g^T g, n^T H n = n^T g
+        const double M_new = f0 - dg + 0.5 * dHd;
+        const double rho = (std::fabs(f0 - f_new) < 1e-15 || std::fabs(f0 - M_new) < 1e-15) ? 0.5 : (f0 - f_new) / (f0 - M_new);
+        if (rho >= 0.75) {
+            const double dn = std::sqrt(cu * cu * uu + 2 * cu * cn * un + cn * cn * nn);
+            *Delta = std::max(*Delta, 3.0 * dn); stay = false;
+        } else if (rho >= 0.25) stay = false;
+        else if (rho >= 0.0) { if (*Delta > 1e-5) *Delta *= 0.5; stay = false; }
+        else { if (*Delta > 1e-5) { *Delta *= 0.5; stay = true; } else stay = false; }
+    }
+    accept_try(h);
+    *error = f_new;
+    lg->accepted = 1;
+    CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+    CUDA_TRY(cudaEventSynchronize(h->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]));
+    lg->linearize_ms = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[3], h->ev[2]));
+    lg->solve_ms = ms;
+    return ASC_OK;
+}
+
+int check_ready(asc_handle* h, bool need_values) {
+    if (!h) return fail(ASC_ERR_INVALID, "null handle");
+    if (!h->chain_set || !h->cam_set || !h->problem_set) return fail(ASC_ERR_INVALID, "set chain, camera and problem first");
+    if (need_values && !h->values_set) return fail(ASC_ERR_INVALID, "set values first");
+    CUDA_TRY(cudaSetDevice(h->dev));
+    return ASC_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+void asc_default_params(asc_params* p) {
+    std::memset(p, 0, sizeof *p);
+    p->sigma_px = 1.0;            // ArmSlamCalib.h:86
+    p->sigma_landmark = 50.0;     // :83
+    p->cauchy_k = 3.0;            // ArmSlamCalib.cpp:197
+    for (int i = 0; i < ASC_MAX_DOF; ++i) p->sigma_encoder[i] = 0.1;   // ArmSlamCalib.h:79
+    for (int i = 0; i < 6; ++i) p->sigma_extrinsic[i] = 0.1;           // :81-82
+    p->use_dead_band = 0;
+    p->dead_band = 0.05;
+    p->pose3_chart = ASC_POSE3_FIRST_ORDER_CAYLEY;
+    p->max_iterations = 100;
+    p->relative_error_tol = 1e-5;
+    p->absolute_error_tol = 1e-5;
+    p->error_tol = 0.0;
+    p->lambda_initial = 1e-5;
+    p->lambda_factor = 10.0;
+    p->lambda_upper_bound = 1e5;
+    p->lambda_lower_bound = 0.0;
+    p->min_model_fidelity = 1e-3;
+    p->delta_initial = 1.0;
+    p->pcg_rel_tol = 1e-12;
+    p->pcg_max_iters = 2000;
+    p->device = -1;
+}
+
+const char* asc_last_error(void) { return g_last_error.c_str(); }
+const char* asc_version(void) { return "arm_slam_calib_b200 0.1 (sm_100a)"; }
+
+int asc_create(const asc_params* params, asc_handle** out) {
+    if (!params || !out) return fail(ASC_ERR_INVALID, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(ASC_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    int dev = params->device;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(ASC_ERR_INVALID, "device %d out of range", dev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(ASC_ERR_CUDA, "device %d is sm_%d%d; this library ships sm_100a code only", dev, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(dev));
+    asc_handle* h = new asc_handle();
+    h->prm = *params;
+    h->dev = dev;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) CUDA_TRY(cudaEventCreate(&ev));
+    CUDA_TRY(cudaMallocHost((void**)&h->h_status, 64 * sizeof(double)));
+    CUDA_TRY(cudaMallocHost((void**)&h->h_flags, 8 * sizeof(int)));
+    h->t_base.resize(12);
+    asc::xf_to12(asc::xf_identity(), h->t_base.data());
+    *out = h;
+    return ASC_OK;
+}
+
+int asc_destroy(asc_handle* h) {
+    if (!h) return ASC_OK;
+    cudaSetDevice(h->dev);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    free_device(h);
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ASC_OK;
+}
+
+int asc_set_chain(asc_handle* h, int32_t n, const double* t_p2j, const double* axis, const double* t_c2j, const uint8_t* continuous,
+                  const double* t_base) {
+    if (!h || !t_p2j || !axis || !t_c2j) return fail(ASC_ERR_INVALID, "null argument");
+    if (!dof_supported(n)) return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", n);
+    if (h->problem_set && n != h->N) return fail(ASC_ERR_INVALID, "chain DOF changed after the problem was set");
+    h->N = n;
+    h->t_p2j.assign(t_p2j, t_p2j + 12 * n);
+    h->axis.assign(axis, axis + 3 * n);
+    h->t_c2j.assign(t_c2j, t_c2j + 12 * n);
+    h->continuous.assign(n, 0);
+    if (continuous) h->continuous.assign(continuous, continuous + n);
+    if (t_base) h->t_base.assign(t_base, t_base + 12);
+    h->chain_set = true;
+    return ASC_OK;
+}
+
+int asc_set_camera(asc_handle* h, double fx, double fy, double cx, double cy) {
+    if (!h) return fail(ASC_ERR_INVALID, "null handle");
+    h->cm.fx = fx; h->cm.fy = fy; h->cm.cx = cx; h->cm.cy = cy;
+    h->cam_set = true;
+    return ASC_OK;
+}
+
+int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_t* pose_idx, const int32_t* lm_idx, const double* uv,
+                    const double* enc, const uint8_t* has_enc, const double* lm_prior, const double* x_prior) {
+    if (!h || !h->chain_set || !h->cam_set) return fail(ASC_ERR_INVALID, "set chain and camera first");
+    if (P <= 0 || L < 0 || M < 0 || M >= (int64_t)0x7fffffff) return fail(ASC_ERR_INVALID, "bad sizes");
+    if ((M > 0 && (!pose_idx || !lm_idx || !uv)) || !enc || (L > 0 && !lm_prior) || !x_prior) return fail(ASC_ERR_INVALID, "null argument");
+    for (int64_t m = 0; m < M; ++m)
+        if (pose_idx[m] < 0 || pose_idx[m] >= P || lm_idx[m] < 0 || lm_idx[m] >= L) return fail(ASC_ERR_INVALID, "observation %lld has an out-of-range index", (long long)m);
+    CUDA_TRY(cudaSetDevice(h->dev));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    free_device(h);
+    const int N = h->N;
+    h->P = P; h->L = L; h->M = M;
+    h->values_set = false; h->linearized = false; h->lin_lambda = -1.0;
+    // constants
+    const asc_params& pr = h->prm;
+    h->cm.inv_sigma_px = 1.0 / pr.sigma_px;
+    h->cm.k2 = pr.cauchy_k * pr.cauchy_k;
+    h->cm.inv_sigma_lm = 1.0 / pr.sigma_landmark;
+    std::memcpy(h->pc.x_prior, x_prior, sizeof h->pc.x_prior);
+    for (int i = 0; i < 6; ++i) h->pc.inv_sigma_x[i] = 1.0 / pr.sigma_extrinsic[i];
+    for (int i = 0; i < ASC_MAX_DOF; ++i) h->pc.inv_sigma_enc[i] = 1.0 / pr.sigma_encoder[i];
+    h->pc.continuous_mask = 0;
+    for (int i = 0; i < N; ++i) if (h->continuous[i]) h->pc.continuous_mask |= 1 << i;
+    h->pc.use_dead_band = pr.use_dead_band; h->pc.dead_band = pr.dead_band; h->pc.chart = pr.pose3_chart;
+
+    // ---- the two observation orders (stable counting sorts: list order kept inside each segment)
+    std::vector<int> pose_ptr(P + 1, 0), lm_ptr(L + 1, 0);
+    for (int64_t m = 0; m < M; ++m) { pose_ptr[pose_idx[m] + 1]++; lm_ptr[lm_idx[m] + 1]++; }
+    for (int p = 0; p < P; ++p) pose_ptr[p + 1] += pose_ptr[p];
+    for (int j = 0; j < L; ++j) lm_ptr[j + 1] += lm_ptr[j];
+    std::vector<int> p_lm(M), p_pose(M), p_orig(M), pos_of(M), l_pose(M), l_perm(M);
+    std::vector<double> p_uv(2 * M), l_uv(2 * M);
+    {
+        std::vector<int> fill(pose_ptr.begin(), pose_ptr.end() - 1);
+        for (int64_t m = 0; m < M; ++m) {
+            const int k = fill[pose_idx[m]]++;
+            p_lm[k] = lm_idx[m]; p_pose[k] = pose_idx[m]; p_orig[k] = (int)m; pos_of[m] = k;
+            p_uv[2 * k] = uv[2 * m]; p_uv[2 * k + 1] = uv[2 * m + 1];
+        }
+        std::vector<int> fl(lm_ptr.begin(), lm_ptr.end() - 1);
+        for (int64_t m = 0; m < M; ++m) {
+            const int k = fl[lm_idx[m]]++;
+            l_pose[k] = pose_idx[m]; l_perm[k] = pos_of[m];
+            l_uv[2 * k] = uv[2 * m]; l_uv[2 * k + 1] = uv[2 * m + 1];
+        }
+    }
+    h->h_p_orig = p_orig;
+
+    const size_t PN = (size_t)P * N, Mz = (size_t)M;
+    h->nCtaPose = cdiv(P, kWarpsPerCta);
+    h->nBlkLm = std::max(1, cdiv(L, 128));
+    int rc;
+#define ALLOC(ptr, count) if ((rc = dev_alloc(h, &h->ptr, (count)))) return rc
+    ALLOC(pose_ptr, P + 1); ALLOC(p_lm, Mz); ALLOC(p_pose, Mz); ALLOC(p_orig, Mz); ALLOC(p_uv, Mz);
+    ALLOC(lm_ptr, L + 1); ALLOC(l_pose, Mz); ALLOC(l_perm, Mz); ALLOC(l_uv, Mz);
+    ALLOC(enc, PN); ALLOC(lm_prior, (size_t)L * 3);
+    if (has_enc) ALLOC(has_enc, P); else h->has_enc = nullptr;
+    ALLOC(q, PN); ALLOC(q_try, PN); ALLOC(lm4, (size_t)L * 4); ALLOC(lm4_try, (size_t)L * 4); ALLOC(X, 12); ALLOC(X_try, 12);
+    ALLOC(cam, (size_t)P * 12); ALLOC(chain, PN * 6);
+    ALLOC(J, (size_t)(N + 3) * Mz); ALLOC(b_dbg, 1);
+    ALLOC(poseblk, PN * N + PN * 6 + 36 + PN + 6 + 8);
+    h->Bpp = h->poseblk; h->BpK = h->Bpp + PN * N; h->BKK = h->BpK + PN * 6; h->gr = h->BKK + 36; h->err_lin = h->gr + PN + 6;
+    ALLOC(C, (size_t)L * 6); ALLOC(gl, (size_t)L * 3); ALLOC(WK, (size_t)L * 18); ALLOC(Cinv, (size_t)L * 6);
+    ALLOC(cg4, (size_t)L * 4); ALLOC(u4, (size_t)L * 4); ALLOC(dl4, (size_t)L * 4); ALLOC(gl4, (size_t)L * 4); ALLOC(v4, Mz * 4);
+    ALLOC(precblk, PN * N + PN + kPartCols);
+    h->Dloc = h->precblk; h->rloc = h->Dloc + PN * N; h->krow = h->rloc + PN;
+    ALLOC(Minv, PN * N); ALLOC(MinvK, 36); ALLOC(rhs, PN + 8);
+    ALLOC(vx, PN + 8); ALLOC(vr, PN + 8); ALLOC(vz, PN + 8); ALLOC(vp, PN + 8);
+    ALLOC(ybuf, PN + 8 + 2 * kPartCols);
+    const size_t nStep = (size_t)cdiv(std::max<int64_t>((int64_t)PN + 6, (int64_t)L * 4), 256);
+    ALLOC(partA, std::max<size_t>(h->nCtaPose, nStep) * kPartCols); ALLOC(partC, (size_t)h->nCtaPose * kPartCols);
+    ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols);
+    h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
+    ALLOC(errblk, h->nErrBlk);
+    ALLOC(scal, 8); ALLOC(status, 64); ALLOC(flags, 4); ALLOC(cheir, 1);
+#undef ALLOC
+#define UP(dst, src, bytes) CUDA_TRY(cudaMemcpyAsync(h->dst, src, (bytes), cudaMemcpyHostToDevice, h->stream))
+    UP(pose_ptr, pose_ptr.data(), sizeof(int) * (P + 1)); UP(lm_ptr, lm_ptr.data(), sizeof(int) * (L + 1));
+    if (M) {
+        UP(p_lm, p_lm.data(), sizeof(int) * Mz); UP(p_pose, p_pose.data(), sizeof(int) * Mz); UP(p_orig, p_orig.data(), sizeof(int) * Mz);
+        UP(p_uv, p_uv.data(), sizeof(double) * 2 * Mz); UP(l_pose, l_pose.data(), sizeof(int) * Mz); UP(l_perm, l_perm.data(), sizeof(int) * Mz);
+        UP(l_uv, l_uv.data(), sizeof(double) * 2 * Mz);
+    }
+    UP(enc, enc, sizeof(double) * PN);
+    if (L) UP(lm_prior, lm_prior, sizeof(double) * 3 * L);
+    if (has_enc) UP(has_enc, has_enc, P);
+#undef UP
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // host staging vectors go out of scope
+    h->problem_set = true;
+    return ASC_OK;
+}
+
+int asc_set_values(asc_handle* h, const double* q, const double* l, const double* x) {
+    if (!h || !h->problem_set) return fail(ASC_ERR_INVALID, "set the problem first");
+    if (!q || (h->L > 0 && !l) || !x) return fail(ASC_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->dev));
+    CUDA_TRY(cudaMemcpyAsync(h->q, q, sizeof(double) * h->P * h->N, cudaMemcpyHostToDevice, h->stream));
+    if (h->L) CUDA_TRY(cudaMemcpy2DAsync(h->lm4, 4 * sizeof(double), l, 3 * sizeof(double), 3 * sizeof(double), h->L, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->X, x, sizeof(double) * 12, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->values_set = true;
+    h->linearized = false;
+    return ASC_OK;
+}
+
+int asc_get_values(asc_handle* h, double* q, double* l, double* x) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (q) CUDA_TRY(cudaMemcpyAsync(q, h->q, sizeof(double) * h->P * h->N, cudaMemcpyDeviceToHost, h->stream));
+    if (l && h->L) CUDA_TRY(cudaMemcpy2DAsync(l, 3 * sizeof(double), h->lm4, 4 * sizeof(double), 3 * sizeof(double), h->L, cudaMemcpyDeviceToHost, h->stream));
+    if (x) CUDA_TRY(cudaMemcpyAsync(x, h->X, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ASC_OK;
+}
+
+int asc_error(asc_handle* h, double* error) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!error) return fail(ASC_ERR_INVALID, "null argument");
+    h->linearized = false;   // the FK table is overwritten
+    return dispatch_error(h, h->q, h->lm4, h->X, error);
+}
+
+int asc_linearize(asc_handle* h, asc_linear_stats* stats) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    float a = 0, b = 0;
+    rc = dispatch_linearize(h, false, &a, &b);
+    if (rc) return rc;
+    if (stats) {
+        unsigned long long ch = 0;
+        CUDA_TRY(cudaMemcpyAsync(&ch, h->cheir, sizeof ch, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->h_status, h->err_lin, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        stats->error = h->h_status[0];
+        stats->linearize_ms = a; stats->assemble_ms = b; stats->cheirality = (int64_t)ch;
+    }
+    return ASC_OK;
+}
+
+int asc_optimize(asc_handle* h, int32_t mode, asc_iter_log* log, int32_t log_capacity, int32_t* n_iterations, double* final_error) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (mode != ASC_BATCH_LM && mode != ASC_BATCH_DOGLEG) return fail(ASC_ERR_INVALID, "unknown optimisation mode %d", mode);
+    const asc_params& p = h->prm;
+    double error = 0.0, lambda = p.lambda_initial, Delta = p.delta_initial;
+    rc = dispatch_error(h, h->q, h->lm4, h->X, &error);   // NonlinearOptimizer state at construction
+    if (rc) return rc;
+    int iterations = 0;
+    if (!(error <= p.error_tol) && iterations < p.max_iterations) {   // defaultOptimize, SURVEY Appendix C.1
+        double e_old;
+        do {
+            e_old = error;
+            asc_iter_log lg;
+            std::memset(&lg, 0, sizeof lg);
+            rc = mode == ASC_BATCH_LM ? lm_iterate(h, &error, &lambda, &lg) : dogleg_iterate(h, &error, &Delta, &lg);
+            if (rc) break;
+            ++iterations;
+            lg.iteration = iterations; lg.error = error; lg.lambda_or_delta = mode == ASC_BATCH_LM ? lambda : Delta;
+            if (log && iterations <= log_capacity) log[iterations - 1] = lg;
+        } while (iterations < p.max_iterations && !converged(p, e_old, error));
+    }
+    if (n_iterations) *n_iterations = iterations;
+    if (final_error) *final_error = error;
+    return rc;
+}
+
+int asc_indeterminate_key(asc_handle* h, char* kind, int64_t* index) {
+    if (!h || !kind || !index) return fail(ASC_ERR_INVALID, "null argument");
+    *kind = h->fail_kind; *index = h->fail_index;
+    return ASC_OK;
+}
+
+int asc_get_projection_blocks(asc_handle* h, double* b, double* jq, double* jl) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    const size_t M = (size_t)h->M, N = h->N;
+    double2* bdbg = nullptr;
+    double *d_b = nullptr, *d_jq = nullptr, *d_jl = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&bdbg, std::max<size_t>(M, 1) * sizeof(double2)));
+    CUDA_TRY(cudaMalloc((void**)&d_b, std::max<size_t>(M, 1) * 2 * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&d_jq, std::max<size_t>(M, 1) * 2 * N * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&d_jl, std::max<size_t>(M, 1) * 6 * sizeof(double)));
+    double2* saved = h->b_dbg;
+    h->b_dbg = bdbg;
+    rc = dispatch_linearize(h, true, nullptr, nullptr);
+    if (!rc && M) rc = dispatch_unpack(h, d_b, d_jq, d_jl);
+    h->b_dbg = saved;
+    if (!rc) {
+        if (b) cudaMemcpyAsync(b, d_b, M * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (jq) cudaMemcpyAsync(jq, d_jq, M * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (jl) cudaMemcpyAsync(jl, d_jl, M * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(bdbg); cudaFree(d_b); cudaFree(d_jq); cudaFree(d_jl);
+    return rc;
+}
+
+int asc_get_landmark_blocks(asc_handle* h, double* c, double* gl, double* wk) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!h->linearized) return fail(ASC_ERR_INVALID, "call asc_linearize first");
+    const size_t L = h->L;
+    std::vector<double> c6(L * 6);
+    CUDA_TRY(cudaMemcpyAsync(c6.data(), h->C, L * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (gl) CUDA_TRY(cudaMemcpyAsync(gl, h->gl, L * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (wk) CUDA_TRY(cudaMemcpyAsync(wk, h->WK, L * 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (c)
+        for (size_t j = 0; j < L; ++j) {
+            const double* s = &c6[6 * j];
+            double* o = c + 9 * j;
+            o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[1]; o[4] = s[3]; o[5] = s[4]; o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
+        }
+    return ASC_OK;
+}
+
+int asc_get_pose_blocks(asc_handle* h, double* bpp, double* bpk, double* gp, double* bkk, double* gk) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!h->linearized) return fail(ASC_ERR_INVALID, "call asc_linearize first");
+    const size_t PN = (size_t)h->P * h->N;
+    if (bpp) CUDA_TRY(cudaMemcpyAsync(bpp, h->Bpp, PN * h->N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (bpk) CUDA_TRY(cudaMemcpyAsync(bpk, h->BpK, PN * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (gp) CUDA_TRY(cudaMemcpyAsync(gp, h->gr, PN * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (bkk) CUDA_TRY(cudaMemcpyAsync(bkk, h->BKK, 36 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (gk) CUDA_TRY(cudaMemcpyAsync(gk, h->gr + PN, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ASC_OK;
+}
+
+int asc_solve_damped(asc_handle* h, double lambda, double* dq, double* dl, double* dx, int32_t* pcg_iterations) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!h->linearized) { rc = dispatch_linearize(h, false, nullptr, nullptr); if (rc) return rc; }
+    int its = 0;
+    rc = dispatch_solve(h, lambda, &its);
+    if (pcg_iterations) *pcg_iterations = its;
+    if (rc) return rc;
+    const size_t PN = (size_t)h->P * h->N;
+    if (dq) CUDA_TRY(cudaMemcpyAsync(dq, h->vx, PN * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (dx) CUDA_TRY(cudaMemcpyAsync(dx, h->vx + PN, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (dl && h->L) CUDA_TRY(cudaMemcpy2DAsync(dl, 3 * sizeof(double), h->dl4, 4 * sizeof(double), 3 * sizeof(double), h->L, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ASC_OK;
+}
+
+// ---- multi-GPU
+int asc_comm_id_size(void) { return (int)sizeof(ncclUniqueId); }
+
+int asc_comm_create_id(void* id_bytes) {
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return fail(ASC_ERR_COMM, "ncclGetUniqueId failed");
+    std::memcpy(id_bytes, &id, sizeof id);
+    return ASC_OK;
+}
+
+int asc_comm_init(asc_handle* h, int32_t rank, int32_t world, const void* id_bytes) {
+    if (!h || !id_bytes || rank < 0 || rank >= world) return fail(ASC_ERR_INVALID, "bad communicator arguments");
+    if (world == 1) { h->rank = 0; h->world = 1; return ASC_OK; }
+    int rc = load_nccl();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(h->dev));
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) return fail(ASC_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+    h->rank = rank; h->world = world;
+    return ASC_OK;
+}
+
+int asc_shard_by_landmark(int32_t L, int64_t M, const int32_t* lm_idx, int32_t world, int32_t* lm_begin) {
+    if (L < 0 || M < 0 || world <= 0 || !lm_begin || (M > 0 && !lm_idx)) return fail(ASC_ERR_INVALID, "bad arguments");
+    std::vector<int64_t> cnt(L + 1, 0);
+    for (int64_t m = 0; m < M; ++m) {
+        if (lm_idx[m] < 0 || lm_idx[m] >= L) return fail(ASC_ERR_INVALID, "landmark index out of range");
+        cnt[lm_idx[m] + 1]++;
+    }
+    for (int j = 0; j < L; ++j) cnt[j + 1] += cnt[j] + 1;   // +1: weigh the landmark itself so empty ones spread too
+    const int64_t total = cnt[L];
+    lm_begin[0] = 0;
+    int j = 0;
+    for (int r = 1; r < world; ++r) {
+        const int64_t target = total * r / world;
+        while (j < L && cnt[j] < target) ++j;
+        lm_begin[r] = j;
+    }
+    lm_begin[world] = L;
+    return ASC_OK;
+}
+
+}  // extern "C"

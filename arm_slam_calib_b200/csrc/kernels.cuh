@@ -1,0 +1,1282 @@
+// sm_100a kernels of the batch optimisation path.
+//
+// Data layout in HBM (all fp64 unless noted; k = position in the POSE-major observation order,
+// kk = position in the LANDMARK-major order; both orders are built once in asc_set_problem):
+//   cam   [P][12]      camera pose per keyframe  R_cam row-major (9) | t_cam (3)       (FK kernel)
+//   chain [P][6N]      world joint axis a_i (3) | joint origin o_i (3) per joint        (FK kernel)
+//   p_uv  [M] double2, p_lm [M] int32, p_pose [M] int32          pose-major static observation data
+//   l_uv  [M] double2, l_pose [M] int32, l_perm [M] int32        landmark-major static data,
+//                                                                l_perm[kk] = k of the same factor
+//   J     [(N+3)][M] double2   whitened+reweighted Jacobian planes, pose-major: the flat vector
+//                              [Jq row0 (N) | Jq row1 (N) | Jl row0 (3) | Jl row1 (3)] of observation k,
+//                              component pair i at J[i*M + k] -> every load is a coalesced LDG.128
+//   lm4   [L][4], u4 [L][4], v4 [M][4]   3-vectors padded to one 32-byte sector for gathers
+//   C [L][6] (sym), gl [L][3], WK [L][18], Cinv [L][6]            landmark blocks
+//   Bpp [P][N*N], BpK [P][N*6], gp [P][N], Minv [P][N*N]          pose blocks
+// Reductions are two-level with a fixed tree (no atomics), so results are run-to-run identical.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace asck {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr int kPartCols = 32;   // width of every partial-sum row (padded)
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Camera {
+    double fx, fy, cx, cy;
+    double inv_sigma_px, k2;      // 1/sigma_px, cauchy k^2
+    double inv_sigma_lm;          // 1/sigma_landmark
+};
+
+template <int N>
+struct ChainConst {               // host-precomposed serial chain
+    double F0[12];                // T_base * T_p2j[0]
+    double Lk[N][12];             // inverse(T_c2j[i]) * T_p2j[i+1]   (last: inverse(T_c2j[N-1]))
+    double axis[N][3];
+};
+
+struct PriorConst {
+    double x_prior[12];
+    double inv_sigma_x[6];
+    double inv_sigma_enc[20];
+    int continuous_mask;          // bit i set: joint i is continuous (RobotConfig.h:72-77)
+    int use_dead_band;
+    double dead_band;
+    int chart;
+};
+
+// ------------------------------------------------------------------ tiny device helpers
+__device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void mul_xf(const double* A, const double* B, double* O) {   // 3x4 [R|t] row-major
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double s = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
+            if (c == 3) s += A[4 * r + 3];
+            O[4 * r + c] = s;
+        }
+    }
+}
+
+__device__ __forceinline__ void rodrigues(const double* ax, double th, double* R) {   // 3x3 row-major
+    double s, c;
+    sincos(th, &s, &c);
+    const double v = 1.0 - c, x = ax[0], y = ax[1], z = ax[2];
+    R[0] = c + x * x * v; R[1] = x * y * v - z * s; R[2] = x * z * v + y * s;
+    R[3] = y * x * v + z * s; R[4] = c + y * y * v; R[5] = y * z * v - x * s;
+    R[6] = z * x * v - y * s; R[7] = z * y * v + x * s; R[8] = c + z * z * v;
+}
+
+// [DEP] Rot3 / Pose3 charts; x12 is [R|t] row-major 3x4
+__device__ inline void rot3_logmap(const double* A, double* w) {   // A 3x3 row-major
+    const double tr = A[0] + A[4] + A[8];
+    if (fabs(tr + 1.0) < 1e-10) {
+        const double PI = 3.14159265358979323846;
+        if (fabs(A[8] + 1.0) > 1e-10) { const double s = PI / sqrt(2.0 + 2.0 * A[8]); w[0] = s * A[2]; w[1] = s * A[5]; w[2] = s * (1.0 + A[8]); }
+        else if (fabs(A[4] + 1.0) > 1e-10) { const double s = PI / sqrt(2.0 + 2.0 * A[4]); w[0] = s * A[1]; w[1] = s * (1.0 + A[4]); w[2] = s * A[7]; }
+        else { const double s = PI / sqrt(2.0 + 2.0 * A[0]); w[0] = s * (1.0 + A[0]); w[1] = s * A[3]; w[2] = s * A[6]; }
+        return;
+    }
+    double mag;
+    const double tr3 = tr - 3.0;
+    if (tr3 < -1e-7) { const double th = acos((tr - 1.0) / 2.0); mag = th / (2.0 * sin(th)); }
+    else mag = 0.5 - tr3 * tr3 / 12.0;
+    w[0] = mag * (A[7] - A[5]); w[1] = mag * (A[2] - A[6]); w[2] = mag * (A[3] - A[1]);
+}
+
+__device__ inline void pose3_local(int chart, const double* X0, const double* X1, double* xi) {
+    double A[9], d[3], t[3];   // A = R0^T R1, t = R0^T (t1 - t0)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) d[r] = X1[4 * r + 3] - X0[4 * r + 3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A[3 * r + c] = X0[r] * X1[c] + X0[4 + r] * X1[4 + c] + X0[8 + r] * X1[8 + c];
+        t[r] = X0[r] * d[0] + X0[4 + r] * d[1] + X0[8 + r] * d[2];
+    }
+    if (chart == 0) {   // inverse Cayley
+        const double k = 2.0 / (1.0 + A[0] + A[4] + A[8]);
+        xi[0] = k * (A[7] - A[5]); xi[1] = k * (A[2] - A[6]); xi[2] = k * (A[3] - A[1]);
+    } else rot3_logmap(A, xi);
+    if (chart == 2) {   // Pose3::Logmap translation part
+        const double th = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+        if (th < 1e-10) { xi[3] = t[0]; xi[4] = t[1]; xi[5] = t[2]; }
+        else {
+            const double n[3] = {xi[0] / th, xi[1] / th, xi[2] / th};
+            const double WT[3] = {n[1] * t[2] - n[2] * t[1], n[2] * t[0] - n[0] * t[2], n[0] * t[1] - n[1] * t[0]};
+            const double WWT[3] = {n[1] * WT[2] - n[2] * WT[1], n[2] * WT[0] - n[0] * WT[2], n[0] * WT[1] - n[1] * WT[0]};
+            const double Tan = tan(0.5 * th);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) xi[3 + r] = t[r] - (0.5 * th) * WT[r] + (1 - th / (2. * Tan)) * WWT[r];
+        }
+    } else { xi[3] = t[0]; xi[4] = t[1]; xi[5] = t[2]; }
+}
+
+__device__ inline void pose3_retract(int chart, const double* X, const double* xi, double* O) {
+    double E[12];   // increment [R|t]
+    const double x = xi[0], y = xi[1], z = xi[2];
+    if (chart == 0) {
+        const double x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, xz = x * z, yz = y * z;
+        const double f = 1.0 / (4.0 + x2 + y2 + z2), f2 = 2.0 * f;
+        E[0] = (4 + x2 - y2 - z2) * f; E[1] = (xy - 2 * z) * f2; E[2] = (xz + 2 * y) * f2;
+        E[4] = (xy + 2 * z) * f2; E[5] = (4 - x2 + y2 - z2) * f; E[6] = (yz - 2 * x) * f2;
+        E[8] = (xz - 2 * y) * f2; E[9] = (yz + 2 * x) * f2; E[10] = (4 - x2 - y2 + z2) * f;
+    } else {
+        const double th = sqrt(x * x + y * y + z * z);
+        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (!(th < 1e-10)) { const double ax[3] = {x / th, y / th, z / th}; rodrigues(ax, th, R); }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { E[4 * r] = R[3 * r]; E[4 * r + 1] = R[3 * r + 1]; E[4 * r + 2] = R[3 * r + 2]; }
+    }
+    if (chart == 2) {
+        const double th = sqrt(x * x + y * y + z * z);
+        const double* v = xi + 3;
+        if (th < 1e-10) { E[3] = v[0]; E[7] = v[1]; E[11] = v[2]; }
+        else {
+            const double n[3] = {x / th, y / th, z / th};
+            const double vn = n[0] * v[0] + n[1] * v[1] + n[2] * v[2];
+            const double c[3] = {n[1] * v[2] - n[2] * v[1], n[2] * v[0] - n[0] * v[2], n[0] * v[1] - n[1] * v[0]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double Rc = E[4 * r] * c[0] + E[4 * r + 1] * c[1] + E[4 * r + 2] * c[2];
+                E[4 * r + 3] = (c[r] - Rc) / th + vn * n[r];
+            }
+        }
+    } else { E[3] = xi[3]; E[7] = xi[4]; E[11] = xi[5]; }   // first order: t + R v
+    mul_xf(X, E, O);
+}
+
+// ------------------------------------------------------------------ K0: forward kinematics table
+// One thread per keyframe.  Replaces the three DART setPositions/FK passes the reference does for
+// EVERY factor (RobotProjectionFactor.h:206,:235,:257): FK is evaluated once per pose.
+template <int N, bool WITH_CHAIN>
+__global__ void __launch_bounds__(128) fk_kernel(ChainConst<N> cc, const double* __restrict__ q, const double* __restrict__ X,
+                                                 int P, double* __restrict__ cam, double* __restrict__ chain) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double F[12], T[12], R[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) F[i] = cc.F0[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double* ax = cc.axis[i];
+        if (WITH_CHAIN) {
+            double* o = chain + (size_t)p * 6 * N + 6 * i;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                o[r] = F[4 * r] * ax[0] + F[4 * r + 1] * ax[1] + F[4 * r + 2] * ax[2];
+                o[3 + r] = F[4 * r + 3];
+            }
+        }
+        double Rq[9];
+        rodrigues(ax, q[(size_t)p * N + i], Rq);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { R[4 * r] = Rq[3 * r]; R[4 * r + 1] = Rq[3 * r + 1]; R[4 * r + 2] = Rq[3 * r + 2]; R[4 * r + 3] = 0; }
+        mul_xf(F, R, T);
+        mul_xf(T, cc.Lk[i], F);
+    }
+    double Xl[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Xl[i] = X[i];
+    mul_xf(F, Xl, T);   // T_cam = T_link * X   (RobotProjectionFactor.h:208)
+    double* o = cam + (size_t)p * 12;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { o[3 * r] = T[4 * r]; o[3 * r + 1] = T[4 * r + 1]; o[3 * r + 2] = T[4 * r + 2]; o[9 + r] = T[4 * r + 3]; }
+}
+
+// ------------------------------------------------------------------ projection factor core
+// Everything RobotProjectionFactor::project + evaluateError + Robust::WhitenSystem produce for one
+// factor except J_q (which needs the chain).  R,t = camera pose in the world.
+struct ProjOut {
+    double b0, b1;       // whitened, reweighted right-hand side  b = -sqrt(w) r / sigma
+    double jl[6];        // whitened, reweighted 2x3
+    double jk[12];       // whitened, reweighted 2x6
+    double err;          // 0.5 w |r/sigma|^2
+    bool cheir;
+};
+
+template <bool WITH_J, bool WITH_JK>
+__device__ __forceinline__ void project_factor(const Camera& cm, const double* R, const double* t, double lx, double ly, double lz,
+                                               double zu, double zv, ProjOut& o) {
+    const double d0 = lx - t[0], d1 = ly - t[1], d2 = lz - t[2];
+    const double px = R[0] * d0 + R[3] * d1 + R[6] * d2;
+    const double py = R[1] * d0 + R[4] * d1 + R[7] * d2;
+    const double pz = R[2] * d0 + R[5] * d1 + R[8] * d2;
+    const bool bad = pz < 0.01;                              // RobotProjectionFactor.h:213
+    const double iz = 1.0 / pz, u = px * iz, v = py * iz;
+    const double pu = bad ? 2.0 * cm.fx : cm.fx * u + cm.cx; // :219 returns (2fx, 2fx)
+    const double pv = bad ? 2.0 * cm.fx : cm.fy * v + cm.cy;
+    const double r0 = (pu - zu) * cm.inv_sigma_px, r1 = (pv - zv) * cm.inv_sigma_px;
+    const double n2 = r0 * r0 + r1 * r1;
+    const double w = cm.k2 / (cm.k2 + n2), sw = sqrt(w);
+    o.b0 = -sw * r0; o.b1 = -sw * r1;
+    o.err = 0.5 * w * n2;
+    o.cheir = bad;
+    if (WITH_J) {
+        const double s = bad ? 0.0 : sw * cm.inv_sigma_px;   // zero Jacobians behind the camera (:215-217)
+        const double su = s * cm.fx * iz, sv = s * cm.fy * iz;
+        const double uu = bad ? 0.0 : u, vv = bad ? 0.0 : v;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            o.jl[c] = bad ? 0.0 : su * (R[3 * c] - uu * R[3 * c + 2]);
+            o.jl[3 + c] = bad ? 0.0 : sv * (R[3 * c + 1] - vv * R[3 * c + 2]);
+        }
+        if (WITH_JK) {
+            const double a = s * cm.fx, c2 = s * cm.fy, iz2 = bad ? 0.0 : iz;
+            o.jk[0] = a * (uu * vv); o.jk[1] = a * (-1.0 - uu * uu); o.jk[2] = a * vv;
+            o.jk[3] = a * (-iz2); o.jk[4] = 0.0; o.jk[5] = a * (iz2 * uu);
+            o.jk[6] = c2 * (1.0 + vv * vv); o.jk[7] = c2 * (-uu * vv); o.jk[8] = c2 * (-uu);
+            o.jk[9] = 0.0; o.jk[10] = c2 * (-iz2); o.jk[11] = c2 * (iz2 * vv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ warp-level bilinear accumulation
+// acc(c, c2) += sum_r U[r][c] * V[r][c2] over the 32 observations of a tile, for the D x D symmetric
+// result, each unordered pair owned by exactly one lane: lane column c accumulates c2 = (c + t) mod D,
+// t = 0..D/2.  For D <= 16 the two half-warps split the two residual rows and are added at the end.
+template <int D>
+struct GramCfg {
+    static constexpr int GS = D <= 16 ? 16 : 32;     // lanes per group
+    static constexpr int G = 32 / GS;                // groups (rows handled in parallel)
+    static constexpr int H = D / 2 + 1;              // offsets per lane
+    static constexpr int LD = (D % 2) ? D : D + 1;   // odd leading dimension: conflict-free column reads
+};
+
+template <int D, bool SYM_UV>
+__device__ __forceinline__ void gram_tile(const double* __restrict__ U, const double* __restrict__ V, int count, int lane,
+                                          double (&acc)[GramCfg<D>::H]) {
+    // U, V: [2][32][LD] in shared memory (V == U when SYM_UV)
+    typedef GramCfg<D> Cf;
+    const int g = lane / Cf::GS, c = lane % Cf::GS;
+    if (c >= D) return;
+    for (int o = 0; o < count; ++o) {
+#pragma unroll
+        for (int rr = 0; rr < 2 / Cf::G; ++rr) {
+            const int r = Cf::G == 2 ? g : rr;
+            const double* vrow = V + (r * 32 + o) * Cf::LD;
+            const double mine = SYM_UV ? vrow[c] : U[(r * 32 + o) * Cf::LD + c];
+#pragma unroll
+            for (int t = 0; t < Cf::H; ++t) {
+                int c2 = c + t;
+                if (c2 >= D) c2 -= D;
+                acc[t] = fma(mine, vrow[c2], acc[t]);
+            }
+        }
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void gram_finish(double (&acc)[GramCfg<D>::H]) {
+    if (GramCfg<D>::G == 2) {
+#pragma unroll
+        for (int t = 0; t < GramCfg<D>::H; ++t) acc[t] += __shfl_xor_sync(kFull, acc[t], 16);
+    }
+}
+
+// ------------------------------------------------------------------ K1 (+K2b): linearise, pose-major
+// One warp per keyframe.  The keyframe's FK row (camera pose + joint axes/origins) is staged in shared
+// memory once; each lane then evaluates one projection factor per tile: residual, J_q, J_l, J_K,
+// Robust-Cauchy whitening (RobotProjectionFactor.h:96-259 + SURVEY rows A1-A3).  J_q/J_l go to HBM as
+// double2 planes; [J_q | J_K | b] goes to a shared-memory tile from which the warp accumulates the
+// keyframe's blocks B_pp, B_pK, g_p and its share of B_KK, g_K and the error, in a fixed order.
+template <int N>
+struct LinSmem {
+    static constexpr int D = N + 7;
+    static constexpr int LD = GramCfg<D>::LD;
+    static constexpr int kPerWarpDoubles = 12 + 6 * N + 2 * 32 * LD + kPartCols;
+    static constexpr size_t kBytes = sizeof(double) * kPerWarpDoubles * kWarpsPerCta;
+};
+
+template <int N, bool STORE_B>
+__global__ void __launch_bounds__(kCtaThreads)
+linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
+                      const double2* __restrict__ p_uv, const double* __restrict__ cam, const double* __restrict__ chain,
+                      const double* __restrict__ lm4, const double* __restrict__ q, const double* __restrict__ enc,
+                      const uint8_t* __restrict__ has_enc, int add_priors, double2* __restrict__ J, double* __restrict__ Bpp,
+                      double* __restrict__ BpK, double* __restrict__ gp, double* __restrict__ cta_part, double2* __restrict__ b_out,
+                      unsigned long long* __restrict__ cheir_count) {
+    constexpr int D = N + 7;
+    typedef GramCfg<D> Cf;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sw_ = smem + (size_t)warp * LinSmem<N>::kPerWarpDoubles;
+    double* s_cam = sw_;                 // 12
+    double* s_chain = sw_ + 12;          // 6N
+    double* s_A = s_chain + 6 * N;       // [2][32][LD]
+    double* s_part = s_A + 2 * 32 * Cf::LD;   // kPartCols
+    const int p = blockIdx.x * kWarpsPerCta + warp;
+    if (lane < kPartCols) s_part[lane] = 0.0;
+    if (p < P) {
+        for (int i = lane; i < 12; i += 32) s_cam[i] = cam[(size_t)p * 12 + i];
+        for (int i = lane; i < 6 * N; i += 32) s_chain[i] = chain[(size_t)p * 6 * N + i];
+        __syncwarp();
+        double acc[Cf::H];
+#pragma unroll
+        for (int t = 0; t < Cf::H; ++t) acc[t] = 0.0;
+        unsigned ncheir = 0;
+        const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+        for (int base = k0; base < k1; base += 32) {
+            const int k = base + lane;
+            const int count = min(32, k1 - base);
+            if (k < k1) {
+                const double2 z = ldg2(p_uv + k);
+                const int j = __ldg(p_lm + k);
+                const double2 l01 = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j));
+                const double lz = __ldg(lm4 + 4 * (size_t)j + 2);
+                ProjOut o;
+                project_factor<true, true>(cm, s_cam, s_cam + 9, l01.x, l01.y, lz, z.x, z.y, o);
+                ncheir += o.cheir ? 1u : 0u;
+                double jq[2 * N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {   // column i of getLinearJacobian: a_i x (l - o_i)   (:240)
+                    const double* a = s_chain + 6 * i;
+                    const double rx = l01.x - a[3], ry = l01.y - a[4], rz = lz - a[5];
+                    const double cx = a[1] * rz - a[2] * ry, cy = a[2] * rx - a[0] * rz, cz = a[0] * ry - a[1] * rx;
+                    jq[i] = -(o.jl[0] * cx + o.jl[1] * cy + o.jl[2] * cz);       // J1 = -(Dpoint * Jrobot)   (:245)
+                    jq[N + i] = -(o.jl[3] * cx + o.jl[4] * cy + o.jl[5] * cz);
+                }
+                // packed planes [jq row0 | jq row1 | jl row0 | jl row1]
+                double flat[2 * N + 6];
+#pragma unroll
+                for (int i = 0; i < 2 * N; ++i) flat[i] = jq[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) flat[2 * N + i] = o.jl[i];
+#pragma unroll
+                for (int i = 0; i < N + 3; ++i) J[(size_t)i * M + k] = make_double2(flat[2 * i], flat[2 * i + 1]);
+                if (STORE_B) b_out[k] = make_double2(o.b0, o.b1);
+                double* a0 = s_A + (0 * 32 + lane) * Cf::LD;
+                double* a1 = s_A + (1 * 32 + lane) * Cf::LD;
+#pragma unroll
+                for (int i = 0; i < N; ++i) { a0[i] = jq[i]; a1[i] = jq[N + i]; }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { a0[N + i] = o.jk[i]; a1[N + i] = o.jk[6 + i]; }
+                a0[N + 6] = o.b0; a1[N + 6] = o.b1;
+            }
+            __syncwarp();
+            gram_tile<D, true>(s_A, s_A, count, lane, acc);
+            __syncwarp();
+        }
+        gram_finish<D>(acc);
+        // scatter the D(D+1)/2 entries to their blocks (lanes of group 0)
+        if (lane < D) {
+            const int c = lane;
+            double* B = Bpp + (size_t)p * N * N;
+            double* BK = BpK + (size_t)p * N * 6;
+            double* g = gp + (size_t)p * N;
+            const bool with_enc = add_priors && (has_enc == nullptr || has_enc[p]);
+#pragma unroll
+            for (int t = 0; t < Cf::H; ++t) {
+                int c2 = c + t;
+                if (c2 >= D) c2 -= D;
+                const int lo = min(c, c2), hi = max(c, c2);
+                double v = acc[t];
+                if (hi < N) {
+                    if (lo == hi && with_enc) v += pc.inv_sigma_enc[lo] * pc.inv_sigma_enc[lo];
+                    B[lo * N + hi] = v; B[hi * N + lo] = v;
+                } else if (lo < N && hi < N + 6) BK[lo * 6 + (hi - N)] = v;
+                else if (lo < N) g[lo] = v;                 // hi == N+6: J_q^T b   (encoder part added below)
+                else if (hi < N + 6) { const int a = lo - N, bb = hi - N; s_part[a * 6 - a * (a - 1) / 2 + (bb - a)] = v; }
+                else if (lo < N + 6) s_part[21 + lo - N] = v;
+                else s_part[27] = 0.5 * v;
+            }
+        }
+        __syncwarp();
+        // EncoderFactor (EncoderFactor.h:60-99): residual q - enc (SO(2)-wrapped if continuous), J = I
+        if (add_priors && (has_enc == nullptr || has_enc[p])) {
+            double e2 = 0.0;
+            if (lane < N) {
+                const double qq = q[(size_t)p * N + lane], ee = enc[(size_t)p * N + lane];
+                double d = qq - ee;
+                if ((pc.continuous_mask >> lane) & 1) d = atan2(sin(qq - ee), cos(qq - ee));
+                if (pc.use_dead_band) d = fabs(d) < pc.dead_band ? 0.0 : (d < 0 ? d + pc.dead_band : d - pc.dead_band);
+                const double is = pc.inv_sigma_enc[lane], wr = d * is;
+                gp[(size_t)p * N + lane] += -wr * is;
+                e2 = 0.5 * wr * wr;
+            }
+            e2 = warp_sum(e2);
+            if (lane == 0) s_part[27] += e2;
+        }
+        ncheir = __reduce_add_sync(kFull, ncheir);
+        if (lane == 0 && ncheir) atomicAdd(cheir_count, (unsigned long long)ncheir);   // statistics only
+    }
+    __syncthreads();
+    // fixed-order combine of the CTA's keyframes -> one partial row per CTA
+    if (threadIdx.x < kPartCols) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) s += smem[(size_t)w * LinSmem<N>::kPerWarpDoubles + 12 + 6 * N + 2 * 32 * Cf::LD + threadIdx.x];
+        cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------ deterministic row reduction
+// out[b][c] = sum over the rows of chunk b of in[r][c]; C <= 32 columns, fixed order.
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const double* __restrict__ in, int64_t R, int C, int ld_in, int rows_per_block,
+                                                          double* __restrict__ out) {
+    __shared__ double s[8][kPartCols];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(R, r0 + rows_per_block);
+    double a = 0.0;
+    if (lane < C)
+        for (int64_t r = r0 + warp; r < r1; r += 8) a += in[r * ld_in + lane];
+    s[warp][lane] = a;
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s[w][lane];
+        out[(size_t)blockIdx.x * kPartCols + lane] = lane < C ? t : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------ K2a: landmark blocks (landmark-major)
+// One thread per landmark: C_j = sum J_l^T J_l + prior, g_j = sum J_l^T b + prior, W_Kj = sum J_K^T J_l.
+// The camera-side Jacobians are recomputed here from the [P][12] camera table (L2-resident) so that
+// nothing per-observation has to be stored or permuted for this pass.
+__global__ void __launch_bounds__(128)
+landmark_blocks_kernel(Camera cm, int L, const int* __restrict__ lm_ptr, const int* __restrict__ l_pose, const double2* __restrict__ l_uv,
+                       const double* __restrict__ cam, const double* __restrict__ lm4, const double* __restrict__ lm_prior,
+                       double* __restrict__ C, double* __restrict__ gl, double* __restrict__ WK, double* __restrict__ blk_err) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double err = 0.0;
+    if (j < L) {
+        const double lx = lm4[4 * (size_t)j], ly = lm4[4 * (size_t)j + 1], lz = lm4[4 * (size_t)j + 2];
+        double c[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, wk[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) wk[i] = 0.0;
+        const int k0 = lm_ptr[j], k1 = lm_ptr[j + 1];
+        for (int k = k0; k < k1; ++k) {
+            const int p = __ldg(l_pose + k);
+            const double2 z = ldg2(l_uv + k);
+            double R[12];
+            const double2* cp = reinterpret_cast<const double2*>(cam + (size_t)p * 12);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { const double2 t = ldg2(cp + i); R[2 * i] = t.x; R[2 * i + 1] = t.y; }
+            ProjOut o;
+            project_factor<true, true>(cm, R, R + 9, lx, ly, lz, z.x, z.y, o);
+            c[0] += o.jl[0] * o.jl[0] + o.jl[3] * o.jl[3]; c[1] += o.jl[0] * o.jl[1] + o.jl[3] * o.jl[4];
+            c[2] += o.jl[0] * o.jl[2] + o.jl[3] * o.jl[5]; c[3] += o.jl[1] * o.jl[1] + o.jl[4] * o.jl[4];
+            c[4] += o.jl[1] * o.jl[2] + o.jl[4] * o.jl[5]; c[5] += o.jl[2] * o.jl[2] + o.jl[5] * o.jl[5];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) g[a] += o.jl[a] * o.b0 + o.jl[3 + a] * o.b1;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) wk[3 * r + a] += o.jk[r] * o.jl[a] + o.jk[6 + r] * o.jl[3 + a];
+        }
+        // PriorFactor<Point3> with Robust(Cauchy k, Diagonal sigma_lm)  (ArmSlamCalib.cpp:705, :1648-1651)
+        const double r0 = (lx - lm_prior[3 * (size_t)j]) * cm.inv_sigma_lm, r1 = (ly - lm_prior[3 * (size_t)j + 1]) * cm.inv_sigma_lm,
+                     r2 = (lz - lm_prior[3 * (size_t)j + 2]) * cm.inv_sigma_lm;
+        const double n2 = r0 * r0 + r1 * r1 + r2 * r2, w = cm.k2 / (cm.k2 + n2);
+        const double d = w * cm.inv_sigma_lm * cm.inv_sigma_lm;
+        c[0] += d; c[3] += d; c[5] += d;
+        g[0] -= w * r0 * cm.inv_sigma_lm; g[1] -= w * r1 * cm.inv_sigma_lm; g[2] -= w * r2 * cm.inv_sigma_lm;
+        err = 0.5 * w * n2;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) C[6 * (size_t)j + i] = c[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) gl[3 * (size_t)j + i] = g[i];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) WK[18 * (size_t)j + i] = wk[i];
+    }
+    // block partial of the prior error (fixed tree)
+    __shared__ double s[4];
+    err = warp_sum(err);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = err;
+    __syncthreads();
+    if (threadIdx.x == 0) blk_err[blockIdx.x] = s[0] + s[1] + s[2] + s[3];
+}
+
+// closed-form inverse of the symmetric 3x3 (xx,xy,xz,yy,yz,zz); false if not positive definite
+__device__ __forceinline__ bool spd3_inv(const double* c, double lambda, double* inv) {
+    const double a = c[0] + lambda, b = c[1], d = c[2], e = c[3] + lambda, f = c[4], g = c[5] + lambda;
+    const double d1 = e - b * b / a;
+    const double l21 = (f - d * b / a) / d1;
+    const double d2 = g - d * d / a - l21 * l21 * d1;
+    const double c00 = e * g - f * f, c01 = d * f - b * g, c02 = b * f - d * e;
+    const double id = 1.0 / (a * c00 + b * c01 + d * c02);
+    inv[0] = c00 * id; inv[1] = c01 * id; inv[2] = c02 * id;
+    inv[3] = (a * g - d * d) * id; inv[4] = (b * d - a * f) * id; inv[5] = (a * e - b * b) * id;
+    return (a > 0) && (d1 > 0) && (d2 > 0);
+}
+
+__device__ __forceinline__ void sym3_mul(const double* s, double x, double y, double z, double& ox, double& oy, double& oz) {
+    ox = s[0] * x + s[1] * y + s[2] * z; oy = s[1] * x + s[3] * y + s[4] * z; oz = s[2] * x + s[4] * y + s[5] * z;
+}
+
+// ------------------------------------------------------------------ K2a': damp + invert landmark blocks
+// Cinv_j = (C_j + lambda I)^-1, cg_j = Cinv_j g_j, and the per-block partials of
+// S_KK -= W_Kj Cinv_j W_Kj^T (21 sym) and rhs_K -= W_Kj cg_j (6).   One thread per landmark.
+__global__ void __launch_bounds__(128)
+landmark_invert_kernel(int L, double lambda, const double* __restrict__ C, const double* __restrict__ gl, const double* __restrict__ WK,
+                       double* __restrict__ Cinv, double* __restrict__ u4, double* __restrict__ blk_part, int* __restrict__ fail_idx) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double part[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) part[i] = 0.0;
+    if (j < L) {
+        double ci[6];
+        if (!spd3_inv(C + 6 * (size_t)j, lambda, ci)) atomicMin(fail_idx, j);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Cinv[6 * (size_t)j + i] = ci[i];
+        double gx, gy, gz;
+        sym3_mul(ci, gl[3 * (size_t)j], gl[3 * (size_t)j + 1], gl[3 * (size_t)j + 2], gx, gy, gz);
+        u4[4 * (size_t)j] = gx; u4[4 * (size_t)j + 1] = gy; u4[4 * (size_t)j + 2] = gz; u4[4 * (size_t)j + 3] = 0.0;
+        double W[18], Y[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) W[i] = WK[18 * (size_t)j + i];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) sym3_mul(ci, W[3 * r], W[3 * r + 1], W[3 * r + 2], Y[3 * r], Y[3 * r + 1], Y[3 * r + 2]);
+        int idx = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c) part[idx++] = Y[3 * r] * W[3 * c] + Y[3 * r + 1] * W[3 * c + 1] + Y[3 * r + 2] * W[3 * c + 2];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) part[21 + r] = W[3 * r] * gx + W[3 * r + 1] * gy + W[3 * r + 2] * gz;
+    }
+    __shared__ double s[4][kPartCols];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) {
+        const double t = warp_sum(part[i]);
+        if (lane == 0) s[warp][i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPartCols) blk_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = threadIdx.x < 27 ? s[0][threadIdx.x] + s[1][threadIdx.x] + s[2][threadIdx.x] + s[3][threadIdx.x] : 0.0;
+}
+
+// ------------------------------------------------------------------ load one observation's Jacobian planes
+template <int N>
+__device__ __forceinline__ void load_planes(const double2* __restrict__ J, int64_t M, int k, double (&f)[2 * N + 6]) {
+#pragma unroll
+    for (int i = 0; i < N + 3; ++i) {
+        const double2 t = ldg2(J + (size_t)i * M + k);
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+}
+
+// ------------------------------------------------------------------ Schur-diagonal blocks + reduced rhs (pose-major)
+// Per keyframe: Dloc_p = - sum_m J_q^T (J_l Cinv_j J_l^T) J_q  and  rloc_p = - sum_m J_q^T J_l (Cinv_j g_j)
+// (the parts of S_pp and of the reduced right-hand side that come from this rank's observations).
+template <int N>
+struct PrecSmem {
+    static constexpr int LD = GramCfg<N>::LD;
+    static constexpr int kPerWarpDoubles = 2 * 2 * 32 * LD + 64;
+    static constexpr size_t kBytes = sizeof(double) * kPerWarpDoubles * kWarpsPerCta;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kCtaThreads)
+pose_schur_diag_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm, const double2* __restrict__ J,
+                       const double* __restrict__ Cinv, const double* __restrict__ u4, double* __restrict__ Dloc, double* __restrict__ rloc) {
+    typedef GramCfg<N> Cf;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWarpsPerCta + warp;
+    if (p >= P) return;
+    double* s_U = smem + (size_t)warp * PrecSmem<N>::kPerWarpDoubles;   // Q J_q  [2][32][LD]
+    double* s_V = s_U + 2 * 32 * Cf::LD;                                // J_q    [2][32][LD]
+    double* s_e = s_V + 2 * 32 * Cf::LD;                                // e = J_l cg  [32][2]
+    double acc[Cf::H];
+#pragma unroll
+    for (int t = 0; t < Cf::H; ++t) acc[t] = 0.0;
+    double racc = 0.0;
+    const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+    for (int base = k0; base < k1; base += 32) {
+        const int k = base + lane, count = min(32, k1 - base);
+        if (k < k1) {
+            double f[2 * N + 6];
+            load_planes<N>(J, M, k, f);
+            const int j = __ldg(p_lm + k);
+            const double* ci = Cinv + 6 * (size_t)j;
+            const double* jl = f + 2 * N;
+            double t0x, t0y, t0z, t1x, t1y, t1z;
+            sym3_mul(ci, jl[0], jl[1], jl[2], t0x, t0y, t0z);
+            sym3_mul(ci, jl[3], jl[4], jl[5], t1x, t1y, t1z);
+            const double q00 = jl[0] * t0x + jl[1] * t0y + jl[2] * t0z, q01 = jl[0] * t1x + jl[1] * t1y + jl[2] * t1z;
+            const double q11 = jl[3] * t1x + jl[4] * t1y + jl[5] * t1z;
+            const double2 c01 = ldg2(reinterpret_cast<const double2*>(u4 + 4 * (size_t)j));
+            const double cz = __ldg(u4 + 4 * (size_t)j + 2);
+            s_e[2 * lane] = jl[0] * c01.x + jl[1] * c01.y + jl[2] * cz;
+            s_e[2 * lane + 1] = jl[3] * c01.x + jl[4] * c01.y + jl[5] * cz;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                s_V[(0 * 32 + lane) * Cf::LD + i] = f[i];
+                s_V[(1 * 32 + lane) * Cf::LD + i] = f[N + i];
+                s_U[(0 * 32 + lane) * Cf::LD + i] = q00 * f[i] + q01 * f[N + i];
+                s_U[(1 * 32 + lane) * Cf::LD + i] = q01 * f[i] + q11 * f[N + i];
+            }
+        }
+        __syncwarp();
+        gram_tile<N, false>(s_U, s_V, count, lane, acc);
+        {   // rhs: lanes of group g take row g (or both rows when one group)
+            const int g = lane / Cf::GS, c = lane % Cf::GS;
+            if (c < N)
+                for (int o = 0; o < count; ++o) {
+#pragma unroll
+                    for (int rr = 0; rr < 2 / Cf::G; ++rr) {
+                        const int r = Cf::G == 2 ? g : rr;
+                        racc = fma(s_V[(r * 32 + o) * Cf::LD + c], s_e[2 * o + r], racc);
+                    }
+                }
+        }
+        __syncwarp();
+    }
+    gram_finish<N>(acc);
+    if (Cf::G == 2) racc += __shfl_xor_sync(kFull, racc, 16);
+    if (lane < N) {
+        const int c = lane;
+        double* Dp = Dloc + (size_t)p * N * N;
+#pragma unroll
+        for (int t = 0; t < Cf::H; ++t) {
+            int c2 = c + t;
+            if (c2 >= N) c2 -= N;
+            Dp[c * N + c2] = -acc[t]; Dp[c2 * N + c] = -acc[t];
+        }
+        rloc[(size_t)p * N + c] = -racc;
+    }
+}
+
+// Minv_p = (B_pp + lambda I + Dsum_p)^-1 by in-shared-memory Gauss-Jordan (SPD, no pivoting); one warp per keyframe.
+// rhs_p = g_p + rsum_p.  Dsum/rsum are the (all-reduced) outputs of pose_schur_diag_kernel.
+template <int N>
+__global__ void __launch_bounds__(kCtaThreads)
+pose_invert_kernel(int P, double lambda, const double* __restrict__ Bpp, const double* __restrict__ gp, const double* __restrict__ Dsum,
+                   const double* __restrict__ rsum, double* __restrict__ Minv, double* __restrict__ rhs, int* __restrict__ fail_idx) {
+    __shared__ double sA[kWarpsPerCta][N][2 * N + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWarpsPerCta + warp;
+    if (p >= P) return;
+    double(*A)[2 * N + 1] = sA[warp];
+    for (int i = lane; i < N * N; i += 32) {
+        const int r = i / N, c = i % N;
+        A[r][c] = Bpp[(size_t)p * N * N + i] + Dsum[(size_t)p * N * N + i] + (r == c ? lambda : 0.0);
+        A[r][N + c] = r == c ? 1.0 : 0.0;
+    }
+    if (lane < N) rhs[(size_t)p * N + lane] = gp[(size_t)p * N + lane] + rsum[(size_t)p * N + lane];
+    __syncwarp();
+    bool ok = true;
+    for (int k = 0; k < N; ++k) {
+        const double piv = A[k][k];
+        ok = ok && (piv > 0);
+        const double ip = 1.0 / piv;
+        __syncwarp();
+        for (int c = lane; c < 2 * N; c += 32) A[k][c] *= ip;
+        __syncwarp();
+        for (int i = lane; i < N * 2 * N; i += 32) {
+            const int r = i / (2 * N), c = i % (2 * N);
+            if (r != k && c != k) A[r][c] -= A[r][k] * A[k][c];
+        }
+        __syncwarp();
+        for (int r = lane; r < N; r += 32) if (r != k) A[r][k] = 0.0;
+        __syncwarp();
+    }
+    for (int i = lane; i < N * N; i += 32) Minv[(size_t)p * N * N + i] = A[i / N][N + i % N];
+    if (!ok && lane == 0) atomicMin(fail_idx, p);
+}
+
+// ------------------------------------------------------------------ K3: implicit Schur complement  y = S x
+// pass A (pose-major): v_k = J_l^T (J_q x_p)            [optionally first p_p <- z_p + beta p_p]
+template <int N, bool UPDATE_P>
+__global__ void __launch_bounds__(kCtaThreads)
+schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const double2* __restrict__ J, double* __restrict__ x,
+                    const double* __restrict__ z, const double* __restrict__ scal, const int* __restrict__ done, double* __restrict__ v4) {
+    if (done && *done) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWarpsPerCta + warp;
+    if (p >= P) return;
+    double mine = 0.0;
+    if (lane < N) {
+        mine = x[(size_t)p * N + lane];
+        if (UPDATE_P) { mine = z[(size_t)p * N + lane] + scal[1] * mine; x[(size_t)p * N + lane] = mine; }   // scal[1] = beta
+    }
+    double xp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) xp[i] = __shfl_sync(kFull, mine, i);
+    const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+    for (int k = k0 + lane; k < k1; k += 32) {
+        double f[2 * N + 6];
+        load_planes<N>(J, M, k, f);
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { s0 = fma(f[i], xp[i], s0); s1 = fma(f[N + i], xp[i], s1); }
+        const double* jl = f + 2 * N;
+        double2* o = reinterpret_cast<double2*>(v4 + 4 * (size_t)k);
+        o[0] = make_double2(jl[0] * s0 + jl[3] * s1, jl[1] * s0 + jl[4] * s1);
+        o[1] = make_double2(jl[2] * s0 + jl[5] * s1, 0.0);
+    }
+}
+
+// pass B (landmark-major): u_j = Cinv_j (sum_k v + W_Kj^T x_K) [or cg_j - that, for back-substitution];
+// block partials of sum_j W_Kj u_j.   One thread per landmark.
+template <bool BACKSUB>
+__global__ void __launch_bounds__(128)
+schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const int* __restrict__ l_perm, const double* __restrict__ v4,
+                    const double* __restrict__ WK, const double* __restrict__ Cinv, const double* __restrict__ xK,
+                    const int* __restrict__ done, const double* __restrict__ cg4, double* __restrict__ u4, double* __restrict__ blk_part) {
+    if (done && *done) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double wu[6] = {0, 0, 0, 0, 0, 0};
+    if (j < L) {
+        double tx = 0, ty = 0, tz = 0;
+        const int k0 = lm_ptr[j], k1 = lm_ptr[j + 1];
+        for (int k = k0; k < k1; ++k) {
+            const int pk = __ldg(l_perm + k);
+            const double2 a = ldg2(reinterpret_cast<const double2*>(v4 + 4 * (size_t)pk));
+            const double c = __ldg(v4 + 4 * (size_t)pk + 2);
+            tx += a.x; ty += a.y; tz += c;
+        }
+        double W[18], xk[6];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) W[i] = WK[18 * (size_t)j + i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xk[i] = xK[i];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { tx += W[3 * r] * xk[r]; ty += W[3 * r + 1] * xk[r]; tz += W[3 * r + 2] * xk[r]; }
+        double ux, uy, uz;
+        sym3_mul(Cinv + 6 * (size_t)j, tx, ty, tz, ux, uy, uz);
+        if (BACKSUB) { ux = cg4[4 * (size_t)j] - ux; uy = cg4[4 * (size_t)j + 1] - uy; uz = cg4[4 * (size_t)j + 2] - uz; }
+        u4[4 * (size_t)j] = ux; u4[4 * (size_t)j + 1] = uy; u4[4 * (size_t)j + 2] = uz; u4[4 * (size_t)j + 3] = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) wu[r] = W[3 * r] * ux + W[3 * r + 1] * uy + W[3 * r + 2] * uz;
+    }
+    if (BACKSUB) return;
+    __shared__ double s[4][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const double t = warp_sum(wu[i]); if (lane == 0) s[warp][i] = t; }
+    __syncthreads();
+    if (threadIdx.x < kPartCols) blk_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = threadIdx.x < 6 ? s[0][threadIdx.x] + s[1][threadIdx.x] + s[2][threadIdx.x] + s[3][threadIdx.x] : 0.0;
+}
+
+// pass C (pose-major): yloc_p = - sum_m J_q^T (J_l u_j); then (if add_diag) y_p = (B_pp + lambda) x_p + B_pK x_K + yloc_p.
+// CTA partial row: [ sum_p B_pK^T x_p (6) | sum_p x_p . y_p (1) ]
+template <int N>
+__global__ void __launch_bounds__(kCtaThreads)
+schur_pass_c_kernel(int P, int64_t M, double lambda, int add_diag, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
+                    const double2* __restrict__ J, const double* __restrict__ u4, const double* __restrict__ x, const double* __restrict__ Bpp,
+                    const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part) {
+    if (done && *done) return;
+    __shared__ double s_part[kWarpsPerCta][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWarpsPerCta + warp;
+    if (lane < 8) s_part[warp][lane] = 0.0;
+    if (p < P) {
+        double acc[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = 0.0;
+        const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+        for (int k = k0 + lane; k < k1; k += 32) {
+            double f[2 * N + 6];
+            load_planes<N>(J, M, k, f);
+            const int j = __ldg(p_lm + k);
+            const double2 u01 = ldg2(reinterpret_cast<const double2*>(u4 + 4 * (size_t)j));
+            const double uz = __ldg(u4 + 4 * (size_t)j + 2);
+            const double* jl = f + 2 * N;
+            const double e0 = jl[0] * u01.x + jl[1] * u01.y + jl[2] * uz, e1 = jl[3] * u01.x + jl[4] * u01.y + jl[5] * uz;
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i] = fma(f[i], e0, fma(f[N + i], e1, acc[i]));
+        }
+        double mine = 0.0;   // lane c keeps component c
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const double t = warp_sum(acc[i]); if (lane == i) mine = -t; }
+        double xm = lane < N ? x[(size_t)p * N + lane] : 0.0;
+        if (add_diag) {
+            double xp[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) xp[i] = __shfl_sync(kFull, xm, i);
+            if (lane < N) {
+                const double* B = Bpp + (size_t)p * N * N + lane * N;
+                const double* BK = BpK + (size_t)p * N * 6 + lane * 6;
+                const double* xK = x + (size_t)P * N;
+                double t = lambda * xm;
+#pragma unroll
+                for (int i = 0; i < N; ++i) t = fma(B[i], xp[i], t);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) t = fma(BK[i], xK[i], t);
+                mine += t;
+            }
+            // B_pK^T x_p : lane c < 6 takes column c
+            double bk = 0.0;
+            if (lane < 6) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) bk = fma(BpK[(size_t)p * N * 6 + i * 6 + lane], xp[i], bk);
+                s_part[warp][lane] = bk;
+            }
+        }
+        if (lane < N) y[(size_t)p * N + lane] = mine;
+        const double dot = warp_sum(lane < N ? xm * mine : 0.0);
+        if (lane == 0) s_part[warp][6] = dot;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPartCols) {
+        double s = 0.0;
+        if (threadIdx.x < 7)
+#pragma unroll
+            for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w][threadIdx.x];
+        cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------ single-block helpers
+// sum rows [0,R) of a [R][kPartCols] partial array, fixed order; call with 256 threads. Result valid in all threads for col < 32.
+__device__ inline double block_reduce_rows(const double* __restrict__ part, int R, int col_lane, double (*s)[kPartCols]) {
+    const int warp = threadIdx.x >> 5;
+    double a = 0.0;
+    for (int r = warp; r < R; r += 8) a += part[(size_t)r * kPartCols + col_lane];
+    __syncthreads();
+    s[warp][col_lane] = a;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w][col_lane];
+    return t;
+}
+
+// Device-side PCG scalars: scal[0]=alpha, [1]=beta, [2]=rz, [3]=rz0, [4]=pSp, [5]=iterations, [6]=breakdown flag
+// Finish y = S p: gathers the K rows, alpha, and updates the K part of x, r, z.  One block of 256 threads.
+//   partC: CTA partials of pass C [nC][32] (cols 0..5 = sum B_pK^T p_p, col 6 = sum p_p.y_p)
+//   partB: block partials of pass B [nB][32] (cols 0..5 = sum W_Kj u_j)
+// Multi-GPU: the partial sums have been all-reduced already and arrive as a single row each (nC = nB = 1).
+__global__ void __launch_bounds__(256)
+pcg_mid_kernel(int P, int N, double lambda, const double* __restrict__ partC, int nC, const double* __restrict__ partB, int nB,
+               const double* __restrict__ BKK, const double* __restrict__ MinvK, double* __restrict__ p, double* __restrict__ x,
+               double* __restrict__ r, double* __restrict__ z, double* __restrict__ yK_out, double* __restrict__ scal, int* __restrict__ done) {
+    if (*done) return;
+    __shared__ double s[8][kPartCols];
+    __shared__ double sh[16];
+    const int lane = threadIdx.x & 31;
+    const double c = block_reduce_rows(partC, nC, lane, s);
+    const double b = block_reduce_rows(partB, nB, lane, s);
+    double* pK = p + (size_t)P * N;
+    if (threadIdx.x < 32) {
+        double yk = 0.0;
+        if (lane < 6) {
+            yk = lambda * pK[lane] + c - b;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) yk += BKK[6 * lane + i] * pK[i];
+        }
+        double dot = lane < 6 ? yk * pK[lane] : 0.0;
+        dot = warp_sum(dot);
+        const double cdot = __shfl_sync(kFull, c, 6);
+        const double pSp = cdot + dot;
+        const double alpha = scal[2] / pSp;
+        if (lane == 0) { scal[0] = alpha; scal[4] = pSp; if (!(pSp > 0)) { scal[6] = 1.0; } }
+        double rk = 0.0;
+        if (lane < 6) {
+            yK_out[lane] = yk;
+            x[(size_t)P * N + lane] += alpha * pK[lane];
+            rk = r[(size_t)P * N + lane] - alpha * yk;
+            r[(size_t)P * N + lane] = rk;
+            sh[lane] = rk;
+        }
+        __syncwarp();
+        if (lane < 6) {
+            double zk = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) zk += MinvK[6 * lane + i] * sh[i];
+            z[(size_t)P * N + lane] = zk;
+            sh[8 + lane] = zk * rk;
+        }
+        __syncwarp();
+        if (lane == 0) scal[7] = sh[8] + sh[9] + sh[10] + sh[11] + sh[12] + sh[13];   // r_K . z_K
+    }
+}
+
+// x_p += alpha p_p; r_p -= alpha y_p; z_p = Minv_p r_p; CTA partial of r_p . z_p.  One warp per keyframe.
+template <int N>
+__global__ void __launch_bounds__(kCtaThreads)
+pcg_update_kernel(int P, const double* __restrict__ p, const double* __restrict__ y, const double* __restrict__ Minv, double* __restrict__ x,
+                  double* __restrict__ r, double* __restrict__ z, const double* __restrict__ scal, const int* __restrict__ done,
+                  double* __restrict__ cta_part) {
+    if (*done) return;
+    __shared__ double s_part[kWarpsPerCta];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pp = blockIdx.x * kWarpsPerCta + warp;
+    double dot = 0.0;
+    if (pp < P) {
+        const double alpha = scal[0];
+        double rm = 0.0;
+        if (lane < N) {
+            const size_t i = (size_t)pp * N + lane;
+            x[i] += alpha * p[i];
+            rm = r[i] - alpha * y[i];
+            r[i] = rm;
+        }
+        double zm = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double ri = __shfl_sync(kFull, rm, i);
+            if (lane < N) zm = fma(Minv[(size_t)pp * N * N + lane * N + i], ri, zm);
+        }
+        if (lane < N) z[(size_t)pp * N + lane] = zm;
+        dot = warp_sum(lane < N ? rm * zm : 0.0);
+    }
+    if (lane == 0) s_part[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x < kPartCols) {
+        double s = 0.0;
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w];
+        cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
+    }
+}
+
+// rz_new, beta, convergence test, p_K <- z_K + beta p_K.  One block of 256 threads.
+__global__ void __launch_bounds__(256)
+pcg_end_kernel(int P, int N, const double* __restrict__ part, int nPart, double tol2, int max_iters, double* __restrict__ p,
+               const double* __restrict__ z, double* __restrict__ scal, int* __restrict__ done) {
+    if (*done) return;
+    __shared__ double s[8][kPartCols];
+    const int lane = threadIdx.x & 31;
+    const double t = block_reduce_rows(part, nPart, lane, s);
+    if (threadIdx.x < 32) {
+        const double rz_new = __shfl_sync(kFull, t, 0) + scal[7];
+        const double beta = rz_new / scal[2];
+        const double it = scal[5] + 1.0;
+        if (lane < 6) p[(size_t)P * N + lane] = z[(size_t)P * N + lane] + beta * p[(size_t)P * N + lane];
+        __syncwarp();
+        if (lane == 0) {
+            scal[1] = beta; scal[2] = rz_new; scal[5] = it;
+            if (!(rz_new > tol2 * scal[3]) || it >= max_iters || scal[6] != 0.0) *done = 1;
+        }
+    }
+}
+
+// PCG start: x = 0, r = rhs, z = Minv r, p = z, CTA partials of r.z  (one warp per keyframe); K part by block 0 / warp 0 extra.
+template <int N>
+__global__ void __launch_bounds__(kCtaThreads)
+pcg_init_kernel(int P, const double* __restrict__ rhs, const double* __restrict__ Minv, const double* __restrict__ MinvK, double* __restrict__ x,
+                double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ cta_part) {
+    __shared__ double s_part[kWarpsPerCta + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pp = blockIdx.x * kWarpsPerCta + warp;
+    double dot = 0.0;
+    if (pp < P) {
+        double rm = lane < N ? rhs[(size_t)pp * N + lane] : 0.0;
+        double zm = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double ri = __shfl_sync(kFull, rm, i);
+            if (lane < N) zm = fma(Minv[(size_t)pp * N * N + lane * N + i], ri, zm);
+        }
+        if (lane < N) {
+            const size_t i = (size_t)pp * N + lane;
+            x[i] = 0.0; r[i] = rm; z[i] = zm; p[i] = zm;
+        }
+        dot = warp_sum(lane < N ? rm * zm : 0.0);
+    }
+    if (lane == 0) s_part[warp] = dot;
+    if (blockIdx.x == 0 && warp == 0) {
+        double rk = lane < 6 ? rhs[(size_t)P * N + lane] : 0.0, zk = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const double ri = __shfl_sync(kFull, rk, i);
+            if (lane < 6) zk = fma(MinvK[6 * lane + i], ri, zk);
+        }
+        if (lane < 6) {
+            const size_t i = (size_t)P * N + lane;
+            x[i] = 0.0; r[i] = rk; z[i] = zk; p[i] = zk;
+        }
+        const double dk = warp_sum(lane < 6 ? rk * zk : 0.0);
+        if (lane == 0) s_part[kWarpsPerCta] = dk;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPartCols) {
+        double s = 0.0;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w];
+            if (blockIdx.x == 0) s += s_part[kWarpsPerCta];
+        }
+        cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pcg_init_end_kernel(const double* __restrict__ part, int nPart, double* __restrict__ scal, int* __restrict__ done) {
+    __shared__ double s[8][kPartCols];
+    const int lane = threadIdx.x & 31;
+    const double t = block_reduce_rows(part, nPart, lane, s);
+    if (threadIdx.x == 0) {
+        scal[0] = 0.0; scal[1] = 0.0; scal[2] = t; scal[3] = t; scal[4] = 0.0; scal[5] = 0.0; scal[6] = 0.0; scal[7] = 0.0;
+        *done = (t > 0.0) ? 0 : 1;   // zero right-hand side: nothing to do
+    }
+}
+
+// ------------------------------------------------------------------ reduced-system K rows (single block)
+// S_KK = B_KK + lambda I - sum_j W_Kj Cinv W_Kj^T ; rhs_K = g_K - sum_j W_Kj cg_j ; MinvK = S_KK^-1
+__global__ void __launch_bounds__(256)
+k_rows_kernel(double lambda, const double* __restrict__ part, int nPart, const double* __restrict__ BKK, const double* __restrict__ gK,
+              double* __restrict__ MinvK, double* __restrict__ rhsK, int* __restrict__ fail_idx) {
+    __shared__ double s[8][kPartCols];
+    __shared__ double A[6][13];
+    const int lane = threadIdx.x & 31;
+    const double t = block_reduce_rows(part, nPart, lane, s);
+    if (threadIdx.x < 32) {
+        // unpack the 21 symmetric entries
+        if (lane < 21) {
+            int r = 0, rem = lane;
+            while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+            const int c = r + rem;
+            const double v = BKK[6 * r + c] - t + (r == c ? lambda : 0.0);
+            A[r][c] = v; A[c][r] = v;
+        }
+        if (lane >= 21 && lane < 27) rhsK[lane - 21] = gK[lane - 21] - t;
+        for (int i = lane; i < 36; i += 32) A[i / 6][6 + i % 6] = (i / 6 == i % 6) ? 1.0 : 0.0;
+        __syncwarp();
+        bool ok = true;
+        for (int k = 0; k < 6; ++k) {
+            const double piv = A[k][k];
+            ok = ok && (piv > 0);
+            const double ip = 1.0 / piv;
+            __syncwarp();
+            if (lane < 12) A[k][lane] *= ip;
+            __syncwarp();
+            for (int i = lane; i < 72; i += 32) {
+                const int r = i / 12, c = i % 12;
+                if (r != k && c != k) A[r][c] -= A[r][k] * A[k][c];
+            }
+            __syncwarp();
+            if (lane < 6 && lane != k) A[lane][k] = 0.0;
+            __syncwarp();
+        }
+        for (int i = lane; i < 36; i += 32) MinvK[i] = A[i / 6][6 + i % 6];
+        if (!ok && lane == 0) atomicMin(fail_idx, 0);
+    }
+}
+
+// ------------------------------------------------------------------ linearisation finish (single block)
+// B_KK (full 6x6), g_K, total error from the CTA partials of the linearise kernel, the landmark-prior
+// error partials and the extrinsic prior (PriorFactor<Pose3>, J = I; ArmSlamCalib.cpp:684-685).
+__global__ void __launch_bounds__(256)
+linearize_finish_kernel(PriorConst pc, int add_priors, const double* __restrict__ X, const double* __restrict__ cta_part, int nPart,
+                        const double* __restrict__ lm_err, int nLmErr, double* __restrict__ BKK, double* __restrict__ gK, double* __restrict__ err_out) {
+    __shared__ double s[8][kPartCols];
+    __shared__ double sl[256];
+    const int lane = threadIdx.x & 31;
+    const double t = block_reduce_rows(cta_part, nPart, lane, s);
+    double e = 0.0;
+    for (int i = threadIdx.x; i < nLmErr; i += 256) e += lm_err[i];
+    sl[threadIdx.x] = e;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double xi[6] = {0, 0, 0, 0, 0, 0};
+        if (add_priors) pose3_local(pc.chart, pc.x_prior, X, xi);
+        if (lane < 21) {
+            int r = 0, rem = lane;
+            while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+            const int c = r + rem;
+            const double v = t + ((r == c && add_priors) ? pc.inv_sigma_x[r] * pc.inv_sigma_x[r] : 0.0);
+            BKK[6 * r + c] = v; BKK[6 * c + r] = v;
+        }
+        if (lane >= 21 && lane < 27) {
+            const int i = lane - 21;
+            gK[i] = t - (add_priors ? xi[i] * pc.inv_sigma_x[i] * pc.inv_sigma_x[i] : 0.0);
+        }
+        if (lane == 27) {
+            double le = 0.0;
+            for (int i = 0; i < 256; ++i) le += sl[i];
+            double pe = 0.0;
+            for (int i = 0; i < 6; ++i) { const double w = xi[i] * pc.inv_sigma_x[i]; pe += 0.5 * w * w; }
+            *err_out = t + le + pe;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K1e: error only
+// projection factors, one thread per observation (pose-major so neighbouring lanes share the camera row)
+__global__ void __launch_bounds__(256)
+error_proj_kernel(Camera cm, int64_t M, const int* __restrict__ p_pose, const int* __restrict__ p_lm, const double2* __restrict__ p_uv,
+                  const double* __restrict__ cam, const double* __restrict__ lm4, double* __restrict__ blk_err) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (k < M) {
+        const int p = __ldg(p_pose + k), j = __ldg(p_lm + k);
+        const double2 z = ldg2(p_uv + k);
+        double R[12];
+        const double2* cp = reinterpret_cast<const double2*>(cam + (size_t)p * 12);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const double2 t = ldg2(cp + i); R[2 * i] = t.x; R[2 * i + 1] = t.y; }
+        const double2 l01 = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j));
+        const double lz = __ldg(lm4 + 4 * (size_t)j + 2);
+        ProjOut o;
+        project_factor<false, false>(cm, R, R + 9, l01.x, l01.y, lz, z.x, z.y, o);
+        e = o.err;
+    }
+    __shared__ double s[8];
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) blk_err[blockIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+// encoder factors (thread per keyframe) and landmark priors (thread per landmark), block partials
+__global__ void __launch_bounds__(256)
+error_prior_kernel(Camera cm, PriorConst pc, int N, int P, int L, int with_enc, const double* __restrict__ q, const double* __restrict__ enc,
+                   const uint8_t* __restrict__ has_enc, const double* __restrict__ lm4, const double* __restrict__ lm_prior,
+                   double* __restrict__ blk_err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (i < P) {
+        if (with_enc && (has_enc == nullptr || has_enc[i])) {
+            for (int c = 0; c < N; ++c) {
+                const double qq = q[(size_t)i * N + c], ee = enc[(size_t)i * N + c];
+                double d = qq - ee;
+                if ((pc.continuous_mask >> c) & 1) d = atan2(sin(qq - ee), cos(qq - ee));
+                if (pc.use_dead_band) d = fabs(d) < pc.dead_band ? 0.0 : (d < 0 ? d + pc.dead_band : d - pc.dead_band);
+                const double w = d * pc.inv_sigma_enc[c];
+                e += 0.5 * w * w;
+            }
+        }
+    } else if (i < P + L) {
+        const int j = i - P;
+        const double r0 = (lm4[4 * (size_t)j] - lm_prior[3 * (size_t)j]) * cm.inv_sigma_lm, r1 = (lm4[4 * (size_t)j + 1] - lm_prior[3 * (size_t)j + 1]) * cm.inv_sigma_lm,
+                     r2 = (lm4[4 * (size_t)j + 2] - lm_prior[3 * (size_t)j + 2]) * cm.inv_sigma_lm;
+        const double n2 = r0 * r0 + r1 * r1 + r2 * r2;
+        e = 0.5 * (cm.k2 / (cm.k2 + n2)) * n2;
+    }
+    __shared__ double s[8];
+    e = warp_sum(e);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) blk_err[blockIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+// total = sum of block partials (+ extrinsic prior on rank 0).  One block, fixed order.
+__global__ void __launch_bounds__(256)
+error_finish_kernel(PriorConst pc, int with_prior, const double* __restrict__ X, const double* __restrict__ blk_err, int n, double* __restrict__ out) {
+    __shared__ double sl[256];
+    double e = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) e += blk_err[i];
+    sl[threadIdx.x] = e;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sl[threadIdx.x] += sl[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double pe = 0.0;
+        if (with_prior) {
+            double xi[6];
+            pose3_local(pc.chart, pc.x_prior, X, xi);
+            for (int i = 0; i < 6; ++i) { const double w = xi[i] * pc.inv_sigma_x[i]; pe += 0.5 * w * w; }
+        }
+        *out = sl[0] + pe;
+    }
+}
+
+// ------------------------------------------------------------------ K4: retract  (Values::retract)
+// q' = q + s_q dq, l' = l + s_l dl (padded rows), X' = X (+) dX     (RobotConfig.h:112-126, Point3, Pose3 chart)
+// delta = cu * du + cn * dn lets the Dogleg blend reuse the kernel (du may be null).
+__global__ void __launch_bounds__(256)
+retract_kernel(int chart, int64_t nq, int L, const double* __restrict__ q, const double* __restrict__ lm4, const double* __restrict__ X,
+               double cn, const double* __restrict__ nq_, const double* __restrict__ nl4, const double* __restrict__ nK, double cu,
+               const double* __restrict__ uq, const double* __restrict__ ul3, const double* __restrict__ uK, double* __restrict__ q2,
+               double* __restrict__ l2, double* __restrict__ X2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) q2[i] = q[i] + (cn * nq_[i] + (uq ? cu * uq[i] : 0.0));
+    if (i < (int64_t)L * 4) {
+        const int c = (int)(i & 3);
+        const int64_t j = i >> 2;
+        l2[i] = c == 3 ? 0.0 : lm4[i] + (cn * nl4[i] + (ul3 ? cu * ul3[3 * j + c] : 0.0));
+    }
+    if (i == 0) {
+        double xi[6], O[12], Xl[12];
+        for (int c = 0; c < 6; ++c) xi[c] = cn * nK[c] + (uK ? cu * uK[c] : 0.0);
+        for (int c = 0; c < 12; ++c) Xl[c] = X[c];
+        pose3_retract(chart, Xl, xi, O);
+        for (int c = 0; c < 12; ++c) X2[c] = O[c];
+    }
+}
+
+// ------------------------------------------------------------------ small dot products (deterministic)
+// out[slot] = sum a[i] * b[i]; block partials then a fixed tree by the caller's finish kernel.
+__global__ void __launch_bounds__(256)
+dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, int stride_a, int width_a, int stride_b, double* __restrict__ blk) {
+    // element e of the logical vector lives at a[(e / width_a) * stride_a + e % width_a]; same for b with width_a
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (e < n) {
+        const int64_t row = e / width_a;
+        const int col = (int)(e % width_a);
+        v = a[row * stride_a + col] * b[row * stride_b + col];
+    }
+    __shared__ double s[8];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) blk[blockIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+__global__ void __launch_bounds__(256) sum_kernel(const double* __restrict__ blk, int n, double* __restrict__ out) {
+    __shared__ double sl[256];
+    double e = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) e += blk[i];
+    sl[threadIdx.x] = e;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sl[threadIdx.x] += sl[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sl[0];
+}
+
+// ------------------------------------------------------------------ K5: Dogleg quadratic forms
+// per landmark: g_j^T C_j g_j + 2 g_K^T W_Kj g_j   (undamped C)
+__global__ void __launch_bounds__(256)
+dogleg_landmark_quad_kernel(int L, const double* __restrict__ C, const double* __restrict__ gl, const double* __restrict__ WK,
+                            const double* __restrict__ gK, double* __restrict__ blk) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (j < L) {
+        const double x = gl[3 * (size_t)j], y = gl[3 * (size_t)j + 1], z = gl[3 * (size_t)j + 2];
+        double ox, oy, oz;
+        sym3_mul(C + 6 * (size_t)j, x, y, z, ox, oy, oz);
+        v = x * ox + y * oy + z * oz;
+        const double* W = WK + 18 * (size_t)j;
+        for (int r = 0; r < 6; ++r) v += 2.0 * gK[r] * (W[3 * r] * x + W[3 * r + 1] * y + W[3 * r + 2] * z);
+    }
+    __shared__ double s[8];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) blk[blockIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+// copy gl [L][3] into a padded [L][4] vector
+__global__ void pad3to4_kernel(int L, const double* __restrict__ in3, double* __restrict__ out4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)L * 4) { const int c = (int)(i & 3); out4[i] = c == 3 ? 0.0 : in3[3 * (i >> 2) + c]; }
+}
+
+// gather pose-major per-observation data back to the caller's observation order (parity accessor)
+template <int N>
+__global__ void unpack_blocks_kernel(int64_t M, const int* __restrict__ p_orig, const double2* __restrict__ J, const double2* __restrict__ b,
+                                     double* __restrict__ b_out, double* __restrict__ jq_out, double* __restrict__ jl_out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const int64_t m = p_orig[k];
+    double f[2 * N + 6];
+    load_planes<N>(J, M, (int)k, f);
+    for (int i = 0; i < 2 * N; ++i) jq_out[m * 2 * N + i] = f[i];
+    for (int i = 0; i < 6; ++i) jl_out[m * 6 + i] = f[2 * N + i];
+    b_out[2 * m] = b[k].x; b_out[2 * m + 1] = b[k].y;
+}
+
+}  // namespace asck

@@ -1,0 +1,223 @@
+/*
+ * asc.h -- C ABI of the B200-native batch optimiser for arm_slam_calib graphs.
+ *
+ * This is the drop-in boundary.  Everything the reference does
+ * between "here is the factor graph and the current estimate" and "here is the new
+ * estimate" -- ArmSlamCalib::OptimizeStep(), src/ArmSlamCalib.cpp:429-533, i.e. the
+ * gtsam::LevenbergMarquardtOptimizer / gtsam::DoglegOptimizer calls at :443-449 and
+ * :460-465 -- is reachable through the entry points below.  The header-only facade in
+ * include/gtsam_facade/ packs a GTSAM-shaped graph into these calls.
+ *
+ * Conventions
+ *   - plain C, caller-owned host buffers, opaque handle, int status codes, no exceptions
+ *   - all floating point is IEEE double (GTSAM Vector/Matrix are double)
+ *   - rigid transforms are 12 doubles, row-major 3x4 [R | t]
+ *   - Pose3 tangent order is [omega(3), v(3)] (GTSAM convention)
+ *   - indices are int32, 0-based
+ *   - there is NO CPU fallback: every compute entry point fails with ASC_ERR_CUDA when
+ *     no sm_100 device is usable
+ */
+#ifndef ASC_H_
+#define ASC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASC_MAX_DOF 20 /* data/dof_experiments.py:17 sweeps 4..19 DOF */
+
+typedef struct asc_handle asc_handle;
+
+enum asc_status {
+    ASC_OK = 0,
+    ASC_ERR_INVALID = 1,       /* bad argument / call order */
+    ASC_ERR_CUDA = 2,          /* no device, launch or allocation failure */
+    ASC_ERR_INDETERMINATE = 3, /* gtsam::IndeterminantLinearSystemException, ArmSlamCalib.cpp:451 */
+    ASC_ERR_COMM = 4           /* NCCL failure */
+};
+
+/* optimization_mode, include/arm_slam_calib/ArmSlamCalib.h:59-64 (ISAM is out of scope) */
+enum asc_mode { ASC_BATCH_LM = 0, ASC_BATCH_DOGLEG = 1 };
+
+/* [DEP] GTSAM build flags that change Pose3 retract/localCoordinates */
+enum asc_pose3_chart {
+    ASC_POSE3_FIRST_ORDER_CAYLEY = 0, /* GTSAM 3.2 default build */
+    ASC_POSE3_FIRST_ORDER_EXPMAP = 1, /* GTSAM_ROT3_EXPMAP */
+    ASC_POSE3_FULL_EXPMAP = 2         /* GTSAM_POSE3_EXPMAP */
+};
+
+/* Noise / robust-loss parameters; defaults = ArmSlamCalib::Params(), ArmSlamCalib.h:69-105 */
+typedef struct asc_params {
+    double sigma_px;                 /* projectionNoiseLevel, ArmSlamCalib.h:86 (1.0) */
+    double sigma_landmark;           /* landmarkNoiseLevel, ArmSlamCalib.h:83 (50.0) */
+    double cauchy_k;                 /* cauchy_multiplier, ArmSlamCalib.cpp:197-198 (3.0) */
+    double sigma_encoder[ASC_MAX_DOF]; /* encoderNoiseLevel per joint, ArmSlamCalib.cpp:672-677 (0.1) */
+    double sigma_extrinsic[6];       /* PriorFactor<Pose3> sigmas in tangent order, ArmSlamCalib.cpp:684 */
+    int32_t use_dead_band;           /* useDeadBand, ArmSlamCalib.h:94 (0) */
+    double dead_band;                /* deadBandSize, ArmSlamCalib.h:96 (0.05) */
+    int32_t pose3_chart;             /* enum asc_pose3_chart */
+    /* optimiser parameters: GTSAM 3.2 defaults */
+    int32_t max_iterations;          /* 100 */
+    double relative_error_tol;       /* 1e-5 */
+    double absolute_error_tol;       /* 1e-5 */
+    double error_tol;                /* 0 */
+    double lambda_initial;           /* 1e-5 */
+    double lambda_factor;            /* 10 */
+    double lambda_upper_bound;       /* 1e5 */
+    double lambda_lower_bound;       /* 0 */
+    double min_model_fidelity;       /* 1e-3 */
+    double delta_initial;            /* Dogleg trust region, 1.0 */
+    /* linear solver (replaces SEQUENTIAL_CHOLESKY, ArmSlamCalib.cpp:461) */
+    double pcg_rel_tol;              /* ||r||_M^-1 / ||b||_M^-1 stopping ratio (1e-12) */
+    int32_t pcg_max_iters;           /* 2000 */
+    int32_t device;                  /* CUDA device ordinal, -1 = current */
+} asc_params;
+
+/* One record per outer iterate() of the optimiser */
+typedef struct asc_iter_log {
+    int32_t iteration;     /* 1-based */
+    int32_t inner_steps;   /* damped solves (LM) or trust-region tries (Dogleg) in this iterate() */
+    int32_t accepted;      /* 1 if the estimate moved */
+    int32_t pcg_iterations;/* summed over inner steps */
+    double error;          /* graph.error(values) after the iteration */
+    double lambda_or_delta;/* lambda (LM) or Delta (Dogleg) after the iteration */
+    double linearize_ms;   /* device time of the linearisation + assembly kernels */
+    double solve_ms;       /* device time of Schur/PCG/back-substitution */
+} asc_iter_log;
+
+typedef struct asc_linear_stats {
+    double error;          /* 0.5 * sum ||whitened, reweighted residual||^2 over all factors */
+    double linearize_ms;   /* device time of the FK + projection-linearise kernel(s) only */
+    double assemble_ms;    /* device time of landmark/pose block assembly */
+    int64_t cheirality;    /* number of projection factors that hit the z<0.01 guard */
+} asc_linear_stats;
+
+void asc_default_params(asc_params* p);
+const char* asc_last_error(void);
+const char* asc_version(void);
+
+int asc_create(const asc_params* params, asc_handle** out);
+int asc_destroy(asc_handle* h);
+
+/*
+ * Serial revolute chain; replaces the DART skeleton/group the factors hold
+ * (RobotProjectionFactor.h:33-35, ArmSlamCalib.cpp:224-272).  Joint i:
+ *   T_world<-child(i) = T_world<-parent(i) * T_p2j[i] * Rot(axis[i], q[i]) * inverse(T_c2j[i])
+ * The camera link is child(N-1).  t_base (nullable) places the chain root.
+ */
+int asc_set_chain(asc_handle* h, int32_t n_dof, const double* t_p2j /*[N][12]*/,
+                  const double* axis /*[N][3]*/, const double* t_c2j /*[N][12]*/,
+                  const uint8_t* continuous /*[N], RobotConfig.h:72-77*/,
+                  const double* t_base /*[12] or NULL*/);
+
+/* Cal3_S2(fx, fy, 0, cx, cy), ArmSlamCalib.cpp:670 */
+int asc_set_camera(asc_handle* h, double fx, double fy, double cx, double cy);
+
+/*
+ * The factor graph, flattened.  Observation m is RobotProjectionFactor(uv[m], q_{pose_idx[m]},
+ * l_{lm_idx[m]}, K0) (ArmSlamCalib.cpp:1625-1646); pose p has EncoderFactor(enc[p]) iff
+ * has_enc[p] (ArmSlamCalib.cpp:299-305; NULL = all); landmark j has PriorFactor<Point3>
+ * (lm_prior[j]) (ArmSlamCalib.cpp:1648-1651); K0 has PriorFactor<Pose3>(x_prior) (:685).
+ * The order of the observation list is preserved in every per-observation output.
+ */
+int asc_set_problem(asc_handle* h, int32_t n_poses, int32_t n_landmarks, int64_t n_obs,
+                    const int32_t* pose_idx, const int32_t* lm_idx, const double* uv /*[M][2]*/,
+                    const double* enc /*[P][N]*/, const uint8_t* has_enc /*[P] or NULL*/,
+                    const double* lm_prior /*[L][3]*/, const double* x_prior /*[12]*/);
+
+/* Values: q_i (RobotConfig), l_j (Point3), K0 (Pose3) */
+int asc_set_values(asc_handle* h, const double* q /*[P][N]*/, const double* l /*[L][3]*/,
+                   const double* x /*[12]*/);
+int asc_get_values(asc_handle* h, double* q, double* l, double* x);
+
+/* NonlinearFactorGraph::error(values) */
+int asc_error(asc_handle* h, double* error);
+
+/* NonlinearFactorGraph::linearize(values) + block assembly; exposed for the
+ * "factor linearisations/s" metric and per-kernel parity */
+int asc_linearize(asc_handle* h, asc_linear_stats* stats);
+
+/* {LevenbergMarquardt,Dogleg}Optimizer::optimize(); the estimate is updated in place */
+int asc_optimize(asc_handle* h, int32_t mode, asc_iter_log* log, int32_t log_capacity,
+                 int32_t* n_iterations, double* final_error);
+
+/* key of the variable named by the last ASC_ERR_INDETERMINATE:
+ * kind 'l' / 'q' / 'K', index as in Symbol(kind, index) (ArmSlamCalib.h:284-286) */
+int asc_indeterminate_key(asc_handle* h, char* kind, int64_t* index);
+
+/* ---- parity / inspection accessors (valid after asc_linearize) ------------------- */
+/* whitened + reweighted per-observation blocks, original observation order */
+int asc_get_projection_blocks(asc_handle* h, double* b /*[M][2]*/, double* jq /*[M][2][N]*/,
+                              double* jl /*[M][2][3]*/);
+/* undamped landmark blocks: C_j (3x3 full), g_l (3), W_Kj (6x3) */
+int asc_get_landmark_blocks(asc_handle* h, double* c /*[L][9]*/, double* gl /*[L][3]*/,
+                            double* wk /*[L][18]*/);
+/* undamped pose blocks: B_pp (NxN full), B_pK (Nx6), g_p (N); and B_KK (6x6), g_K (6) */
+int asc_get_pose_blocks(asc_handle* h, double* bpp /*[P][N][N]*/, double* bpk /*[P][N][6]*/,
+                        double* gp /*[P][N]*/, double* bkk /*[36]*/, double* gk /*[6]*/);
+/* Solve (H + lambda I) delta = g with the device Schur/PCG path; delta_q [P][N], delta_l [L][3],
+ * delta_x [6].  Returns the PCG iteration count. */
+int asc_solve_damped(asc_handle* h, double lambda, double* delta_q, double* delta_l,
+                     double* delta_x, int32_t* pcg_iterations);
+
+/* ---- multi-GPU: landmark sharding --------------------------- */
+/* Size in bytes of the opaque communicator id (ncclUniqueId). */
+int asc_comm_id_size(void);
+/* rank 0 creates the id; the caller broadcasts the bytes (e.g. torch.distributed). */
+int asc_comm_create_id(void* id_bytes);
+/* Collective: every rank calls with the same id.  After this, asc_set_problem expects only this
+ * rank's shard of landmarks/observations (see asc_shard_by_landmark) with q/enc replicated. */
+int asc_comm_init(asc_handle* h, int32_t rank, int32_t world_size, const void* id_bytes);
+/* Host-side partitioner: contiguous landmark ranges balanced by observation count.
+ * lm_begin[r], lm_begin[r+1] bound rank r's landmark ids. */
+int asc_shard_by_landmark(int32_t n_landmarks, int64_t n_obs, const int32_t* lm_idx,
+                          int32_t world_size, int32_t* lm_begin /*[world_size+1]*/);
+
+/* ---- synthetic problems (host side; ArmSlamCalib.cpp:535-602, :654-706, :1773-1887) ---- */
+typedef struct asc_sim_config {
+    int32_t trajectory_size;   /* trajectory_length, ArmSlamCalib.h:70 */
+    int32_t num_landmarks_x, num_landmarks_y; /* ArmSlamCalib.h:71-72 */
+    double landmark_size_x, landmark_size_y;  /* ArmSlamCalib.h:73-74 */
+    double landmark_z_min, landmark_z_max;    /* utils::Rand(-5, 5), ArmSlamCalib.cpp:662 */
+    double max_range;          /* [NEW] visibility thinning, 0 = none */
+    double encoder_noise;      /* encoderNoiseLevel */
+    double velocity_noise;     /* velocityNoiseLevel */
+    int32_t seed;              /* ros param "seed", ArmSlamCalib.cpp:193,:542 */
+    int32_t min_observations;  /* admission rule observations.size() > 3, ArmSlamCalib.cpp:1860 */
+    double sim_extrinsic[12];  /* simExtrinsic (ground truth) */
+    double extrinsic_guess[12];/* extrinsicInitialGuess */
+} asc_sim_config;
+
+typedef struct asc_sim_problem asc_sim_problem;
+
+void asc_sim_default_config(asc_sim_config* c);
+/* chain fixtures: writes N x {t_p2j[12], axis[3], t_c2j[12]}; returns N or <0 */
+int asc_chain_mico(double* t_p2j, double* axis, double* t_c2j);
+/* RobotGenerator::GenerateRobot(numDof, scale, growth, randomLength, randomAngle, false, 6),
+ * src/RobotGenerator.cpp:22-147; consumes rand() like the reference (call srand first) */
+int asc_chain_generate(int32_t n_dof, double scale, double growth, double random_length,
+                       double random_angle, double* t_p2j, double* axis, double* t_c2j);
+
+int asc_sim_create(const asc_sim_config* cfg, int32_t n_dof, const double* t_p2j,
+                   const double* axis, const double* t_c2j, double fx, double fy, double cx,
+                   double cy, asc_sim_problem** out);
+void asc_sim_destroy(asc_sim_problem* s);
+/* sizes: P, L (landmarks in graph), M, L_sim (all simulated landmarks) */
+int asc_sim_sizes(const asc_sim_problem* s, int32_t* n_poses, int32_t* n_landmarks,
+                  int64_t* n_obs, int32_t* n_sim_landmarks);
+/* copies out the flattened graph; lm_id[j] is the reference landmark id of compact index j;
+ * factor_order[m] is the position of observation m in the reference's graph (AddFactor order) */
+int asc_sim_export(const asc_sim_problem* s, int32_t* pose_idx, int32_t* lm_idx, double* uv,
+                   double* enc, double* q_truth, double* lm_truth, int32_t* lm_id,
+                   int64_t* factor_order);
+
+/* host forward kinematics of the chain (used by the generator; exported for tests) */
+int asc_chain_fk(int32_t n_dof, const double* t_p2j, const double* axis, const double* t_c2j,
+                 const double* q, double* t_link /*[12]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASC_H_ */
