@@ -31,6 +31,8 @@ class AscParams(C.Structure):
         ("pcg_rel_tol", C.c_double),
         ("pcg_max_iters", C.c_int32),
         ("device", C.c_int32),
+        ("pcg_cluster_max", C.c_int32),
+        ("pcg_cluster_covis", C.c_double),
     ]
 
 
@@ -72,4 +74,5 @@ class AscSimConfig(C.Structure):
         ("min_observations", C.c_int32),
         ("sim_extrinsic", C.c_double * 12),
         ("extrinsic_guess", C.c_double * 12),
+        ("segment_length", C.c_int32),
     ]

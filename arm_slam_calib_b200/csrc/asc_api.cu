@@ -113,11 +113,18 @@ struct asc_handle {
     double *Minv = nullptr, *MinvK = nullptr, *rhs = nullptr;
     double *vx = nullptr, *vr = nullptr, *vz = nullptr, *vp = nullptr;
     double *ybuf = nullptr;      // [y (PN) | yK(6) pad to 8 | rowC(32) | rowB(32)]
-    double *partA = nullptr, *partB = nullptr, *partC = nullptr, *partL = nullptr, *errblk = nullptr;
+    double *partA = nullptr, *partB = nullptr, *partC = nullptr, *partL = nullptr, *partR = nullptr, *errblk = nullptr;
     int nCtaPose = 0, nBlkLm = 0, nErrBlk = 0;
     double *scal = nullptr, *status = nullptr;
     int *flags = nullptr;        // [0] pcg done, [1] landmark fail idx, [2] pose fail idx, [3] K fail
     unsigned long long* cheir = nullptr;
+    // cluster-Jacobi preconditioner
+    bool use_clusters = false;
+    int nC = 0, nmax = 0;
+    size_t scTotal = 0, regionA = 0;
+    int *cl_ptr = nullptr, *pose_cluster = nullptr, *p_run_lo = nullptr, *p_run_hi = nullptr;
+    long long* cl_off = nullptr;
+    double *Wm = nullptr, *Mc = nullptr;
     double* h_status = nullptr;  // pinned: status(32) + scal(8)
     int* h_flags = nullptr;      // pinned
 };
@@ -179,6 +186,8 @@ struct Engine {
         CUDA_TRY(cudaFuncSetAttribute(linearize_pose_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<N>::kBytes));
         CUDA_TRY(cudaFuncSetAttribute(linearize_pose_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<N>::kBytes));
         CUDA_TRY(cudaFuncSetAttribute(pose_schur_diag_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PrecSmem<N>::kBytes));
+        CUDA_TRY(cudaFuncSetAttribute(cluster_schur_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(cluster_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         done = true;
         return ASC_OK;
     }
@@ -205,7 +214,10 @@ struct Engine {
         landmark_blocks_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->cm, h->L, h->lm_ptr, h->l_pose, h->l_uv, h->cam, h->lm4, h->lm_prior, h->C,
                                                                 h->gl, h->WK, h->errblk);
         CUDA_TRY(cudaGetLastError());
-        linearize_finish_kernel<<<1, 256, 0, h->stream>>>(h->pc, add_priors, h->X, h->partA, h->nCtaPose, h->errblk, h->nBlkLm, h->BKK,
+        const int nR1 = std::min(64, h->nCtaPose), rpb = cdiv(h->nCtaPose, nR1);
+        reduce_rows_kernel<<<cdiv(h->nCtaPose, rpb), 256, 0, h->stream>>>(h->partA, h->nCtaPose, 28, kPartCols, rpb, h->partR);
+        CUDA_TRY(cudaGetLastError());
+        linearize_finish_kernel<<<1, 256, 0, h->stream>>>(h->pc, add_priors, h->X, h->partR, cdiv(h->nCtaPose, rpb), h->errblk, h->nBlkLm, h->BKK,
                                                          h->gr + (size_t)h->P * N, h->err_lin);
         CUDA_TRY(cudaGetLastError());
         if (h->world > 1) {
@@ -215,6 +227,10 @@ struct Engine {
         }
         pad3to4_kernel<<<cdiv((int64_t)h->L * 4, 256), 256, 0, h->stream>>>(h->L, h->gl, h->gl4);
         CUDA_TRY(cudaGetLastError());
+        if (h->use_clusters && h->M) {
+            obs_w_kernel<N><<<cdiv(h->M, 256), 256, 0, h->stream>>>(h->M, h->J, h->Wm);
+            CUDA_TRY(cudaGetLastError());
+        }
         CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
         h->linearized = true;
         h->lin_lambda = -1.0;
@@ -233,22 +249,37 @@ struct Engine {
         CUDA_TRY(cudaMemcpyAsync(h->flags, init_flags, sizeof init_flags, cudaMemcpyHostToDevice, h->stream));
         landmark_invert_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->L, lambda, h->C, h->gl, h->WK, h->Cinv, h->cg4, h->partL, h->flags + 1);
         CUDA_TRY(cudaGetLastError());
-        pose_schur_diag_kernel<N><<<h->nCtaPose, kCtaThreads, PrecSmem<N>::kBytes, h->stream>>>(h->P, h->M, h->pose_ptr, h->p_lm, h->J, h->Cinv, h->cg4,
-                                                                                              h->Dloc, h->rloc);
+        if (h->use_clusters) {
+            const size_t sm = sizeof(double) * kWarpsPerCta * ((size_t)N * h->nmax + 3 * N);
+            cluster_schur_kernel<N><<<h->nCtaPose, kCtaThreads, sm, h->stream>>>(h->P, lambda, h->rank == 0 ? 1 : 0, h->nmax, h->pose_ptr, h->p_lm,
+                                                                               h->p_run_lo, h->p_run_hi, h->l_pose, h->l_perm, h->Wm, h->Cinv, h->cg4,
+                                                                               h->Bpp, h->pose_cluster, h->cl_ptr, h->cl_off, h->Dloc, h->rloc);
+        } else {
+            pose_schur_diag_kernel<N><<<h->nCtaPose, kCtaThreads, PrecSmem<N>::kBytes, h->stream>>>(h->P, h->M, h->pose_ptr, h->p_lm, h->J, h->Cinv, h->cg4,
+                                                                                                  h->Dloc, h->rloc);
+        }
         CUDA_TRY(cudaGetLastError());
-        const double* kpart = h->partL;
-        int nk = h->nBlkLm;
+        const int nR1 = std::min(64, h->nBlkLm), rpb = cdiv(h->nBlkLm, nR1);
+        reduce_rows_kernel<<<cdiv(h->nBlkLm, rpb), 256, 0, h->stream>>>(h->partL, h->nBlkLm, 27, kPartCols, rpb, h->partR);
+        CUDA_TRY(cudaGetLastError());
+        const double* kpart = h->partR;
+        int nk = cdiv(h->nBlkLm, rpb);
         if (h->world > 1) {
-            reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partL, h->nBlkLm, 27, kPartCols, h->nBlkLm, h->krow);
+            reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partR, nk, 27, kPartCols, nk, h->krow);
             CUDA_TRY(cudaGetLastError());
-            int rc = allreduce(h, h->precblk, (size_t)h->P * (N * N + N) + kPartCols);
+            int rc = allreduce(h, h->precblk, h->regionA + (size_t)h->P * N + kPartCols);
             if (rc) return rc;
             kpart = h->krow;
             nk = 1;
         }
         k_rows_kernel<<<1, 256, 0, h->stream>>>(lambda, kpart, nk, h->BKK, h->gr + (size_t)h->P * N, h->MinvK, h->rhs + (size_t)h->P * N, h->flags + 3);
         CUDA_TRY(cudaGetLastError());
-        pose_invert_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, lambda, h->Bpp, h->gr, h->Dloc, h->rloc, h->Minv, h->rhs, h->flags + 2);
+        if (h->use_clusters) {
+            const size_t sm = sizeof(double) * (size_t)h->nmax * (h->nmax | 1);
+            cluster_invert_kernel<<<h->nC, 256, sm, h->stream>>>(N, h->cl_ptr, h->cl_off, h->Dloc, h->gr, h->rloc, h->Mc, h->rhs, h->flags + 2);
+        } else {
+            pose_invert_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, lambda, h->Bpp, h->gr, h->Dloc, h->rloc, h->Minv, h->rhs, h->flags + 2);
+        }
         CUDA_TRY(cudaGetLastError());
         h->lin_lambda = lambda;
         return ASC_OK;
@@ -273,9 +304,18 @@ struct Engine {
     // block-Jacobi PCG on the reduced system; solution left in vx.  Returns iterations through *iters.
     static int pcg(asc_handle* h, double lambda, int* iters) {
         const size_t PN = (size_t)h->P * N;
-        pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
-        CUDA_TRY(cudaGetLastError());
-        pcg_init_end_kernel<<<1, 256, 0, h->stream>>>(h->partA, h->nCtaPose, h->scal, h->flags);
+        const int nUpd = h->use_clusters ? h->nC : h->nCtaPose;
+        if (h->use_clusters) {
+            pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(1, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp, h->scal,
+                                                                  h->flags, h->partA);
+            pcg_init_k_kernel<<<1, 32, 0, h->stream>>>((int64_t)PN, h->rhs, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->status + 40);
+            CUDA_TRY(cudaGetLastError());
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags);
+        } else {
+            pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
+            CUDA_TRY(cudaGetLastError());
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags);
+        }
         CUDA_TRY(cudaGetLastError());
         const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
         const int chunk = 8;
@@ -290,19 +330,23 @@ struct Engine {
                 if (h->world > 1) {
                     double* rowC = h->ybuf + PN + 8;
                     double* rowB = rowC + kPartCols;
-                    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPartCols, h->nCtaPose, rowC);
-                    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partB, h->nBlkLm, 6, kPartCols, h->nBlkLm, rowB);
+                    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, h->nCtaPose, rowC);
+                    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partB, h->nBlkLm, 6, kPcgCols, h->nBlkLm, rowB);
                     CUDA_TRY(cudaGetLastError());
                     rc = allreduce(h, h->ybuf, PN + 8 + 2 * kPartCols);
                     if (rc) return rc;
                     pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
                 }
-                pcg_mid_kernel<<<1, 256, 0, h->stream>>>(h->P, N, lambda, pc_, nC, pb_, nB, h->BKK, h->MinvK, h->vp, h->vx, h->vr, h->vz,
+                pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, pc_, nC, pb_, nB, h->BKK, h->MinvK, h->vp, h->vx, h->vr, h->vz,
                                                         h->ybuf + PN, h->scal, h->flags);
                 CUDA_TRY(cudaGetLastError());
-                pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
+                if (h->use_clusters)
+                    pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
+                                                                          h->scal, h->flags, h->partA);
+                else
+                    pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
                 CUDA_TRY(cudaGetLastError());
-                pcg_end_kernel<<<1, 256, 0, h->stream>>>(h->P, N, h->partA, h->nCtaPose, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags);
+                pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, h->partA, nUpd, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags);
                 CUDA_TRY(cudaGetLastError());
             }
             launched += chunk;
@@ -547,7 +591,7 @@ int dogleg_gHg(asc_handle* h, double* out) {
     const size_t PN = (size_t)h->P * N;
     int rc = dispatch_schur_c(h, 0.0, h->gr, h->gl4);   // yloc = -W g_l ; partC col 6 = sum g_p . yloc_p
     if (rc) return rc;
-    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPartCols, h->nCtaPose, h->status + 16);   // [16+6] = T1
+    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, h->nCtaPose, h->status + 16);   // [16+6] = T1
     const int nbp = cdiv(h->P, 256), nbl = cdiv(h->L, 256);
     dogleg_pose_quad_kernel<<<nbp, 256, 0, h->stream>>>(h->P, N, h->Bpp, h->BpK, h->gr, h->errblk);
     dogleg_landmark_quad_kernel<<<std::max(nbl, 1), 256, 0, h->stream>>>(h->L, h->C, h->gl, h->WK, h->gr + PN, h->errblk + nbp);
@@ -670,6 +714,8 @@ void asc_default_params(asc_params* p) {
     p->pcg_rel_tol = 1e-12;
     p->pcg_max_iters = 2000;
     p->device = -1;
+    p->pcg_cluster_max = 10;
+    p->pcg_cluster_covis = 0.25;
 }
 
 const char* asc_last_error(void) { return g_last_error.c_str(); }
@@ -776,13 +822,72 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             p_lm[k] = lm_idx[m]; p_pose[k] = pose_idx[m]; p_orig[k] = (int)m; pos_of[m] = k;
             p_uv[2 * k] = uv[2 * m]; p_uv[2 * k + 1] = uv[2 * m + 1];
         }
+        // landmark-major: inside a landmark, observations ordered by keyframe (then by list order)
         std::vector<int> fl(lm_ptr.begin(), lm_ptr.end() - 1);
-        for (int64_t m = 0; m < M; ++m) {
+        for (int64_t kp = 0; kp < M; ++kp) {
+            const int m = p_orig[kp];
             const int k = fl[lm_idx[m]]++;
-            l_pose[k] = pose_idx[m]; l_perm[k] = pos_of[m];
+            l_pose[k] = pose_idx[m]; l_perm[k] = (int)kp;
             l_uv[2 * k] = uv[2 * m]; l_uv[2 * k + 1] = uv[2 * m + 1];
         }
     }
+    // ---- preconditioner clusters: runs of consecutive keyframes that share landmarks
+    const int gmax = std::max(1, std::min(pr.pcg_cluster_max, 128 / N));
+    h->use_clusters = gmax > 1;
+    std::vector<int> cl_ptr, pose_cluster(P, 0), run_lo, run_hi;
+    std::vector<long long> cl_off;
+    if (h->use_clusters) {
+        std::vector<double> cnt(2 * (size_t)P, 0.0);   // [shared with previous | own count], as doubles for the all-reduce
+        std::vector<int> mark(std::max(L, 1), -2);
+        for (int p = 0; p < P; ++p) {
+            int shared = 0;
+            for (int k = pose_ptr[p]; k < pose_ptr[p + 1]; ++k) {
+                const int j = p_lm[k];
+                if (mark[j] == p - 1) ++shared;
+            }
+            for (int k = pose_ptr[p]; k < pose_ptr[p + 1]; ++k) mark[p_lm[k]] = p;
+            cnt[p] = shared; cnt[P + p] = pose_ptr[p + 1] - pose_ptr[p];
+        }
+        if (h->world > 1) {   // every rank must build the same clusters: sum the shard-local counts
+            double* d = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&d, cnt.size() * sizeof(double)));
+            CUDA_TRY(cudaMemcpyAsync(d, cnt.data(), cnt.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            int rc2 = allreduce(h, d, cnt.size());
+            if (rc2) { cudaFree(d); return rc2; }
+            CUDA_TRY(cudaMemcpyAsync(cnt.data(), d, cnt.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            cudaFree(d);
+        }
+        int size = 0;
+        for (int p = 0; p < P; ++p) {
+            const double mn = p > 0 ? std::min(cnt[P + p], cnt[P + p - 1]) : 0.0;
+            const bool joined = p > 0 && size < gmax && mn > 0 && cnt[p] >= pr.pcg_cluster_covis * mn;
+            if (!joined) { cl_ptr.push_back(p); size = 0; }
+            ++size;
+            pose_cluster[p] = (int)cl_ptr.size() - 1;
+        }
+        cl_ptr.push_back(P);
+        h->nC = (int)cl_ptr.size() - 1;
+        cl_off.assign(h->nC + 1, 0);
+        h->nmax = 0;
+        for (int c = 0; c < h->nC; ++c) {
+            const long long n = (long long)(cl_ptr[c + 1] - cl_ptr[c]) * N;
+            cl_off[c + 1] = cl_off[c] + n * n;
+            h->nmax = std::max(h->nmax, (int)n);
+        }
+        h->scTotal = (size_t)cl_off[h->nC];
+        run_lo.assign(M, 0); run_hi.assign(M, 0);
+        for (int j = 0; j < L; ++j) {
+            int a = lm_ptr[j];
+            while (a < lm_ptr[j + 1]) {
+                int b = a + 1;
+                const int cid = pose_cluster[l_pose[a]];
+                while (b < lm_ptr[j + 1] && pose_cluster[l_pose[b]] == cid) ++b;
+                for (int kk = a; kk < b; ++kk) { run_lo[l_perm[kk]] = a; run_hi[l_perm[kk]] = b; }
+                a = b;
+            }
+        }
+    } else { h->nC = 0; h->nmax = 0; h->scTotal = 0; }
     h->h_p_orig = p_orig;
 
     const size_t PN = (size_t)P * N, Mz = (size_t)M;
@@ -801,14 +906,19 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     h->Bpp = h->poseblk; h->BpK = h->Bpp + PN * N; h->BKK = h->BpK + PN * 6; h->gr = h->BKK + 36; h->err_lin = h->gr + PN + 6;
     ALLOC(C, (size_t)L * 6); ALLOC(gl, (size_t)L * 3); ALLOC(WK, (size_t)L * 18); ALLOC(Cinv, (size_t)L * 6);
     ALLOC(cg4, (size_t)L * 4); ALLOC(u4, (size_t)L * 4); ALLOC(dl4, (size_t)L * 4); ALLOC(gl4, (size_t)L * 4); ALLOC(v4, Mz * 4);
-    ALLOC(precblk, PN * N + PN + kPartCols);
-    h->Dloc = h->precblk; h->rloc = h->Dloc + PN * N; h->krow = h->rloc + PN;
+    h->regionA = std::max(PN * N, h->scTotal);
+    ALLOC(precblk, h->regionA + PN + kPartCols);
+    h->Dloc = h->precblk; h->rloc = h->Dloc + h->regionA; h->krow = h->rloc + PN;
+    if (h->use_clusters) {
+        ALLOC(cl_ptr, h->nC + 1); ALLOC(cl_off, h->nC + 1); ALLOC(pose_cluster, P); ALLOC(p_run_lo, Mz); ALLOC(p_run_hi, Mz);
+        ALLOC(Wm, Mz * 3 * N); ALLOC(Mc, h->scTotal);
+    }
     ALLOC(Minv, PN * N); ALLOC(MinvK, 36); ALLOC(rhs, PN + 8);
     ALLOC(vx, PN + 8); ALLOC(vr, PN + 8); ALLOC(vz, PN + 8); ALLOC(vp, PN + 8);
     ALLOC(ybuf, PN + 8 + 2 * kPartCols);
     const size_t nStep = (size_t)cdiv(std::max<int64_t>((int64_t)PN + 6, (int64_t)L * 4), 256);
-    ALLOC(partA, std::max<size_t>(h->nCtaPose, nStep) * kPartCols); ALLOC(partC, (size_t)h->nCtaPose * kPartCols);
-    ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols);
+    ALLOC(partA, std::max<size_t>(std::max<size_t>(h->nCtaPose, nStep), (size_t)h->nC) * kPartCols); ALLOC(partC, (size_t)h->nCtaPose * kPartCols);
+    ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
     h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
     ALLOC(errblk, h->nErrBlk);
     ALLOC(scal, 8); ALLOC(status, 64); ALLOC(flags, 4); ALLOC(cheir, 1);
@@ -819,6 +929,11 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         UP(p_lm, p_lm.data(), sizeof(int) * Mz); UP(p_pose, p_pose.data(), sizeof(int) * Mz); UP(p_orig, p_orig.data(), sizeof(int) * Mz);
         UP(p_uv, p_uv.data(), sizeof(double) * 2 * Mz); UP(l_pose, l_pose.data(), sizeof(int) * Mz); UP(l_perm, l_perm.data(), sizeof(int) * Mz);
         UP(l_uv, l_uv.data(), sizeof(double) * 2 * Mz);
+    }
+    if (h->use_clusters) {
+        UP(cl_ptr, cl_ptr.data(), sizeof(int) * (h->nC + 1)); UP(cl_off, cl_off.data(), sizeof(long long) * (h->nC + 1));
+        UP(pose_cluster, pose_cluster.data(), sizeof(int) * P);
+        if (M) { UP(p_run_lo, run_lo.data(), sizeof(int) * Mz); UP(p_run_hi, run_hi.data(), sizeof(int) * Mz); }
     }
     UP(enc, enc, sizeof(double) * PN);
     if (L) UP(lm_prior, lm_prior, sizeof(double) * 3 * L);

@@ -22,7 +22,9 @@ namespace asck {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kCtaThreads = kWarpsPerCta * 32;
-constexpr int kPartCols = 32;   // width of every partial-sum row (padded)
+constexpr int kPartCols = 32;   // width of the linearisation partial-sum rows (padded)
+constexpr int kPcgCols = 8;     // width of the per-CTA partial rows written inside the PCG loop
+constexpr int kReduceThreads = 1024;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct Camera {
@@ -689,6 +691,175 @@ pose_invert_kernel(int P, double lambda, const double* __restrict__ Bpp, const d
     if (!ok && lane == 0) atomicMin(fail_idx, p);
 }
 
+// ------------------------------------------------------------------ cluster-Jacobi preconditioner
+// Preconditioner blocks are the diagonal blocks of S over "clusters" = runs of consecutive, co-visible keyframes
+// (built on the host).  With per-keyframe blocks the intra-cluster coupling through shared landmarks is what
+// makes PCG crawl on arm trajectories (hundreds of keyframes looking at the same points).
+//
+// W_k = J_q^T J_l (N x 3, row-major) per observation, pose-major AoS [M][3N]
+template <int N>
+__global__ void __launch_bounds__(256) obs_w_kernel(int64_t M, const double2* __restrict__ J, double* __restrict__ Wm) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    double f[2 * N + 6];
+    load_planes<N>(J, M, (int)k, f);
+    const double* jl = f + 2 * N;
+    double* o = Wm + (size_t)k * 3 * N;
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[3 * a + c] = f[a] * jl[c] + f[N + a] * jl[3 + c];
+}
+
+// Row block of keyframe p inside its cluster block of S:
+//   S[p][p'] = [p == p'] (B_pp + lambda I) - sum over landmarks j seen by both of W_m Cinv_j W_m'^T
+// and the keyframe's part of the reduced right-hand side, rloc_p = - sum_m W_m (Cinv_j g_j).
+// One warp per keyframe; the N x n row block lives in shared memory; observations are visited in a fixed order.
+// run_lo/run_hi[k]: the landmark-major range holding the same landmark's observations from this cluster.
+template <int N>
+__global__ void __launch_bounds__(kCtaThreads)
+cluster_schur_kernel(int P, double lambda, int add_diag, int nmax, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
+                     const int* __restrict__ run_lo, const int* __restrict__ run_hi, const int* __restrict__ l_pose,
+                     const int* __restrict__ l_perm, const double* __restrict__ Wm, const double* __restrict__ Cinv,
+                     const double* __restrict__ cg4, const double* __restrict__ Bpp, const int* __restrict__ pose_cluster,
+                     const int* __restrict__ cl_ptr, const long long* __restrict__ cl_off, double* __restrict__ Sc, double* __restrict__ rloc) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWarpsPerCta + warp;
+    if (p >= P) return;
+    double* T = smem + (size_t)warp * (N * nmax + 3 * N);
+    double* Y = T + N * nmax;
+    const int c = pose_cluster[p], c0 = cl_ptr[c], n = (cl_ptr[c + 1] - c0) * N;
+    for (int i = lane; i < N * n; i += 32) T[i] = 0.0;
+    __syncwarp();
+    if (add_diag)
+        for (int e = lane; e < N * N; e += 32) {
+            const int a = e / N, b = e % N;
+            T[a * n + (p - c0) * N + b] = Bpp[(size_t)p * N * N + e] + (a == b ? lambda : 0.0);
+        }
+    __syncwarp();
+    double racc = 0.0;   // lane a < N
+    const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+    for (int k = k0; k < k1; ++k) {
+        const int j = __ldg(p_lm + k);
+        const double* ci = Cinv + 6 * (size_t)j;
+        const double* W = Wm + (size_t)k * 3 * N;
+        for (int i = lane; i < 3 * N; i += 32) {
+            const int a = i / 3, cc = i % 3;
+            const double w0 = W[3 * a], w1 = W[3 * a + 1], w2 = W[3 * a + 2];
+            const double c0_ = cc == 0 ? ci[0] : (cc == 1 ? ci[1] : ci[2]);
+            const double c1_ = cc == 0 ? ci[1] : (cc == 1 ? ci[3] : ci[4]);
+            const double c2_ = cc == 0 ? ci[2] : (cc == 1 ? ci[4] : ci[5]);
+            Y[i] = w0 * c0_ + w1 * c1_ + w2 * c2_;
+        }
+        if (lane < N) {
+            const double* g = cg4 + 4 * (size_t)j;
+            racc += W[3 * lane] * g[0] + W[3 * lane + 1] * g[1] + W[3 * lane + 2] * g[2];
+        }
+        __syncwarp();
+        const int lo = run_lo[k], hi = run_hi[k];
+        for (int kk = lo; kk < hi; ++kk) {
+            const int pp = __ldg(l_pose + kk);
+            const double* W2 = Wm + (size_t)__ldg(l_perm + kk) * 3 * N;
+            for (int e = lane; e < N * N; e += 32) {
+                const int a = e / N, b = e % N;
+                const double v = Y[3 * a] * W2[3 * b] + Y[3 * a + 1] * W2[3 * b + 1] + Y[3 * a + 2] * W2[3 * b + 2];
+                T[a * n + (pp - c0) * N + b] -= v;
+            }
+        }
+        __syncwarp();
+    }
+    double* out = Sc + cl_off[c] + (size_t)(p - c0) * N * n;
+    for (int i = lane; i < N * n; i += 32) out[i] = T[i];
+    if (lane < N) rloc[(size_t)p * N + lane] = -racc;
+}
+
+// In-place Gauss-Jordan inverse of one cluster block (SPD, no pivoting) in shared memory; one CTA per cluster.
+// Also forms the reduced right-hand side of the cluster: rhs = g + rsum.
+__global__ void __launch_bounds__(256)
+cluster_invert_kernel(int N, const int* __restrict__ cl_ptr, const long long* __restrict__ cl_off, const double* __restrict__ Sc,
+                      const double* __restrict__ g, const double* __restrict__ rsum, double* __restrict__ Mc, double* __restrict__ rhs,
+                      int* __restrict__ fail_idx) {
+    extern __shared__ double A[];
+    __shared__ double colk[256];
+    __shared__ int bad;
+    const int c = blockIdx.x, c0 = cl_ptr[c], n = (cl_ptr[c + 1] - c0) * N, ld = n | 1;
+    const double* src = Sc + cl_off[c];
+    if (threadIdx.x == 0) bad = 0;
+    for (int i = threadIdx.x; i < n * n; i += 256) A[(i / n) * ld + i % n] = src[i];
+    for (int i = threadIdx.x; i < n; i += 256) rhs[(size_t)c0 * N + i] = g[(size_t)c0 * N + i] + rsum[(size_t)c0 * N + i];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        const double piv = A[k * ld + k];
+        if (threadIdx.x == 0 && !(piv > 0)) bad = 1;
+        const double ip = 1.0 / piv;
+        for (int i = threadIdx.x; i < n; i += 256) colk[i] = A[i * ld + k];
+        __syncthreads();
+        for (int cc = threadIdx.x; cc < n; cc += 256) A[k * ld + cc] = cc == k ? ip : A[k * ld + cc] * ip;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * n; i += 256) {
+            const int r = i / n, cc = i % n;
+            if (r != k) A[r * ld + cc] = (cc == k ? 0.0 : A[r * ld + cc]) - colk[r] * A[k * ld + cc];
+        }
+        __syncthreads();
+    }
+    double* dst = Mc + cl_off[c];
+    for (int i = threadIdx.x; i < n * n; i += 256) dst[i] = A[(i / n) * ld + i % n];
+    if (threadIdx.x == 0 && bad) atomicMin(fail_idx, c0);
+}
+
+// PCG vector update with the cluster preconditioner; one CTA (128 threads, n <= 128) per cluster:
+//   init: x = 0, r = rhs, z = M r, p = z          else: x += alpha p, r -= alpha y, z = M r
+// part[c][0] = r_c . z_c
+__global__ void __launch_bounds__(128)
+pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const long long* __restrict__ cl_off, const double* __restrict__ Mc,
+                          const double* __restrict__ rhs, const double* __restrict__ y, double* __restrict__ x, double* __restrict__ r,
+                          double* __restrict__ z, double* __restrict__ p, const double* __restrict__ scal, const int* __restrict__ done,
+                          double* __restrict__ part) {
+    if (!init && *done) return;
+    __shared__ double rs[128];
+    __shared__ double red[4];
+    const int c = blockIdx.x, t = threadIdx.x;
+    const size_t base = (size_t)cl_ptr[c] * N;
+    const int n = (cl_ptr[c + 1] - cl_ptr[c]) * N;
+    double rm = 0.0;
+    if (t < n) {
+        const size_t i = base + t;
+        if (init) { rm = rhs[i]; x[i] = 0.0; }
+        else { const double alpha = scal[0]; x[i] += alpha * p[i]; rm = r[i] - alpha * y[i]; }
+        r[i] = rm;
+    }
+    rs[t] = rm;
+    __syncthreads();
+    double zm = 0.0;
+    if (t < n) {
+        const double* Mcol = Mc + cl_off[c] + t;   // column t == row t (symmetric): coalesced across threads
+        for (int col = 0; col < n; ++col) zm = fma(Mcol[(size_t)col * n], rs[col], zm);
+        z[base + t] = zm;
+        if (init) p[base + t] = zm;
+    }
+    const double d = warp_sum(rm * zm);
+    if ((t & 31) == 0) red[t >> 5] = d;
+    __syncthreads();
+    if (t == 0) part[c] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// K rows at PCG start: x_K = 0, r_K = rhs_K, z_K = MinvK r_K, p_K = z_K; scal[7] = r_K . z_K   (one warp)
+__global__ void pcg_init_k_kernel(int64_t PN, const double* __restrict__ rhs, const double* __restrict__ MinvK, double* __restrict__ x,
+                                  double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ kdot) {
+    const int lane = threadIdx.x;
+    const double rk = lane < 6 ? rhs[PN + lane] : 0.0;
+    double zk = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double ri = __shfl_sync(kFull, rk, i);
+        if (lane < 6) zk = fma(MinvK[6 * lane + i], ri, zk);
+    }
+    if (lane < 6) { x[PN + lane] = 0.0; r[PN + lane] = rk; z[PN + lane] = zk; p[PN + lane] = zk; }
+    const double d = warp_sum(lane < 6 ? rk * zk : 0.0);
+    if (lane == 0) *kdot = d;
+}
+
 // ------------------------------------------------------------------ K3: implicit Schur complement  y = S x
 // pass A (pose-major): v_k = J_l^T (J_q x_p)            [optionally first p_p <- z_p + beta p_p]
 template <int N, bool UPDATE_P>
@@ -760,7 +931,7 @@ schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const int* __restrict
 #pragma unroll
     for (int i = 0; i < 6; ++i) { const double t = warp_sum(wu[i]); if (lane == 0) s[warp][i] = t; }
     __syncthreads();
-    if (threadIdx.x < kPartCols) blk_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = threadIdx.x < 6 ? s[0][threadIdx.x] + s[1][threadIdx.x] + s[2][threadIdx.x] + s[3][threadIdx.x] : 0.0;
+    if (threadIdx.x < kPcgCols) blk_part[(size_t)blockIdx.x * kPcgCols + threadIdx.x] = threadIdx.x < 6 ? s[0][threadIdx.x] + s[1][threadIdx.x] + s[2][threadIdx.x] + s[3][threadIdx.x] : 0.0;
 }
 
 // pass C (pose-major): yloc_p = - sum_m J_q^T (J_l u_j); then (if add_diag) y_p = (B_pp + lambda) x_p + B_pK x_K + yloc_p.
@@ -823,13 +994,36 @@ schur_pass_c_kernel(int P, int64_t M, double lambda, int add_diag, const int* __
         if (lane == 0) s_part[warp][6] = dot;
     }
     __syncthreads();
-    if (threadIdx.x < kPartCols) {
+    if (threadIdx.x < kPcgCols) {
         double s = 0.0;
         if (threadIdx.x < 7)
 #pragma unroll
             for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w][threadIdx.x];
-        cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
+        cta_part[(size_t)blockIdx.x * kPcgCols + threadIdx.x] = s;
     }
+}
+
+// Sum the rows of part[R][W] (W = 1 or 8) with all 1024 threads of the block: each thread strides over rows with
+// four independent accumulators (memory-level parallelism), then a fixed shared-memory tree.  out[W] valid after return.
+template <int W>
+__device__ __forceinline__ void block_sum_cols(const double* __restrict__ part, int R, double* out, double* scratch) {
+    constexpr int RL = kReduceThreads / W;
+    const int t = threadIdx.x, col = t % W, rl = t / W;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int r = rl;
+    for (; r + 3 * RL < R; r += 4 * RL) {
+        a0 += part[(size_t)r * W + col]; a1 += part[(size_t)(r + RL) * W + col];
+        a2 += part[(size_t)(r + 2 * RL) * W + col]; a3 += part[(size_t)(r + 3 * RL) * W + col];
+    }
+    for (; r < R; r += RL) a0 += part[(size_t)r * W + col];
+    scratch[t] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    for (int s = RL / 2; s > 0; s >>= 1) {
+        if (rl < s) scratch[t] += scratch[t + s * W];
+        __syncthreads();
+    }
+    if (t < W) out[t] = scratch[t];
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------ single-block helpers
@@ -852,16 +1046,19 @@ __device__ inline double block_reduce_rows(const double* __restrict__ part, int 
 //   partC: CTA partials of pass C [nC][32] (cols 0..5 = sum B_pK^T p_p, col 6 = sum p_p.y_p)
 //   partB: block partials of pass B [nB][32] (cols 0..5 = sum W_Kj u_j)
 // Multi-GPU: the partial sums have been all-reduced already and arrive as a single row each (nC = nB = 1).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kReduceThreads)
 pcg_mid_kernel(int P, int N, double lambda, const double* __restrict__ partC, int nC, const double* __restrict__ partB, int nB,
                const double* __restrict__ BKK, const double* __restrict__ MinvK, double* __restrict__ p, double* __restrict__ x,
                double* __restrict__ r, double* __restrict__ z, double* __restrict__ yK_out, double* __restrict__ scal, int* __restrict__ done) {
     if (*done) return;
-    __shared__ double s[8][kPartCols];
+    __shared__ double scratch[kReduceThreads];
+    __shared__ double sc[kPcgCols], sb[kPcgCols];
     __shared__ double sh[16];
     const int lane = threadIdx.x & 31;
-    const double c = block_reduce_rows(partC, nC, lane, s);
-    const double b = block_reduce_rows(partB, nB, lane, s);
+    block_sum_cols<kPcgCols>(partC, nC, sc, scratch);
+    block_sum_cols<kPcgCols>(partB, nB, sb, scratch);
+    const double c = lane < kPcgCols ? sc[lane] : 0.0;
+    const double b = lane < kPcgCols ? sb[lane] : 0.0;
     double* pK = p + (size_t)P * N;
     if (threadIdx.x < 32) {
         double yk = 0.0;
@@ -928,25 +1125,26 @@ pcg_update_kernel(int P, const double* __restrict__ p, const double* __restrict_
     }
     if (lane == 0) s_part[warp] = dot;
     __syncthreads();
-    if (threadIdx.x < kPartCols) {
+    if (threadIdx.x == 0) {
         double s = 0.0;
-        if (threadIdx.x == 0)
 #pragma unroll
-            for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w];
-        cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
+        for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w];
+        cta_part[blockIdx.x] = s;
     }
 }
 
 // rz_new, beta, convergence test, p_K <- z_K + beta p_K.  One block of 256 threads.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kReduceThreads)
 pcg_end_kernel(int P, int N, const double* __restrict__ part, int nPart, double tol2, int max_iters, double* __restrict__ p,
                const double* __restrict__ z, double* __restrict__ scal, int* __restrict__ done) {
     if (*done) return;
-    __shared__ double s[8][kPartCols];
+    __shared__ double scratch[kReduceThreads];
+    __shared__ double so[1];
     const int lane = threadIdx.x & 31;
-    const double t = block_reduce_rows(part, nPart, lane, s);
+    block_sum_cols<1>(part, nPart, so, scratch);
+    const double t = so[0];
     if (threadIdx.x < 32) {
-        const double rz_new = __shfl_sync(kFull, t, 0) + scal[7];
+        const double rz_new = t + scal[7];
         const double beta = rz_new / scal[2];
         const double it = scal[5] + 1.0;
         if (lane < 6) p[(size_t)P * N + lane] = z[(size_t)P * N + lane] + beta * p[(size_t)P * N + lane];
@@ -997,23 +1195,24 @@ pcg_init_kernel(int P, const double* __restrict__ rhs, const double* __restrict_
         if (lane == 0) s_part[kWarpsPerCta] = dk;
     }
     __syncthreads();
-    if (threadIdx.x < kPartCols) {
+    if (threadIdx.x == 0) {
         double s = 0.0;
-        if (threadIdx.x == 0) {
 #pragma unroll
-            for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w];
-            if (blockIdx.x == 0) s += s_part[kWarpsPerCta];
-        }
-        cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
+        for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w];
+        if (blockIdx.x == 0) s += s_part[kWarpsPerCta];
+        cta_part[blockIdx.x] = s;
     }
 }
 
-__global__ void __launch_bounds__(256)
-pcg_init_end_kernel(const double* __restrict__ part, int nPart, double* __restrict__ scal, int* __restrict__ done) {
-    __shared__ double s[8][kPartCols];
-    const int lane = threadIdx.x & 31;
-    const double t = block_reduce_rows(part, nPart, lane, s);
+__global__ void __launch_bounds__(kReduceThreads)
+pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __restrict__ kdot, double* __restrict__ scal,
+                    int* __restrict__ done) {
+    __shared__ double scratch[kReduceThreads];
+    __shared__ double so[1];
+    block_sum_cols<1>(part, nPart, so, scratch);
+    double t = so[0];
     if (threadIdx.x == 0) {
+        if (kdot) t += *kdot;
         scal[0] = 0.0; scal[1] = 0.0; scal[2] = t; scal[3] = t; scal[4] = 0.0; scal[5] = 0.0; scal[6] = 0.0; scal[7] = 0.0;
         *done = (t > 0.0) ? 0 : 1;   // zero right-hand side: nothing to do
     }

@@ -113,6 +113,7 @@ void asc_sim_default_config(asc_sim_config* c) {
     const Xf I = asc::xf_identity();
     asc::xf_to12(I, c->sim_extrinsic);    // ArmSlamCalib.cpp:193
     asc::xf_to12(I, c->extrinsic_guess);  // ArmSlamCalib.h:87
+    c->segment_length = 0;
 }
 
 int asc_chain_fk(int32_t n, const double* t_p2j, const double* axis, const double* t_c2j, const double* q,
@@ -212,6 +213,12 @@ int asc_sim_create(const asc_sim_config* cfg, int32_t n_dof, const double* t_p2j
         const double freq = 1.0f, mag = 0.01f;   // float literals at the call site (:551)
         std::vector<double> q(N, 0.0), q_dot(N, (double)0.001f), config(N, 0.0), noise(N), next(N);
         for (int i = 0; i < T; ++i) {
+            if (cfg->segment_length > 0 && i > 0 && i % cfg->segment_length == 0) {
+                // [NEW] restart the walk from a random configuration inside 80% of the limits
+                std::default_random_engine start_gen((unsigned)(cfg->seed + 7919 * (i / cfg->segment_length)));
+                std::uniform_real_distribution<double> start(0.8 * lower, 0.8 * upper);
+                for (int k = 0; k < N; ++k) { config[k] = q[k] = start(start_gen); q_dot[k] = (double)0.001f; }
+            }
             for (int j = 0; j < N; ++j) {
                 const double pos = q[j] + 0.25 * (i * 0.01);
                 noise[j] = (perlin.noise((double)(j + 1) * 100, -(double)(j + 1) * 999, pos * freq) - 0.5) * mag;

@@ -40,7 +40,7 @@ def pose12(R=None, t=None):
 
 
 def make_sim_problem(chain=None, trajectory_size=250, nx=25, ny=25, size_x=10.0, size_y=10.0, z_range=(-5.0, 5.0), max_range=0.0,
-                     encoder_noise=0.1, seed=0, sim_extrinsic=None, extrinsic_guess=None, fx=640.0, fy=640.0, cx=320.0, cy=240.0,
+                     encoder_noise=0.1, seed=0, segment_length=0, sim_extrinsic=None, extrinsic_guess=None, fx=640.0, fy=640.0, cx=320.0, cy=240.0,
                      srand=True):
     """CreateSimulation + SimulationStep over the whole trajectory (src/ArmSlamCalib.cpp:654-706, :307-327),
     one batch graph.  Defaults are ArmSlamCalib::Params (ArmSlamCalib.h:69-105) with trajectory_length=250
@@ -59,6 +59,7 @@ def make_sim_problem(chain=None, trajectory_size=250, nx=25, ny=25, size_x=10.0,
     cfg.max_range = max_range
     cfg.encoder_noise = encoder_noise
     cfg.seed = seed
+    cfg.segment_length = segment_length
     if sim_extrinsic is not None:
         cfg.sim_extrinsic[:] = list(np.asarray(sim_extrinsic, dtype=np.float64).reshape(12))
     if extrinsic_guess is not None:

@@ -73,6 +73,10 @@ typedef struct asc_params {
     double pcg_rel_tol;              /* ||r||_M^-1 / ||b||_M^-1 stopping ratio (1e-12) */
     int32_t pcg_max_iters;           /* 2000 */
     int32_t device;                  /* CUDA device ordinal, -1 = current */
+    /* block-Jacobi preconditioner blocks = runs of consecutive, co-visible keyframes ("clusters") */
+    int32_t pcg_cluster_max;         /* max keyframes per cluster (10); <=1: one block per keyframe */
+    double pcg_cluster_covis;        /* start a new cluster when the share of common landmarks with the
+                                        previous keyframe drops below this (0.25) */
 } asc_params;
 
 /* One record per outer iterate() of the optimiser */
@@ -188,6 +192,9 @@ typedef struct asc_sim_config {
     int32_t min_observations;  /* admission rule observations.size() > 3, ArmSlamCalib.cpp:1860 */
     double sim_extrinsic[12];  /* simExtrinsic (ground truth) */
     double extrinsic_guess[12];/* extrinsicInitialGuess */
+    int32_t segment_length;    /* [NEW] 0 = one random walk (reference); k>0 = restart the reference's walk from a
+                                  random in-limits configuration every k steps, so long trajectories keep exploring
+                                  instead of saturating at the joint limits */
 } asc_sim_config;
 
 typedef struct asc_sim_problem asc_sim_problem;
@@ -214,6 +221,9 @@ int asc_sim_export(const asc_sim_problem* s, int32_t* pose_idx, int32_t* lm_idx,
                    int64_t* factor_order);
 
 /* host forward kinematics of the chain (used by the generator; exported for tests) */
+/* srand() of the libc stream utils::Rand draws from (sim_genrobot.cpp:60) */
+void asc_srand(unsigned seed);
+
 int asc_chain_fk(int32_t n_dof, const double* t_p2j, const double* axis, const double* t_c2j,
                  const double* q, double* t_link /*[12]*/);
 
