@@ -29,6 +29,7 @@ SIGNATURES = {
     "asc_version": (C.c_char_p, []),
     "asc_create": (C.c_int, [C.POINTER(D.AscParams), C.POINTER(_vp)]),
     "asc_destroy": (C.c_int, [_vp]),
+    "asc_set_params": (C.c_int, [_vp, C.POINTER(D.AscParams)]),
     "asc_set_chain": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "asc_set_camera": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "asc_set_problem": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -42,6 +43,13 @@ SIGNATURES = {
     "asc_get_landmark_blocks": (C.c_int, [_vp, _vp, _vp, _vp]),
     "asc_get_pose_blocks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "asc_solve_damped": (C.c_int, [_vp, C.c_double, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
+    "asc_save_values": (C.c_int, [_vp]),
+    "asc_restore_values": (C.c_int, [_vp]),
+    "asc_launch_count": (C.c_int64, [_vp]),
+    "asc_timer_start": (C.c_int, [_vp]),
+    "asc_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "asc_profile_begin": (C.c_int, [_vp, C.c_int32, C.c_int32]),
+    "asc_profile_read": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "asc_comm_id_size": (C.c_int, []),
     "asc_comm_create_id": (C.c_int, [_vp]),
     "asc_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp]),
@@ -212,6 +220,10 @@ class BatchOptimizer:
             raise IndeterminantLinearSystemException(rc, msg, kind.value.decode() if kind.value else "?", idx.value)
         raise AscError(rc, msg)
 
+    def set_params(self, params):
+        self.params = params
+        self._check(self.L.asc_set_params(self.h, C.byref(params)))
+
     def set_problem(self, pb):
         pi = np.ascontiguousarray(pb.pose_idx, dtype=np.int32)
         li = np.ascontiguousarray(pb.lm_idx, dtype=np.int32)
@@ -282,6 +294,31 @@ class BatchOptimizer:
 
     def iterations(self):
         return len(self.log)
+
+    def save_values(self):
+        self._check(self.L.asc_save_values(self.h))
+
+    def restore_values(self):
+        self._check(self.L.asc_restore_values(self.h))
+
+    def launch_count(self):
+        return int(self.L.asc_launch_count(self.h))
+
+    def timer_start(self):
+        self._check(self.L.asc_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.L.asc_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_begin(self, kernel_id, max_samples=256):
+        self._check(self.L.asc_profile_begin(self.h, kernel_id, max_samples))
+
+    def profile_read(self):
+        n, mean, mn = C.c_int32(), C.c_double(), C.c_double()
+        self._check(self.L.asc_profile_read(self.h, C.byref(n), C.byref(mean), C.byref(mn)))
+        return n.value, mean.value, mn.value
 
     def close(self):
         if self.h:

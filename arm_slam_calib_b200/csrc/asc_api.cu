@@ -118,6 +118,12 @@ struct asc_handle {
     double *scal = nullptr, *status = nullptr;
     int *flags = nullptr;        // [0] pcg done, [1] landmark fail idx, [2] pose fail idx, [3] K fail
     unsigned long long* cheir = nullptr;
+    // measurement hooks
+    long long launches = 0;
+    cudaEvent_t tm[2] = {nullptr, nullptr};
+    int prof_id = 0, prof_n = 0;
+    std::vector<cudaEvent_t> prof_ev;
+    double *q_save = nullptr, *lm4_save = nullptr, *X_save = nullptr;
     // cluster-Jacobi preconditioner
     bool use_clusters = false;
     int nC = 0, nmax = 0;
@@ -151,6 +157,13 @@ int allreduce(asc_handle* h, double* buf, size_t count) {
     ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream);
     if (r != ncclSuccess) return fail(ASC_ERR_COMM, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
     return ASC_OK;
+}
+
+inline void prof_start(asc_handle* h, int id) {
+    if (h->prof_id == id && 2 * h->prof_n + 1 < (int)h->prof_ev.size()) cudaEventRecord(h->prof_ev[2 * h->prof_n], h->stream);
+}
+inline void prof_stop(asc_handle* h, int id) {
+    if (h->prof_id == id && 2 * h->prof_n + 1 < (int)h->prof_ev.size()) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], h->stream); ++h->prof_n; }
 }
 
 template <int N>
@@ -201,6 +214,7 @@ struct Engine {
         CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
         rc = fk(h, h->q, h->X, true);
         if (rc) return rc;
+        prof_start(h, 1);
         if (store_b)
             linearize_pose_kernel<N, true><<<h->nCtaPose, kCtaThreads, LinSmem<N>::kBytes, h->stream>>>(
                 h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
@@ -210,10 +224,14 @@ struct Engine {
                 h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
                 h->J, h->Bpp, h->BpK, h->gr, h->partA, nullptr, h->cheir);
         CUDA_TRY(cudaGetLastError());
+        prof_stop(h, 1);
         CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+        prof_start(h, 2);
         landmark_blocks_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->cm, h->L, h->lm_ptr, h->l_pose, h->l_uv, h->cam, h->lm4, h->lm_prior, h->C,
                                                                 h->gl, h->WK, h->errblk);
         CUDA_TRY(cudaGetLastError());
+        prof_stop(h, 2);
+        h->launches += 8;
         const int nR1 = std::min(64, h->nCtaPose), rpb = cdiv(h->nCtaPose, nR1);
         reduce_rows_kernel<<<cdiv(h->nCtaPose, rpb), 256, 0, h->stream>>>(h->partA, h->nCtaPose, 28, kPartCols, rpb, h->partR);
         CUDA_TRY(cudaGetLastError());
@@ -246,6 +264,7 @@ struct Engine {
     static int prepare(asc_handle* h, double lambda) {
         const int big = 0x7fffffff;
         int init_flags[4] = {0, big, big, big};
+        h->launches += 5;
         CUDA_TRY(cudaMemcpyAsync(h->flags, init_flags, sizeof init_flags, cudaMemcpyHostToDevice, h->stream));
         landmark_invert_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->L, lambda, h->C, h->gl, h->WK, h->Cinv, h->cg4, h->partL, h->flags + 1);
         CUDA_TRY(cudaGetLastError());
@@ -287,17 +306,24 @@ struct Engine {
 
     // one application y = S x written into ybuf; K rows handled by the caller's kernels
     static int schur_apply_launch(asc_handle* h, double lambda, bool update_p, double* x, const int* done) {
+        h->launches += 3;
+        prof_start(h, 3);
         if (update_p)
             schur_pass_a_kernel<N, true><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4);
         else
             schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4);
         CUDA_TRY(cudaGetLastError());
+        prof_stop(h, 3);
+        prof_start(h, 4);
         schur_pass_b_kernel<false><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->l_perm, h->v4, h->WK, h->Cinv, x + (size_t)h->P * N, done,
                                                                     nullptr, h->u4, h->partB);
         CUDA_TRY(cudaGetLastError());
+        prof_stop(h, 4);
+        prof_start(h, 5);
         schur_pass_c_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, h->rank == 0 ? 1 : 0, h->pose_ptr, h->p_lm, h->J, h->u4, x,
                                                                          h->Bpp, h->BpK, done, h->ybuf, h->partC);
         CUDA_TRY(cudaGetLastError());
+        prof_stop(h, 5);
         return ASC_OK;
     }
 
@@ -305,6 +331,7 @@ struct Engine {
     static int pcg(asc_handle* h, double lambda, int* iters) {
         const size_t PN = (size_t)h->P * N;
         const int nUpd = h->use_clusters ? h->nC : h->nCtaPose;
+        h->launches += 3;
         if (h->use_clusters) {
             pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(1, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp, h->scal,
                                                                   h->flags, h->partA);
@@ -346,6 +373,7 @@ struct Engine {
                 else
                     pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
                 CUDA_TRY(cudaGetLastError());
+                h->launches += 3;
                 pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, h->partA, nUpd, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags);
                 CUDA_TRY(cudaGetLastError());
             }
@@ -361,6 +389,7 @@ struct Engine {
 
     // delta_l = Cinv (g_l - W^T delta_r) -> dl4
     static int backsub(asc_handle* h) {
+        h->launches += 2;
         schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, h->vx, nullptr, nullptr, nullptr, h->v4);
         CUDA_TRY(cudaGetLastError());
         schur_pass_b_kernel<true><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->l_perm, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
@@ -388,8 +417,11 @@ struct Engine {
         int rc = fk(h, q, X, false);
         if (rc) return rc;
         const int nb1 = cdiv(h->M, 256), nb2 = cdiv((int64_t)h->P + h->L, 256);
+        h->launches += 4;
+        prof_start(h, 6);
         if (nb1) error_proj_kernel<<<nb1, 256, 0, h->stream>>>(h->cm, h->M, h->p_pose, h->p_lm, h->p_uv, h->cam, lm4, h->errblk);
         CUDA_TRY(cudaGetLastError());
+        prof_stop(h, 6);
         error_prior_kernel<<<nb2, 256, 0, h->stream>>>(h->cm, h->pc, N, h->P, h->L, h->rank == 0 ? 1 : 0, q, h->enc, h->has_enc, lm4, h->lm_prior, h->errblk + nb1);
         CUDA_TRY(cudaGetLastError());
         error_finish_kernel<<<1, 256, 0, h->stream>>>(h->pc, h->rank == 0 ? 1 : 0, X, h->errblk, nb1 + nb2, h->status + 4);
@@ -746,6 +778,14 @@ int asc_create(const asc_params* params, asc_handle** out) {
     return ASC_OK;
 }
 
+int asc_set_params(asc_handle* h, const asc_params* params) {
+    if (!h || !params) return fail(ASC_ERR_INVALID, "null argument");
+    const int dev = h->prm.device;
+    h->prm = *params;
+    h->prm.device = dev;
+    return ASC_OK;
+}
+
 int asc_destroy(asc_handle* h) {
     if (!h) return ASC_OK;
     cudaSetDevice(h->dev);
@@ -753,6 +793,7 @@ int asc_destroy(asc_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     free_device(h);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->prof_ev) cudaEventDestroy(ev);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -900,6 +941,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     ALLOC(enc, PN); ALLOC(lm_prior, (size_t)L * 3);
     if (has_enc) ALLOC(has_enc, P); else h->has_enc = nullptr;
     ALLOC(q, PN); ALLOC(q_try, PN); ALLOC(lm4, (size_t)L * 4); ALLOC(lm4_try, (size_t)L * 4); ALLOC(X, 12); ALLOC(X_try, 12);
+    ALLOC(q_save, PN); ALLOC(lm4_save, (size_t)L * 4); ALLOC(X_save, 12);
     ALLOC(cam, (size_t)P * 12); ALLOC(chain, PN * 6);
     ALLOC(J, (size_t)(N + 3) * Mz); ALLOC(b_dbg, 1);
     ALLOC(poseblk, PN * N + PN * 6 + 36 + PN + 6 + 8);
@@ -1096,6 +1138,81 @@ int asc_solve_damped(asc_handle* h, double lambda, double* dq, double* dl, doubl
     if (dx) CUDA_TRY(cudaMemcpyAsync(dx, h->vx + PN, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (dl && h->L) CUDA_TRY(cudaMemcpy2DAsync(dl, 3 * sizeof(double), h->dl4, 4 * sizeof(double), 3 * sizeof(double), h->L, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ASC_OK;
+}
+
+// ---- measurement support
+int asc_save_values(asc_handle* h) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->q_save, h->q, sizeof(double) * h->P * h->N, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->lm4_save, h->lm4, sizeof(double) * h->L * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->X_save, h->X, sizeof(double) * 12, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return ASC_OK;
+}
+
+int asc_restore_values(asc_handle* h) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->q, h->q_save, sizeof(double) * h->P * h->N, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->lm4, h->lm4_save, sizeof(double) * h->L * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->X, h->X_save, sizeof(double) * 12, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->linearized = false;
+    return ASC_OK;
+}
+
+int64_t asc_launch_count(asc_handle* h) { return h ? h->launches : 0; }
+
+// CUDA-event stopwatch on the stream every kernel of this handle is launched on
+int asc_timer_start(asc_handle* h) {
+    if (!h) return fail(ASC_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->dev));
+    if (!h->tm[0]) { CUDA_TRY(cudaEventCreate(&h->tm[0])); CUDA_TRY(cudaEventCreate(&h->tm[1])); }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaEventRecord(h->tm[0], h->stream));
+    return ASC_OK;
+}
+
+int asc_timer_stop(asc_handle* h, double* elapsed_ms) {
+    if (!h || !h->tm[0] || !elapsed_ms) return fail(ASC_ERR_INVALID, "timer not started");
+    CUDA_TRY(cudaSetDevice(h->dev));
+    CUDA_TRY(cudaEventRecord(h->tm[1], h->stream));
+    CUDA_TRY(cudaEventSynchronize(h->tm[1]));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->tm[0], h->tm[1]));
+    *elapsed_ms = ms;
+    return ASC_OK;
+}
+
+int asc_profile_begin(asc_handle* h, int32_t kernel_id, int32_t max_samples) {
+    if (!h || kernel_id < 0 || kernel_id > 6 || max_samples < 0) return fail(ASC_ERR_INVALID, "bad profile request");
+    CUDA_TRY(cudaSetDevice(h->dev));
+    while ((int)h->prof_ev.size() < 2 * max_samples) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    h->prof_id = kernel_id;
+    h->prof_n = 0;
+    return ASC_OK;
+}
+
+int asc_profile_read(asc_handle* h, int32_t* n_samples, double* mean_ms, double* min_ms) {
+    if (!h) return fail(ASC_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->dev));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    double sum = 0.0, mn = 1e300;
+    for (int i = 0; i < h->prof_n; ++i) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+        sum += ms; mn = std::min(mn, (double)ms);
+    }
+    if (n_samples) *n_samples = h->prof_n;
+    if (mean_ms) *mean_ms = h->prof_n ? sum / h->prof_n : 0.0;
+    if (min_ms) *min_ms = h->prof_n ? mn : 0.0;
+    h->prof_id = 0;
     return ASC_OK;
 }
 

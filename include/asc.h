@@ -104,6 +104,9 @@ const char* asc_version(void);
 
 int asc_create(const asc_params* params, asc_handle** out);
 int asc_destroy(asc_handle* h);
+/* Replace the optimiser-control fields (iteration limits, tolerances, lambda/Delta schedule).  Noise sigmas, the
+ * Cauchy k and the cluster settings are baked into the packed problem and take effect at the next asc_set_problem. */
+int asc_set_params(asc_handle* h, const asc_params* params);
 
 /*
  * Serial revolute chain; replaces the DART skeleton/group the factors hold
@@ -165,6 +168,20 @@ int asc_get_pose_blocks(asc_handle* h, double* bpp /*[P][N][N]*/, double* bpk /*
  * delta_x [6].  Returns the PCG iteration count. */
 int asc_solve_damped(asc_handle* h, double lambda, double* delta_q, double* delta_l,
                      double* delta_x, int32_t* pcg_iterations);
+
+/* ---- measurement support (bench.py) ----------------------------------------------- */
+/* device-resident snapshot of the current values / restore it (keeps the timed region free of H2D copies) */
+int asc_save_values(asc_handle* h);
+int asc_restore_values(asc_handle* h);
+/* number of kernels this handle has launched so far */
+int64_t asc_launch_count(asc_handle* h);
+/* CUDA-event stopwatch recorded on the stream this handle launches its kernels on */
+int asc_timer_start(asc_handle* h);
+int asc_timer_stop(asc_handle* h, double* elapsed_ms);
+/* Bracket up to max_samples launches of one kernel with CUDA events on the launching stream while the normal
+ * entry points run: 1 linearise (K1+K2b), 2 landmark blocks (K2a), 3 Schur pass A, 4 pass B, 5 pass C, 6 error (K1e) */
+int asc_profile_begin(asc_handle* h, int32_t kernel_id, int32_t max_samples);
+int asc_profile_read(asc_handle* h, int32_t* n_samples, double* mean_ms, double* min_ms);
 
 /* ---- multi-GPU: landmark sharding --------------------------- */
 /* Size in bytes of the opaque communicator id (ncclUniqueId). */
