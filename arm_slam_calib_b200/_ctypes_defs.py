@@ -33,6 +33,7 @@ class AscParams(C.Structure):
         ("device", C.c_int32),
         ("pcg_cluster_max", C.c_int32),
         ("pcg_cluster_covis", C.c_double),
+        ("pcg_coarse_max_dim", C.c_int32),
     ]
 
 

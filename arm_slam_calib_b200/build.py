@@ -28,7 +28,7 @@ def build(force=False, verbose=False, dof_list=None):
         cmd += ["-Xptxas", "-v"]
     if dof_list:
         cmd += ["-DASC_DOF_LIST(X)=" + " ".join("X(%d)" % n for n in dof_list)]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lcusolver", "-lcublas", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

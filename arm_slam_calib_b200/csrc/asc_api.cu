@@ -1,7 +1,9 @@
 // Host side of the B200 batch optimiser: the C ABI of include/asc.h, problem packing, the
 // LM / Dogleg controllers and the kernel launch sequences.
 // There is no CPU fallback in this file: every compute entry point needs an sm_100 device.
+#include <cublas_v2.h>
 #include <cuda_runtime.h>
+#include <cusolverDn.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types only; the library is dlopen()ed when a communicator is requested
 
@@ -131,6 +133,19 @@ struct asc_handle {
     int *cl_ptr = nullptr, *pose_cluster = nullptr, *p_run_lo = nullptr, *p_run_hi = nullptr;
     long long* cl_off = nullptr;
     double *Wm = nullptr, *Mc = nullptr;
+    // coarse level (two-level additive preconditioner)
+    bool use_coarse = false;
+    int nz = 0, nInc = 0, nDest = 0;
+    int *inc_lo = nullptr, *inc_hi = nullptr, *inc_lm = nullptr, *dest_ptr = nullptr, *dest_ca = nullptr, *dest_cb = nullptr;
+    int *pair_a = nullptr, *pair_b = nullptr, *cl_inc_ptr = nullptr, *cl_inc = nullptr;
+    double *Vinc = nullptr, *Tinc = nullptr, *E = nullptr, *rc = nullptr, *zc = nullptr, *SKK = nullptr, *work = nullptr;
+    int lwork = 0;
+    bool coarse_valid = false;      // E holds a factorised inverse (possibly from an earlier lambda / linearisation)
+    bool coarse_fresh = false;      // ... computed for exactly the current system
+    int coarse_ref_iters = 0;       // PCG iterations of the solve that followed the last refresh
+    int coarse_last_iters = 0;
+    cusolverDnHandle_t solver = nullptr;
+    cublasHandle_t blas = nullptr;
     double* h_status = nullptr;  // pinned: status(32) + scal(8)
     int* h_flags = nullptr;      // pinned
 };
@@ -263,7 +278,7 @@ struct Engine {
     // damped landmark inverses, Schur-diagonal preconditioner, reduced right-hand side
     static int prepare(asc_handle* h, double lambda) {
         const int big = 0x7fffffff;
-        int init_flags[4] = {0, big, big, big};
+        int init_flags[8] = {0, big, big, big, 0, 0, 0, 0};
         h->launches += 5;
         CUDA_TRY(cudaMemcpyAsync(h->flags, init_flags, sizeof init_flags, cudaMemcpyHostToDevice, h->stream));
         landmark_invert_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->L, lambda, h->C, h->gl, h->WK, h->Cinv, h->cg4, h->partL, h->flags + 1);
@@ -291,11 +306,50 @@ struct Engine {
             kpart = h->krow;
             nk = 1;
         }
-        k_rows_kernel<<<1, 256, 0, h->stream>>>(lambda, kpart, nk, h->BKK, h->gr + (size_t)h->P * N, h->MinvK, h->rhs + (size_t)h->P * N, h->flags + 3);
+        k_rows_kernel<<<1, 256, 0, h->stream>>>(lambda, kpart, nk, h->BKK, h->gr + (size_t)h->P * N, h->MinvK, h->rhs + (size_t)h->P * N, h->SKK, h->flags + 3);
         CUDA_TRY(cudaGetLastError());
         if (h->use_clusters) {
             const size_t sm = sizeof(double) * (size_t)h->nmax * (h->nmax | 1);
             cluster_invert_kernel<<<h->nC, 256, sm, h->stream>>>(N, h->cl_ptr, h->cl_off, h->Dloc, h->gr, h->rloc, h->Mc, h->rhs, h->flags + 2);
+            // The coarse operator is only a preconditioner: any SPD E^-1 keeps PCG exact, so a factorisation from an
+            // earlier lambda / linearisation is reused until it visibly costs iterations (deterministic policy).
+            const bool refresh = h->use_coarse && (!h->coarse_valid || h->coarse_last_iters > h->coarse_ref_iters + h->coarse_ref_iters / 4 + 8);
+            h->coarse_fresh = refresh;
+            if (refresh) {
+                CUDA_TRY(cudaGetLastError());
+                const int nz = h->nz;
+                h->coarse_valid = true;
+                inc_v_kernel<N><<<cdiv(std::max(h->nInc, 1), 4), 128, 0, h->stream>>>(h->nInc, h->inc_lo, h->inc_hi, h->inc_lm, h->l_perm, h->Wm, h->Cinv,
+                                                                                  h->Vinc, h->Tinc);
+                CUDA_TRY(cudaMemsetAsync(h->E, 0, sizeof(double) * (size_t)nz * nz, h->stream));
+                coarse_blocks_kernel<N><<<cdiv(std::max(h->nDest, 1), 4), 128, 0, h->stream>>>(h->nDest, h->dest_ptr, h->dest_ca, h->dest_cb, h->pair_a,
+                                                                                           h->pair_b, h->Vinc, h->Tinc, h->E, nz);
+                if (h->rank == 0) coarse_diag_kernel<<<cdiv((int64_t)h->nC * N * N, 256), 256, 0, h->stream>>>(h->nC, N, lambda, h->cl_ptr, h->Bpp, h->E, nz);
+                coarse_k_kernel<<<cdiv(std::max<int64_t>((int64_t)h->nC * N * 6, 36), 256), 256, 0, h->stream>>>(h->nC, N, h->rank == 0 ? 1 : 0, h->cl_ptr, h->cl_inc_ptr,
+                                                                                                       h->cl_inc, h->inc_lm, h->Tinc, h->WK, h->BpK, h->SKK, h->E, nz);
+                CUDA_TRY(cudaGetLastError());
+                h->launches += 5;
+                if (h->world > 1) {   // S_KK is already global; undo its world-fold replication, then sum the shard contributions
+                    int rc2 = allreduce(h, h->E, (size_t)nz * nz);
+                    if (rc2) return rc2;
+                    // every rank wrote the same S_KK: rescale the 6x6 corner
+                    scale_block_kernel<<<1, 64, 0, h->stream>>>(h->E, nz, h->nC * N, 1.0 / h->world);
+                }
+                static const bool timing = getenv("ASC_TIMING") != nullptr;
+                cudaEvent_t e0, e1, e2;
+                if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, h->stream); }
+                if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 4) != CUSOLVER_STATUS_SUCCESS)
+                    return fail(ASC_ERR_CUDA, "cusolverDnDpotrf failed");
+                if (timing) cudaEventRecord(e1, h->stream);
+                if (cusolverDnDpotri(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 5) != CUSOLVER_STATUS_SUCCESS)
+                    return fail(ASC_ERR_CUDA, "cusolverDnDpotri failed");
+                if (timing) {
+                    cudaEventRecord(e2, h->stream); cudaEventSynchronize(e2);
+                    float a = 0, b = 0, c = 0; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2); cudaEventElapsedTime(&c, h->ev[3], e0);
+                    fprintf(stderr, "[asc] coarse nz=%d potrf %.2f ms potri %.2f ms (since solve start %.2f ms)\n", nz, a, b, c);
+                    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+                }
+            }
         } else {
             pose_invert_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, lambda, h->Bpp, h->gr, h->Dloc, h->rloc, h->Minv, h->rhs, h->flags + 2);
         }
@@ -309,9 +363,11 @@ struct Engine {
         h->launches += 3;
         prof_start(h, 3);
         if (update_p)
-            schur_pass_a_kernel<N, true><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4);
+            schur_pass_a_kernel<N, true><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4,
+                                                                                   h->use_coarse ? h->zc : nullptr, h->pose_cluster);
         else
-            schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4);
+            schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4, nullptr,
+                                                                                    nullptr);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 3);
         prof_start(h, 4);
@@ -333,15 +389,22 @@ struct Engine {
         const int nUpd = h->use_clusters ? h->nC : h->nCtaPose;
         h->launches += 3;
         if (h->use_clusters) {
+            double* rc_ = h->use_coarse ? h->rc : nullptr;
             pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(1, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp, h->scal,
-                                                                  h->flags, h->partA);
-            pcg_init_k_kernel<<<1, 32, 0, h->stream>>>((int64_t)PN, h->rhs, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->status + 40);
+                                                                  h->flags, h->partA, rc_);
+            pcg_init_k_kernel<<<1, 32, 0, h->stream>>>((int64_t)PN, h->rhs, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->status + 40,
+                                                      rc_ ? rc_ + (size_t)h->nC * N : nullptr);
             CUDA_TRY(cudaGetLastError());
-            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags);
+            if (h->use_coarse) {
+                const double one = 1.0, zero = 0.0;
+                if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->rc, 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
+                    return fail(ASC_ERR_CUDA, "cublasDsymv failed");
+            }
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN);
         } else {
             pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
             CUDA_TRY(cudaGetLastError());
-            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags);
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr);
         }
         CUDA_TRY(cudaGetLastError());
         const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
@@ -365,20 +428,28 @@ struct Engine {
                     pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
                 }
                 pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, pc_, nC, pb_, nB, h->BKK, h->MinvK, h->vp, h->vx, h->vr, h->vz,
-                                                        h->ybuf + PN, h->scal, h->flags);
+                                                        h->ybuf + PN, h->scal, h->flags, h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr);
                 CUDA_TRY(cudaGetLastError());
-                if (h->use_clusters)
+                if (h->use_clusters) {
                     pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
-                                                                          h->scal, h->flags, h->partA);
+                                                                          h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr);
+                    if (h->use_coarse) {
+                        const double one = 1.0, zero = 0.0;
+                        if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->rc, 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
+                            return fail(ASC_ERR_CUDA, "cublasDsymv failed");
+                        h->launches += 1;
+                    }
+                }
                 else
                     pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
                 CUDA_TRY(cudaGetLastError());
                 h->launches += 3;
-                pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, h->partA, nUpd, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags);
+                pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, h->partA, nUpd, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags,
+                                                        h->use_coarse ? h->rc : nullptr, h->zc, h->nz);
                 CUDA_TRY(cudaGetLastError());
             }
             launched += chunk;
-            CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(cudaMemcpyAsync(h->h_status + 32, h->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(cudaStreamSynchronize(h->stream));
             if (h->h_flags[0] || launched >= h->prm.pcg_max_iters + chunk) break;
@@ -390,7 +461,8 @@ struct Engine {
     // delta_l = Cinv (g_l - W^T delta_r) -> dl4
     static int backsub(asc_handle* h) {
         h->launches += 2;
-        schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, h->vx, nullptr, nullptr, nullptr, h->v4);
+        schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, h->vx, nullptr, nullptr, nullptr, h->v4, nullptr,
+                                                                                nullptr);
         CUDA_TRY(cudaGetLastError());
         schur_pass_b_kernel<true><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->l_perm, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
                                                                    h->cg4, h->dl4, nullptr);
@@ -402,12 +474,16 @@ struct Engine {
     static int solve(asc_handle* h, double lambda, int* iters) {
         int rc = prepare(h, lambda);
         if (rc) return rc;
-        rc = pcg(h, lambda, iters);
+        int its_local = 0;
+        rc = pcg(h, lambda, &its_local);
+        if (iters) *iters = its_local;
         if (rc) return rc;
+        if (h->use_coarse) { if (h->coarse_fresh) h->coarse_ref_iters = its_local; h->coarse_last_iters = its_local; }
         const int big = 0x7fffffff;
         if (h->h_flags[1] != big) { h->fail_kind = 'l'; h->fail_index = h->h_flags[1]; return fail(ASC_ERR_INDETERMINATE, "landmark block %d is not positive definite", h->h_flags[1]); }
         if (h->h_flags[2] != big) { h->fail_kind = 'q'; h->fail_index = h->h_flags[2]; return fail(ASC_ERR_INDETERMINATE, "pose block %d is not positive definite", h->h_flags[2]); }
         if (h->h_flags[3] != big) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "extrinsic block is not positive definite"); }
+        if (h->use_coarse && (h->h_flags[4] != 0 || h->h_flags[5] != 0)) { h->fail_kind = 'q'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "coarse-level factorisation failed (info %d/%d)", h->h_flags[4], h->h_flags[5]); }
         if (h->h_status[32 + 6] != 0.0) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "PCG breakdown: p^T S p <= 0"); }
         return backsub(h);
     }
@@ -599,6 +675,8 @@ int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
         }
         if (ok) {
             accept_try(h);
+            // a step that changed the error a lot changed the robust weights (hence S) a lot: rebuild the coarse operator
+            if ((*error - new_error) > 0.05 * *error) h->coarse_valid = false;
             *error = new_error;
             *lambda = std::max(*lambda / p.lambda_factor, p.lambda_lower_bound);
             lg->accepted = 1;
@@ -748,6 +826,7 @@ void asc_default_params(asc_params* p) {
     p->device = -1;
     p->pcg_cluster_max = 10;
     p->pcg_cluster_covis = 0.25;
+    p->pcg_coarse_max_dim = 16384;
 }
 
 const char* asc_last_error(void) { return g_last_error.c_str(); }
@@ -791,6 +870,8 @@ int asc_destroy(asc_handle* h) {
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->solver) cusolverDnDestroy(h->solver);
+    if (h->blas) cublasDestroy(h->blas);
     free_device(h);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_ev) cudaEventDestroy(ev);
@@ -837,6 +918,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     const int N = h->N;
     h->P = P; h->L = L; h->M = M;
     h->values_set = false; h->linearized = false; h->lin_lambda = -1.0;
+    h->coarse_valid = false; h->coarse_ref_iters = 0; h->coarse_last_iters = 0;
     // constants
     const asc_params& pr = h->prm;
     h->cm.inv_sigma_px = 1.0 / pr.sigma_px;
@@ -875,6 +957,9 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     // ---- preconditioner clusters: runs of consecutive keyframes that share landmarks
     const int gmax = std::max(1, std::min(pr.pcg_cluster_max, 128 / N));
     h->use_clusters = gmax > 1;
+    struct PairRec { long long key; int a, b; };
+    std::vector<PairRec> pairs;
+    std::vector<int> inc_lo, inc_hi, inc_lm, inc_cl, dest_ptr, dest_ca, dest_cb, pair_a, pair_b, cl_inc_ptr, cl_inc;
     std::vector<int> cl_ptr, pose_cluster(P, 0), run_lo, run_hi;
     std::vector<long long> cl_off;
     if (h->use_clusters) {
@@ -918,17 +1003,43 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         }
         h->scTotal = (size_t)cl_off[h->nC];
         run_lo.assign(M, 0); run_hi.assign(M, 0);
+        h->nz = h->nC * N + 6;
+        h->use_coarse = pr.pcg_coarse_max_dim > 0 && h->nz <= pr.pcg_coarse_max_dim && h->nC > 1;
         for (int j = 0; j < L; ++j) {
             int a = lm_ptr[j];
+            const size_t first_inc = inc_lo.size();
             while (a < lm_ptr[j + 1]) {
                 int b = a + 1;
                 const int cid = pose_cluster[l_pose[a]];
                 while (b < lm_ptr[j + 1] && pose_cluster[l_pose[b]] == cid) ++b;
                 for (int kk = a; kk < b; ++kk) { run_lo[l_perm[kk]] = a; run_hi[l_perm[kk]] = b; }
+                if (h->use_coarse) { inc_lo.push_back(a); inc_hi.push_back(b); inc_lm.push_back(j); inc_cl.push_back(cid); }
                 a = b;
             }
+            if (h->use_coarse)   // block updates of E = Z^T S Z: lower triangle of cluster pairs, in landmark order
+                for (size_t ia = first_inc; ia < inc_lo.size(); ++ia)
+                    for (size_t ib = first_inc; ib < inc_lo.size(); ++ib)
+                        if (inc_cl[ia] >= inc_cl[ib]) pairs.push_back({(long long)inc_cl[ia] * h->nC + inc_cl[ib], (int)ia, (int)ib});
         }
-    } else { h->nC = 0; h->nmax = 0; h->scTotal = 0; }
+        if (h->use_coarse) {
+            std::stable_sort(pairs.begin(), pairs.end(), [](const PairRec& x, const PairRec& y) { return x.key < y.key; });
+            for (size_t i = 0; i < pairs.size(); ++i) {
+                if (i == 0 || pairs[i].key != pairs[i - 1].key) {
+                    dest_ptr.push_back((int)i);
+                    dest_ca.push_back((int)(pairs[i].key / h->nC)); dest_cb.push_back((int)(pairs[i].key % h->nC));
+                }
+                pair_a.push_back(pairs[i].a); pair_b.push_back(pairs[i].b);
+            }
+            dest_ptr.push_back((int)pairs.size());
+            h->nInc = (int)inc_lo.size(); h->nDest = (int)dest_ca.size();
+            cl_inc_ptr.assign(h->nC + 1, 0);
+            for (int c : inc_cl) cl_inc_ptr[c + 1]++;
+            for (int c = 0; c < h->nC; ++c) cl_inc_ptr[c + 1] += cl_inc_ptr[c];
+            cl_inc.assign(inc_cl.size(), 0);
+            std::vector<int> f(cl_inc_ptr.begin(), cl_inc_ptr.end() - 1);
+            for (size_t i = 0; i < inc_cl.size(); ++i) cl_inc[f[inc_cl[i]]++] = (int)i;
+        }
+    } else { h->nC = 0; h->nmax = 0; h->scTotal = 0; h->use_coarse = false; }
     h->h_p_orig = p_orig;
 
     const size_t PN = (size_t)P * N, Mz = (size_t)M;
@@ -955,6 +1066,24 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         ALLOC(cl_ptr, h->nC + 1); ALLOC(cl_off, h->nC + 1); ALLOC(pose_cluster, P); ALLOC(p_run_lo, Mz); ALLOC(p_run_hi, Mz);
         ALLOC(Wm, Mz * 3 * N); ALLOC(Mc, h->scTotal);
     }
+    if (h->use_coarse) {
+        const size_t ni = h->nInc, nd = h->nDest, np = pair_a.size(), nz = h->nz;
+        ALLOC(inc_lo, ni); ALLOC(inc_hi, ni); ALLOC(inc_lm, ni); ALLOC(dest_ptr, nd + 1); ALLOC(dest_ca, nd); ALLOC(dest_cb, nd);
+        ALLOC(pair_a, np); ALLOC(pair_b, np); ALLOC(cl_inc_ptr, h->nC + 1); ALLOC(cl_inc, ni);
+        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, nz); ALLOC(zc, nz);
+        if (!h->solver) {
+            if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cusolverDnCreate failed");
+            if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cublasCreate failed");
+            cusolverDnSetStream(h->solver, h->stream);
+            cublasSetStream(h->blas, h->stream);
+        }
+        int lw1 = 0, lw2 = 0;
+        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw1) != CUSOLVER_STATUS_SUCCESS ||
+            cusolverDnDpotri_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw2) != CUSOLVER_STATUS_SUCCESS)
+            return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
+        h->lwork = std::max(lw1, lw2);
+        ALLOC(work, (size_t)h->lwork);
+    }
     ALLOC(Minv, PN * N); ALLOC(MinvK, 36); ALLOC(rhs, PN + 8);
     ALLOC(vx, PN + 8); ALLOC(vr, PN + 8); ALLOC(vz, PN + 8); ALLOC(vp, PN + 8);
     ALLOC(ybuf, PN + 8 + 2 * kPartCols);
@@ -963,7 +1092,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
     h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
     ALLOC(errblk, h->nErrBlk);
-    ALLOC(scal, 8); ALLOC(status, 64); ALLOC(flags, 4); ALLOC(cheir, 1);
+    ALLOC(scal, 8); ALLOC(status, 64); ALLOC(flags, 8); ALLOC(cheir, 1); ALLOC(SKK, 36);
 #undef ALLOC
 #define UP(dst, src, bytes) CUDA_TRY(cudaMemcpyAsync(h->dst, src, (bytes), cudaMemcpyHostToDevice, h->stream))
     UP(pose_ptr, pose_ptr.data(), sizeof(int) * (P + 1)); UP(lm_ptr, lm_ptr.data(), sizeof(int) * (L + 1));
@@ -976,6 +1105,12 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         UP(cl_ptr, cl_ptr.data(), sizeof(int) * (h->nC + 1)); UP(cl_off, cl_off.data(), sizeof(long long) * (h->nC + 1));
         UP(pose_cluster, pose_cluster.data(), sizeof(int) * P);
         if (M) { UP(p_run_lo, run_lo.data(), sizeof(int) * Mz); UP(p_run_hi, run_hi.data(), sizeof(int) * Mz); }
+    }
+    if (h->use_coarse && h->nInc) {
+        UP(inc_lo, inc_lo.data(), sizeof(int) * h->nInc); UP(inc_hi, inc_hi.data(), sizeof(int) * h->nInc); UP(inc_lm, inc_lm.data(), sizeof(int) * h->nInc);
+        UP(dest_ptr, dest_ptr.data(), sizeof(int) * (h->nDest + 1)); UP(dest_ca, dest_ca.data(), sizeof(int) * h->nDest); UP(dest_cb, dest_cb.data(), sizeof(int) * h->nDest);
+        UP(pair_a, pair_a.data(), sizeof(int) * pair_a.size()); UP(pair_b, pair_b.data(), sizeof(int) * pair_b.size());
+        UP(cl_inc_ptr, cl_inc_ptr.data(), sizeof(int) * (h->nC + 1)); UP(cl_inc, cl_inc.data(), sizeof(int) * h->nInc);
     }
     UP(enc, enc, sizeof(double) * PN);
     if (L) UP(lm_prior, lm_prior, sizeof(double) * 3 * L);
@@ -1040,6 +1175,7 @@ int asc_optimize(asc_handle* h, int32_t mode, asc_iter_log* log, int32_t log_cap
     if (mode != ASC_BATCH_LM && mode != ASC_BATCH_DOGLEG) return fail(ASC_ERR_INVALID, "unknown optimisation mode %d", mode);
     const asc_params& p = h->prm;
     double error = 0.0, lambda = p.lambda_initial, Delta = p.delta_initial;
+    h->coarse_valid = false;   // every optimize() call is self-contained and bitwise repeatable
     rc = dispatch_error(h, h->q, h->lm4, h->X, &error);   // NonlinearOptimizer state at construction
     if (rc) return rc;
     int iterations = 0;
@@ -1130,6 +1266,7 @@ int asc_solve_damped(asc_handle* h, double lambda, double* dq, double* dl, doubl
     if (rc) return rc;
     if (!h->linearized) { rc = dispatch_linearize(h, false, nullptr, nullptr); if (rc) return rc; }
     int its = 0;
+    h->coarse_valid = false;
     rc = dispatch_solve(h, lambda, &its);
     if (pcg_iterations) *pcg_iterations = its;
     if (rc) return rc;

@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(128)
 pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const long long* __restrict__ cl_off, const double* __restrict__ Mc,
                           const double* __restrict__ rhs, const double* __restrict__ y, double* __restrict__ x, double* __restrict__ r,
                           double* __restrict__ z, double* __restrict__ p, const double* __restrict__ scal, const int* __restrict__ done,
-                          double* __restrict__ part) {
+                          double* __restrict__ part, double* __restrict__ rc) {
     if (!init && *done) return;
     __shared__ double rs[128];
     __shared__ double red[4];
@@ -831,6 +831,11 @@ pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const
     }
     rs[t] = rm;
     __syncthreads();
+    if (rc && t < N) {   // restriction Z^T r for this cluster
+        double a = 0.0;
+        for (int i = t; i < n; i += N) a += rs[i];
+        rc[(size_t)c * N + t] = a;
+    }
     double zm = 0.0;
     if (t < n) {
         const double* Mcol = Mc + cl_off[c] + t;   // column t == row t (symmetric): coalesced across threads
@@ -846,7 +851,8 @@ pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const
 
 // K rows at PCG start: x_K = 0, r_K = rhs_K, z_K = MinvK r_K, p_K = z_K; scal[7] = r_K . z_K   (one warp)
 __global__ void pcg_init_k_kernel(int64_t PN, const double* __restrict__ rhs, const double* __restrict__ MinvK, double* __restrict__ x,
-                                  double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ kdot) {
+                                  double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ kdot,
+                                  double* __restrict__ rcK) {
     const int lane = threadIdx.x;
     const double rk = lane < 6 ? rhs[PN + lane] : 0.0;
     double zk = 0.0;
@@ -855,9 +861,114 @@ __global__ void pcg_init_k_kernel(int64_t PN, const double* __restrict__ rhs, co
         const double ri = __shfl_sync(kFull, rk, i);
         if (lane < 6) zk = fma(MinvK[6 * lane + i], ri, zk);
     }
-    if (lane < 6) { x[PN + lane] = 0.0; r[PN + lane] = rk; z[PN + lane] = zk; p[PN + lane] = zk; }
+    if (lane < 6) { x[PN + lane] = 0.0; r[PN + lane] = rk; z[PN + lane] = zk; p[PN + lane] = zk; if (rcK) rcK[lane] = rk; }
     const double d = warp_sum(lane < 6 ? rk * zk : 0.0);
     if (lane == 0) *kdot = d;
+}
+
+// ------------------------------------------------------------------ coarse level of the two-level preconditioner
+// Coarse space Z: one uniform joint-offset vector per cluster (N columns each) plus the extrinsic (6 columns).
+// These are the slow modes of arm calibration -- a whole group of keyframes and the landmarks it sees shifting
+// together -- which cluster-Jacobi cannot damp.  E = Z^T S Z is assembled block by block in a fixed order, factorised
+// and inverted by cuSOLVER (plain library call, once per damping value), and applied additively: M^-1 = M_cl^-1 + Z E^-1 Z^T.
+//
+// "incidence" = (landmark j, cluster c) with at least one observation; V = sum of W_m over them, T = V Cinv_j.
+template <int N>
+__global__ void __launch_bounds__(128)
+inc_v_kernel(int nInc, const int* __restrict__ inc_lo, const int* __restrict__ inc_hi, const int* __restrict__ inc_lm,
+             const int* __restrict__ l_perm, const double* __restrict__ Wm, const double* __restrict__ Cinv, double* __restrict__ V,
+             double* __restrict__ T) {
+    __shared__ double sv[4][3 * N];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int inc = blockIdx.x * 4 + warp;
+    if (inc >= nInc) return;
+    const int lo = inc_lo[inc], hi = inc_hi[inc];
+    for (int e = lane; e < 3 * N; e += 32) {
+        double a = 0.0;
+        for (int kk = lo; kk < hi; ++kk) a += Wm[(size_t)__ldg(l_perm + kk) * 3 * N + e];
+        sv[warp][e] = a;
+        V[(size_t)inc * 3 * N + e] = a;
+    }
+    __syncwarp();
+    const double* ci = Cinv + 6 * (size_t)inc_lm[inc];
+    for (int e = lane; e < 3 * N; e += 32) {
+        const int a = e / 3, cc = e % 3;
+        const double c0_ = cc == 0 ? ci[0] : (cc == 1 ? ci[1] : ci[2]);
+        const double c1_ = cc == 0 ? ci[1] : (cc == 1 ? ci[3] : ci[4]);
+        const double c2_ = cc == 0 ? ci[2] : (cc == 1 ? ci[4] : ci[5]);
+        T[(size_t)inc * 3 * N + e] = sv[warp][3 * a] * c0_ + sv[warp][3 * a + 1] * c1_ + sv[warp][3 * a + 2] * c2_;
+    }
+}
+
+// E[ca][cb] = - sum over the destination's (incidence a, incidence b) pairs of T_a V_b^T ; one warp per destination block
+template <int N>
+__global__ void __launch_bounds__(128)
+coarse_blocks_kernel(int nDest, const int* __restrict__ dest_ptr, const int* __restrict__ dest_ca, const int* __restrict__ dest_cb,
+                     const int* __restrict__ pair_a, const int* __restrict__ pair_b, const double* __restrict__ V, const double* __restrict__ T,
+                     double* __restrict__ E, int nz) {
+    constexpr int NE = (N * N + 31) / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x * 4 + warp;
+    if (d >= nDest) return;
+    double acc[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) acc[i] = 0.0;
+    for (int pr = dest_ptr[d]; pr < dest_ptr[d + 1]; ++pr) {
+        const double* Ta = T + (size_t)__ldg(pair_a + pr) * 3 * N;
+        const double* Vb = V + (size_t)__ldg(pair_b + pr) * 3 * N;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+            const int e = lane + 32 * i;
+            if (e < N * N) {
+                const int a = e / N, b = e % N;
+                acc[i] += Ta[3 * a] * Vb[3 * b] + Ta[3 * a + 1] * Vb[3 * b + 1] + Ta[3 * a + 2] * Vb[3 * b + 2];
+            }
+        }
+    }
+    const int ca = dest_ca[d], cb = dest_cb[d];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+        const int e = lane + 32 * i;
+        if (e < N * N) E[(size_t)(ca * N + e / N) * nz + cb * N + e % N] = -acc[i];
+    }
+}
+
+// E[c][c] += sum_{p in c} (B_pp + lambda I)     (rank 0 only in a multi-GPU run); thread per (c, a, b)
+__global__ void coarse_diag_kernel(int nC, int N, double lambda, const int* __restrict__ cl_ptr, const double* __restrict__ Bpp,
+                                   double* __restrict__ E, int nz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nC * N * N) return;
+    const int c = i / (N * N), a = (i / N) % N, b = i % N;
+    double s = 0.0;
+    for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) s += Bpp[(size_t)p * N * N + a * N + b];
+    if (a == b) s += lambda * (cl_ptr[c + 1] - cl_ptr[c]);
+    E[(size_t)(c * N + a) * nz + c * N + b] += s;
+}
+
+__global__ void scale_block_kernel(double* E, int nz, int off, double s) {
+    const int i = threadIdx.x;
+    if (i < 36) E[(size_t)(off + i / 6) * nz + off + i % 6] *= s;
+}
+
+// K rows: E[K r][c a] = sum_{p in c} B_pK[a][r] - sum over the cluster's incidences of (T W_Kj^T)[a][r]; thread per (c, a, r)
+__global__ void coarse_k_kernel(int nC, int N, int add_diag, const int* __restrict__ cl_ptr, const int* __restrict__ cl_inc_ptr,
+                                const int* __restrict__ cl_inc, const int* __restrict__ inc_lm, const double* __restrict__ T,
+                                const double* __restrict__ WK, const double* __restrict__ BpK, const double* __restrict__ SKK,
+                                double* __restrict__ E, int nz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 36) E[(size_t)(nC * N + i / 6) * nz + nC * N + i % 6] = SKK[i];
+    if (i >= nC * N * 6) return;
+    const int c = i / (N * 6), a = (i / 6) % N, r = i % 6;
+    double s = 0.0;
+    if (add_diag)
+        for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) s += BpK[(size_t)p * N * 6 + a * 6 + r];
+    for (int k = cl_inc_ptr[c]; k < cl_inc_ptr[c + 1]; ++k) {
+        const int inc = cl_inc[k];
+        const double* t = T + (size_t)inc * 3 * N + 3 * a;
+        const double* w = WK + 18 * (size_t)inc_lm[inc] + 3 * r;
+        s -= t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
+    }
+    E[(size_t)(nC * N + r) * nz + c * N + a] = s;
 }
 
 // ------------------------------------------------------------------ K3: implicit Schur complement  y = S x
@@ -865,7 +976,8 @@ __global__ void pcg_init_k_kernel(int64_t PN, const double* __restrict__ rhs, co
 template <int N, bool UPDATE_P>
 __global__ void __launch_bounds__(kCtaThreads)
 schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const double2* __restrict__ J, double* __restrict__ x,
-                    const double* __restrict__ z, const double* __restrict__ scal, const int* __restrict__ done, double* __restrict__ v4) {
+                    const double* __restrict__ z, const double* __restrict__ scal, const int* __restrict__ done, double* __restrict__ v4,
+                    const double* __restrict__ zc, const int* __restrict__ pose_cluster) {
     if (done && *done) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * kWarpsPerCta + warp;
@@ -873,7 +985,12 @@ schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const do
     double mine = 0.0;
     if (lane < N) {
         mine = x[(size_t)p * N + lane];
-        if (UPDATE_P) { mine = z[(size_t)p * N + lane] + scal[1] * mine; x[(size_t)p * N + lane] = mine; }   // scal[1] = beta
+        if (UPDATE_P) {   // p <- z + beta p  (z = cluster part + coarse part Z zc); scal[1] = beta
+            double zz = z[(size_t)p * N + lane];
+            if (zc) zz += zc[(size_t)pose_cluster[p] * N + lane];
+            mine = zz + scal[1] * mine;
+            x[(size_t)p * N + lane] = mine;
+        }
     }
     double xp[N];
 #pragma unroll
@@ -1049,7 +1166,8 @@ __device__ inline double block_reduce_rows(const double* __restrict__ part, int 
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_mid_kernel(int P, int N, double lambda, const double* __restrict__ partC, int nC, const double* __restrict__ partB, int nB,
                const double* __restrict__ BKK, const double* __restrict__ MinvK, double* __restrict__ p, double* __restrict__ x,
-               double* __restrict__ r, double* __restrict__ z, double* __restrict__ yK_out, double* __restrict__ scal, int* __restrict__ done) {
+               double* __restrict__ r, double* __restrict__ z, double* __restrict__ yK_out, double* __restrict__ scal, int* __restrict__ done,
+               double* __restrict__ rcK) {
     if (*done) return;
     __shared__ double scratch[kReduceThreads];
     __shared__ double sc[kPcgCols], sb[kPcgCols];
@@ -1079,6 +1197,7 @@ pcg_mid_kernel(int P, int N, double lambda, const double* __restrict__ partC, in
             x[(size_t)P * N + lane] += alpha * pK[lane];
             rk = r[(size_t)P * N + lane] - alpha * yk;
             r[(size_t)P * N + lane] = rk;
+            if (rcK) rcK[lane] = rk;
             sh[lane] = rk;
         }
         __syncwarp();
@@ -1136,13 +1255,25 @@ pcg_update_kernel(int P, const double* __restrict__ p, const double* __restrict_
 // rz_new, beta, convergence test, p_K <- z_K + beta p_K.  One block of 256 threads.
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_end_kernel(int P, int N, const double* __restrict__ part, int nPart, double tol2, int max_iters, double* __restrict__ p,
-               const double* __restrict__ z, double* __restrict__ scal, int* __restrict__ done) {
+               double* __restrict__ z, double* __restrict__ scal, int* __restrict__ done, const double* __restrict__ rc,
+               const double* __restrict__ zc, int nz) {
     if (*done) return;
     __shared__ double scratch[kReduceThreads];
     __shared__ double so[1];
     const int lane = threadIdx.x & 31;
     block_sum_cols<1>(part, nPart, so, scratch);
-    const double t = so[0];
+    double t = so[0];
+    if (rc) {   // r . (Z zc) = (Z^T r) . zc ; and the K rows of z get their coarse part
+        __shared__ double prod[kReduceThreads];
+        double a = 0.0;
+        for (int i = threadIdx.x; i < nz; i += kReduceThreads) a += rc[i] * zc[i];
+        prod[threadIdx.x] = a;
+        __syncthreads();
+        block_sum_cols<1>(prod, kReduceThreads, so, scratch);
+        t += so[0];
+        if (threadIdx.x < 6) z[(size_t)P * N + threadIdx.x] += zc[nz - 6 + threadIdx.x];
+        __syncthreads();
+    }
     if (threadIdx.x < 32) {
         const double rz_new = t + scal[7];
         const double beta = rz_new / scal[2];
@@ -1206,11 +1337,23 @@ pcg_init_kernel(int P, const double* __restrict__ rhs, const double* __restrict_
 
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __restrict__ kdot, double* __restrict__ scal,
-                    int* __restrict__ done) {
+                    int* __restrict__ done, const double* __restrict__ rc, const double* __restrict__ zc, int nz, double* __restrict__ zK,
+                    double* __restrict__ pK) {
     __shared__ double scratch[kReduceThreads];
     __shared__ double so[1];
     block_sum_cols<1>(part, nPart, so, scratch);
     double t = so[0];
+    if (rc) {
+        __shared__ double prod[kReduceThreads];
+        double a = 0.0;
+        for (int i = threadIdx.x; i < nz; i += kReduceThreads) a += rc[i] * zc[i];
+        prod[threadIdx.x] = a;
+        __syncthreads();
+        block_sum_cols<1>(prod, kReduceThreads, so, scratch);
+        t += so[0];
+        if (threadIdx.x < 6) { const double v = zK[threadIdx.x] + zc[nz - 6 + threadIdx.x]; zK[threadIdx.x] = v; pK[threadIdx.x] = v; }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         if (kdot) t += *kdot;
         scal[0] = 0.0; scal[1] = 0.0; scal[2] = t; scal[3] = t; scal[4] = 0.0; scal[5] = 0.0; scal[6] = 0.0; scal[7] = 0.0;
@@ -1222,7 +1365,7 @@ pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __
 // S_KK = B_KK + lambda I - sum_j W_Kj Cinv W_Kj^T ; rhs_K = g_K - sum_j W_Kj cg_j ; MinvK = S_KK^-1
 __global__ void __launch_bounds__(256)
 k_rows_kernel(double lambda, const double* __restrict__ part, int nPart, const double* __restrict__ BKK, const double* __restrict__ gK,
-              double* __restrict__ MinvK, double* __restrict__ rhsK, int* __restrict__ fail_idx) {
+              double* __restrict__ MinvK, double* __restrict__ rhsK, double* __restrict__ SKK_out, int* __restrict__ fail_idx) {
     __shared__ double s[8][kPartCols];
     __shared__ double A[6][13];
     const int lane = threadIdx.x & 31;
@@ -1235,6 +1378,7 @@ k_rows_kernel(double lambda, const double* __restrict__ part, int nPart, const d
             const int c = r + rem;
             const double v = BKK[6 * r + c] - t + (r == c ? lambda : 0.0);
             A[r][c] = v; A[c][r] = v;
+            SKK_out[6 * r + c] = v; SKK_out[6 * c + r] = v;
         }
         if (lane >= 21 && lane < 27) rhsK[lane - 21] = gK[lane - 21] - t;
         for (int i = lane; i < 36; i += 32) A[i / 6][6 + i % 6] = (i / 6 == i % 6) ? 1.0 : 0.0;

@@ -77,6 +77,9 @@ typedef struct asc_params {
     int32_t pcg_cluster_max;         /* max keyframes per cluster (10); <=1: one block per keyframe */
     double pcg_cluster_covis;        /* start a new cluster when the share of common landmarks with the
                                         previous keyframe drops below this (0.25) */
+    int32_t pcg_coarse_max_dim;      /* second preconditioner level (one joint-offset vector per cluster + the
+                                        extrinsic, dense factorisation by cuSOLVER) is used while its dimension
+                                        nClusters*N+6 is <= this (16384); 0 switches it off */
 } asc_params;
 
 /* One record per outer iterate() of the optimiser */
