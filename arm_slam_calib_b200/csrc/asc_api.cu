@@ -139,7 +139,9 @@ struct asc_handle {
     int *inc_lo = nullptr, *inc_hi = nullptr, *inc_lm = nullptr, *dest_ptr = nullptr, *dest_ca = nullptr, *dest_cb = nullptr;
     int *pair_a = nullptr, *pair_b = nullptr, *cl_inc_ptr = nullptr, *cl_inc = nullptr;
     double *Vinc = nullptr, *Tinc = nullptr, *E = nullptr, *rc = nullptr, *zc = nullptr, *SKK = nullptr, *work = nullptr;
-    int lwork = 0;
+    int lwork = 0, lworkf = 0;
+    float *Ef = nullptr, *workf = nullptr, *Einvf = nullptr;
+    bool coarse_f32_active = false;   // E^-1 currently lives in Ef (fp32) rather than in E (fp64)
     bool coarse_valid = false;      // E holds a factorised inverse (possibly from an earlier lambda / linearisation)
     bool coarse_fresh = false;      // ... computed for exactly the current system
     int coarse_ref_iters = 0;       // PCG iterations of the solve that followed the last refresh
@@ -338,15 +340,35 @@ struct Engine {
                 static const bool timing = getenv("ASC_TIMING") != nullptr;
                 cudaEvent_t e0, e1, e2;
                 if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, h->stream); }
-                if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 4) != CUSOLVER_STATUS_SUCCESS)
-                    return fail(ASC_ERR_CUDA, "cusolverDnDpotrf failed");
-                if (timing) cudaEventRecord(e1, h->stream);
-                if (cusolverDnDpotri(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 5) != CUSOLVER_STATUS_SUCCESS)
-                    return fail(ASC_ERR_CUDA, "cusolverDnDpotri failed");
+                bool f32_ok = false;
+                if (h->prm.pcg_coarse_fp32 && h->Ef) {
+                    const size_t nn = (size_t)nz * nz;
+                    to_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->E, h->Ef, nn);
+                    if (cusolverDnSpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->Ef, nz, h->workf, h->lworkf, h->flags + 6) != CUSOLVER_STATUS_SUCCESS)
+                        return fail(ASC_ERR_CUDA, "cusolverDnSpotrf failed");
+                    if (timing) cudaEventRecord(e1, h->stream);
+                    // E^-1 = solve(U^T U, I): two TRSMs run much closer to peak than cuSOLVER's potri
+                    identity_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->Einvf, nz);
+                    if (cusolverDnSpotrs(h->solver, CUBLAS_FILL_MODE_UPPER, nz, nz, h->Ef, nz, h->Einvf, nz, h->flags + 7) != CUSOLVER_STATUS_SUCCESS)
+                        return fail(ASC_ERR_CUDA, "cusolverDnSpotrs failed");
+                    CUDA_TRY(cudaGetLastError());
+                    int info[2] = {0, 0};
+                    CUDA_TRY(cudaMemcpyAsync(info, h->flags + 6, sizeof info, cudaMemcpyDeviceToHost, h->stream));
+                    CUDA_TRY(cudaStreamSynchronize(h->stream));
+                    f32_ok = info[0] == 0 && info[1] == 0;   // not positive definite in fp32: redo in fp64 below
+                }
+                h->coarse_f32_active = f32_ok;
+                if (!f32_ok) {
+                    if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 4) != CUSOLVER_STATUS_SUCCESS)
+                        return fail(ASC_ERR_CUDA, "cusolverDnDpotrf failed");
+                    if (timing) cudaEventRecord(e1, h->stream);
+                    if (cusolverDnDpotri(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 5) != CUSOLVER_STATUS_SUCCESS)
+                        return fail(ASC_ERR_CUDA, "cusolverDnDpotri failed");
+                }
                 if (timing) {
                     cudaEventRecord(e2, h->stream); cudaEventSynchronize(e2);
                     float a = 0, b = 0, c = 0; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2); cudaEventElapsedTime(&c, h->ev[3], e0);
-                    fprintf(stderr, "[asc] coarse nz=%d potrf %.2f ms potri %.2f ms (since solve start %.2f ms)\n", nz, a, b, c);
+                    fprintf(stderr, "[asc] coarse nz=%d %s potrf %.2f ms potri %.2f ms (since solve start %.2f ms)\n", nz, f32_ok ? "fp32" : "fp64", a, b, c);
                     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
                 }
             }
@@ -383,6 +405,20 @@ struct Engine {
         return ASC_OK;
     }
 
+    // zc = E^-1 rc (coarse correction of the preconditioner)
+    static int coarse_apply(asc_handle* h, const int* done) {
+        h->launches += 1;
+        if (h->coarse_f32_active) {
+            coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, h->rc, h->zc, h->nz, done);
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            const double one = 1.0, zero = 0.0;
+            if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->rc, 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
+                return fail(ASC_ERR_CUDA, "cublasDsymv failed");
+        }
+        return ASC_OK;
+    }
+
     // block-Jacobi PCG on the reduced system; solution left in vx.  Returns iterations through *iters.
     static int pcg(asc_handle* h, double lambda, int* iters) {
         const size_t PN = (size_t)h->P * N;
@@ -395,11 +431,7 @@ struct Engine {
             pcg_init_k_kernel<<<1, 32, 0, h->stream>>>((int64_t)PN, h->rhs, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->status + 40,
                                                       rc_ ? rc_ + (size_t)h->nC * N : nullptr);
             CUDA_TRY(cudaGetLastError());
-            if (h->use_coarse) {
-                const double one = 1.0, zero = 0.0;
-                if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->rc, 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
-                    return fail(ASC_ERR_CUDA, "cublasDsymv failed");
-            }
+            if (h->use_coarse) { int rc3 = coarse_apply(h, nullptr); if (rc3) return rc3; }
             pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN);
         } else {
             pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
@@ -433,12 +465,7 @@ struct Engine {
                 if (h->use_clusters) {
                     pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
                                                                           h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr);
-                    if (h->use_coarse) {
-                        const double one = 1.0, zero = 0.0;
-                        if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->rc, 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
-                            return fail(ASC_ERR_CUDA, "cublasDsymv failed");
-                        h->launches += 1;
-                    }
+                    if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags); if (rc3) return rc3; }
                 }
                 else
                     pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
@@ -676,7 +703,7 @@ int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
         if (ok) {
             accept_try(h);
             // a step that changed the error a lot changed the robust weights (hence S) a lot: rebuild the coarse operator
-            if ((*error - new_error) > 0.05 * *error) h->coarse_valid = false;
+            if ((*error - new_error) > 0.01 * *error) h->coarse_valid = false;
             *error = new_error;
             *lambda = std::max(*lambda / p.lambda_factor, p.lambda_lower_bound);
             lg->accepted = 1;
@@ -827,6 +854,7 @@ void asc_default_params(asc_params* p) {
     p->pcg_cluster_max = 10;
     p->pcg_cluster_covis = 0.25;
     p->pcg_coarse_max_dim = 16384;
+    p->pcg_coarse_fp32 = 1;
 }
 
 const char* asc_last_error(void) { return g_last_error.c_str(); }
@@ -1083,6 +1111,15 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
         h->lwork = std::max(lw1, lw2);
         ALLOC(work, (size_t)h->lwork);
+        if (pr.pcg_coarse_fp32) {
+            ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * nz);
+            int lf1 = 0, lf2 = 0;
+            if (cusolverDnSpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->Ef, h->nz, &lf1) != CUSOLVER_STATUS_SUCCESS ||
+                cusolverDnSpotri_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->Ef, h->nz, &lf2) != CUSOLVER_STATUS_SUCCESS)
+                return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
+            h->lworkf = std::max(lf1, lf2);
+            ALLOC(workf, (size_t)h->lworkf);
+        }
     }
     ALLOC(Minv, PN * N); ALLOC(MinvK, 36); ALLOC(rhs, PN + 8);
     ALLOC(vx, PN + 8); ALLOC(vr, PN + 8); ALLOC(vz, PN + 8); ALLOC(vp, PN + 8);

@@ -945,6 +945,59 @@ __global__ void coarse_diag_kernel(int nC, int N, double lambda, const int* __re
     E[(size_t)(c * N + a) * nz + c * N + b] += s;
 }
 
+// fp64 -> fp32 copy of the coarse matrix (only a preconditioner: single precision is enough, and it makes the
+// factorisation ~4x cheaper and the per-iteration product half the bytes).  Accumulation stays fp64 in the product.
+__global__ void __launch_bounds__(256) to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+__global__ void __launch_bounds__(256) identity_f32_kernel(float* __restrict__ A, int n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)n * n) A[i] = (i / n == i % n) ? 1.0f : 0.0f;
+}
+
+// cuSOLVER leaves the inverse in the row-major lower triangle (column-major UPPER); mirror it so rows are complete
+__global__ void __launch_bounds__(256) mirror_lower_f32_kernel(float* __restrict__ A, int n) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx > by) return;   // blocks on or below the diagonal hold valid data (row >= col)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int row = by * 32 + r, col = bx * 32 + tx;
+        tile[r][tx] = (row < n && col < n && row >= col) ? A[(size_t)row * n + col] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int row = bx * 32 + r, col = by * 32 + tx;   // transposed position
+        if (row < n && col < n && col > row) A[(size_t)row * n + col] = tile[tx][r];
+    }
+}
+
+// zc = Einv(fp32, full symmetric, row-major) * rc, one warp per row, fp64 accumulation
+__global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
+                                                              int n, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + warp;
+    if (row >= n) return;
+    const float* a = A + (size_t)row * n;
+    double acc0 = 0.0, acc1 = 0.0;
+    int i = lane * 2;
+    for (; i + 64 + 1 < n; i += 128) {
+        const float2 u = *reinterpret_cast<const float2*>(a + i);
+        const float2 v = *reinterpret_cast<const float2*>(a + i + 64);
+        acc0 = fma((double)u.x, x[i], fma((double)u.y, x[i + 1], acc0));
+        acc1 = fma((double)v.x, x[i + 64], fma((double)v.y, x[i + 65], acc1));
+    }
+    for (; i < n; i += 64) {
+        acc0 = fma((double)a[i], x[i], acc0);
+        if (i + 1 < n) acc0 = fma((double)a[i + 1], x[i + 1], acc0);
+    }
+    const double t = warp_sum(acc0 + acc1);
+    if (lane == 0) y[row] = t;
+}
+
 __global__ void scale_block_kernel(double* E, int nz, int off, double s) {
     const int i = threadIdx.x;
     if (i < 36) E[(size_t)(off + i / 6) * nz + off + i % 6] *= s;

@@ -80,6 +80,8 @@ typedef struct asc_params {
     int32_t pcg_coarse_max_dim;      /* second preconditioner level (one joint-offset vector per cluster + the
                                         extrinsic, dense factorisation by cuSOLVER) is used while its dimension
                                         nClusters*N+6 is <= this (16384); 0 switches it off */
+    int32_t pcg_coarse_fp32;         /* 1 (default): factorise/apply the coarse operator in fp32 (fp64 accumulation in the
+                                        product; falls back to fp64 if the fp32 Cholesky fails); 0: fp64 throughout */
 } asc_params;
 
 /* One record per outer iterate() of the optimiser */
