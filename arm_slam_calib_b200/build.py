@@ -11,15 +11,22 @@ SOURCES = ["asc_api.cu", "sim_generator.cpp"]
 DEPS = SOURCES + ["kernels.cuh", "host_math.h", os.path.join("..", "..", "include", "asc.h")]
 
 
-def needs_build():
+STAMP = LIB + ".dofs"   # which DOF instantiations the existing library holds ("all" = the default list)
+
+
+def needs_build(dof_list=None):
     if not os.path.exists(LIB):
+        return True
+    want = "all" if not dof_list else ",".join(map(str, dof_list))
+    have = open(STAMP).read().strip() if os.path.exists(STAMP) else ""
+    if want != have:
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
 def build(force=False, verbose=False, dof_list=None):
-    if not force and not needs_build():
+    if not force and not needs_build(dof_list):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,6 +41,8 @@ def build(force=False, verbose=False, dof_list=None):
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    with open(STAMP, "w") as f:
+        f.write("all" if not dof_list else ",".join(map(str, dof_list)))
     return LIB
 
 
