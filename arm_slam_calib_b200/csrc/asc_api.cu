@@ -1074,11 +1074,11 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     h->nCtaPose = cdiv(P, kWarpsPerCta);
     h->nBlkLm = std::max(1, cdiv(L, 128));
     int rc;
-#define ALLOC(ptr, count) if ((rc = dev_alloc(h, &h->ptr, (count)))) return rc
+#define ALLOC(ptr, count) do { if ((rc = dev_alloc(h, &h->ptr, (count)))) return rc; } while (0)
     ALLOC(pose_ptr, P + 1); ALLOC(p_lm, Mz); ALLOC(p_pose, Mz); ALLOC(p_orig, Mz); ALLOC(p_uv, Mz);
     ALLOC(lm_ptr, L + 1); ALLOC(l_pose, Mz); ALLOC(l_perm, Mz); ALLOC(l_uv, Mz);
     ALLOC(enc, PN); ALLOC(lm_prior, (size_t)L * 3);
-    if (has_enc) ALLOC(has_enc, P); else h->has_enc = nullptr;
+    if (has_enc) { ALLOC(has_enc, P); } else { h->has_enc = nullptr; }
     ALLOC(q, PN); ALLOC(q_try, PN); ALLOC(lm4, (size_t)L * 4); ALLOC(lm4_try, (size_t)L * 4); ALLOC(X, 12); ALLOC(X_try, 12);
     ALLOC(q_save, PN); ALLOC(lm4_save, (size_t)L * 4); ALLOC(X_save, 12);
     ALLOC(cam, (size_t)P * 12); ALLOC(chain, PN * 6);

@@ -1,0 +1,41 @@
+"""The GTSAM-shaped C++ facade (include/gtsam_facade/gtsam_facade.h): tests/cpp/facade_test.cpp builds the graph through
+AddFactor/AddValue-style calls and runs the body of ArmSlamCalib::OptimizeStep (src/ArmSlamCalib.cpp:438-467) unchanged."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def facade_exe(asc, tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("facade") / "facade_test")
+    libdir = os.path.join(ROOT, "arm_slam_calib_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++14", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"), "-o", exe, "-L", libdir, "-l:libasc_b200.so",
+                    "-Wl,-rpath," + libdir], check=True)
+    return exe
+
+
+def test_facade_compiles_and_fails_loudly_without_a_gpu(facade_exe):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([facade_exe, "BatchLM", "12"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode_name,mode", [("BatchLM", 0), ("BatchDogLeg", 1), ("BatchDogleg", 1)])
+def test_optimize_step_through_the_facade_matches_the_oracle(asc, oracle_cls, facade_exe, mode_name, mode):
+    r = subprocess.run([facade_exe, mode_name, "40"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    tok = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    iters, err, kx, ky, kz, found = int(tok[1]), float(tok[2]), float(tok[3]), float(tok[4]), float(tok[5]), int(tok[6])
+    pb = asc.make_sim_problem(trajectory_size=40, seed=3)
+    ref = oracle_cls(pb, asc.default_params()).optimize(pb.q0, pb.l0, pb.x0, mode=mode, solver=0)
+    assert iters == ref["iterations"] and found == pb.n_landmarks
+    assert abs(err - ref["error"]) <= 1e-6 * ref["error"]
+    assert np.abs(np.array([kx, ky, kz]) - ref["x"].reshape(3, 4)[:, 3]).max() < 1e-5
