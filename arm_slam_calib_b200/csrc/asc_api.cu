@@ -8,6 +8,7 @@
 #include <nccl.h>   // types only; the library is dlopen()ed when a communicator is requested
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -75,6 +76,16 @@ int load_nccl() {
 
 int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ASC_DEBUG_SYNC=1: synchronise after the named launch and report the first failing kernel (compute-sanitizer stand-in)
+#define DBG_SYNC(h, name)                                                                                             \
+    do {                                                                                                              \
+        static const bool dbg__ = getenv("ASC_DEBUG_SYNC") != nullptr;                                                \
+        if (dbg__) {                                                                                                  \
+            cudaError_t e__ = cudaStreamSynchronize((h)->stream);                                                     \
+            if (e__ != cudaSuccess) return fail(ASC_ERR_CUDA, "kernel %s failed: %s", name, cudaGetErrorString(e__)); \
+        }                                                                                                             \
+    } while (0)
+
 }  // namespace
 
 struct asc_handle {
@@ -91,7 +102,6 @@ struct asc_handle {
     std::vector<uint8_t> continuous;
     Camera cm{};
     PriorConst pc{};
-    std::vector<int32_t> h_p_orig;
     // multi-GPU
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -100,6 +110,8 @@ struct asc_handle {
     int64_t fail_index = -1;
     // device memory
     std::vector<void*> allocs;
+    char* arena = nullptr;          // one grow-only device arena: re-packing a graph does not cudaFree/cudaMalloc
+    size_t arena_bytes = 0;
     int *pose_ptr = nullptr, *p_lm = nullptr, *p_pose = nullptr, *p_orig = nullptr;
     int *lm_ptr = nullptr, *l_pose = nullptr, *l_perm = nullptr;
     double2 *p_uv = nullptr, *l_uv = nullptr, *J = nullptr, *b_dbg = nullptr;
@@ -125,7 +137,7 @@ struct asc_handle {
     cudaEvent_t tm[2] = {nullptr, nullptr};
     int prof_id = 0, prof_n = 0;
     std::vector<cudaEvent_t> prof_ev;
-    double *q_save = nullptr, *lm4_save = nullptr, *X_save = nullptr;
+    double *q_save = nullptr, *lm4_save = nullptr, *X_save = nullptr, *stage3 = nullptr;
     // cluster-Jacobi preconditioner
     bool use_clusters = false;
     int nC = 0, nmax = 0;
@@ -167,6 +179,25 @@ int dev_alloc(asc_handle* h, T** out, size_t count) {
 void free_device(asc_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     h->allocs.clear();
+}
+
+struct ArenaReq { void** dst; size_t bytes; };
+
+// lays the requested buffers out in the handle's arena (256-byte aligned), growing it only when needed
+int commit_arena(asc_handle* h, const std::vector<ArenaReq>& reqs) {
+    size_t total = 0;
+    for (const ArenaReq& r : reqs) total += (r.bytes + 255) & ~(size_t)255;
+    if (total > h->arena_bytes) {
+        if (h->arena) CUDA_TRY(cudaFree(h->arena));
+        h->arena = nullptr; h->arena_bytes = 0;
+        const size_t want = total + total / 8 + (1 << 20);
+        CUDA_TRY(cudaMalloc((void**)&h->arena, want));
+        CUDA_TRY(cudaMemsetAsync(h->arena, 0, want, h->stream));
+        h->arena_bytes = want;
+    }
+    size_t off = 0;
+    for (const ArenaReq& r : reqs) { *r.dst = h->arena + off; off += (r.bytes + 255) & ~(size_t)255; }
+    return ASC_OK;
 }
 
 int allreduce(asc_handle* h, double* buf, size_t count) {
@@ -241,12 +272,14 @@ struct Engine {
                 h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
                 h->J, h->Bpp, h->BpK, h->gr, h->partA, nullptr, h->cheir);
         CUDA_TRY(cudaGetLastError());
+        DBG_SYNC(h, "fk + linearize_pose");
         prof_stop(h, 1);
         CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
         prof_start(h, 2);
         landmark_blocks_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->cm, h->L, h->lm_ptr, h->l_pose, h->l_uv, h->cam, h->lm4, h->lm_prior, h->C,
                                                                 h->gl, h->WK, h->errblk);
         CUDA_TRY(cudaGetLastError());
+        DBG_SYNC(h, "landmark_blocks");
         prof_stop(h, 2);
         h->launches += 8;
         const int nR1 = std::min(64, h->nCtaPose), rpb = cdiv(h->nCtaPose, nR1);
@@ -265,6 +298,7 @@ struct Engine {
         if (h->use_clusters && h->M) {
             obs_w_kernel<N><<<cdiv(h->M, 256), 256, 0, h->stream>>>(h->M, h->J, h->Wm);
             CUDA_TRY(cudaGetLastError());
+            DBG_SYNC(h, "linearize finish + obs_w");
         }
         CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
         h->linearized = true;
@@ -285,6 +319,7 @@ struct Engine {
         CUDA_TRY(cudaMemcpyAsync(h->flags, init_flags, sizeof init_flags, cudaMemcpyHostToDevice, h->stream));
         landmark_invert_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->L, lambda, h->C, h->gl, h->WK, h->Cinv, h->cg4, h->partL, h->flags + 1);
         CUDA_TRY(cudaGetLastError());
+        DBG_SYNC(h, "landmark_invert");
         if (h->use_clusters) {
             const size_t sm = sizeof(double) * kWarpsPerCta * ((size_t)N * h->nmax + 3 * N);
             cluster_schur_kernel<N><<<h->nCtaPose, kCtaThreads, sm, h->stream>>>(h->P, lambda, h->rank == 0 ? 1 : 0, h->nmax, h->pose_ptr, h->p_lm,
@@ -295,6 +330,7 @@ struct Engine {
                                                                                                   h->Dloc, h->rloc);
         }
         CUDA_TRY(cudaGetLastError());
+        DBG_SYNC(h, "cluster_schur / pose_schur_diag");
         const int nR1 = std::min(64, h->nBlkLm), rpb = cdiv(h->nBlkLm, nR1);
         reduce_rows_kernel<<<cdiv(h->nBlkLm, rpb), 256, 0, h->stream>>>(h->partL, h->nBlkLm, 27, kPartCols, rpb, h->partR);
         CUDA_TRY(cudaGetLastError());
@@ -310,9 +346,11 @@ struct Engine {
         }
         k_rows_kernel<<<1, 256, 0, h->stream>>>(lambda, kpart, nk, h->BKK, h->gr + (size_t)h->P * N, h->MinvK, h->rhs + (size_t)h->P * N, h->SKK, h->flags + 3);
         CUDA_TRY(cudaGetLastError());
+        DBG_SYNC(h, "k_rows");
         if (h->use_clusters) {
             const size_t sm = sizeof(double) * (size_t)h->nmax * (h->nmax | 1);
             cluster_invert_kernel<<<h->nC, 256, sm, h->stream>>>(N, h->cl_ptr, h->cl_off, h->Dloc, h->gr, h->rloc, h->Mc, h->rhs, h->flags + 2);
+            DBG_SYNC(h, "cluster_invert");
             // The coarse operator is only a preconditioner: any SPD E^-1 keeps PCG exact, so a factorisation from an
             // earlier lambda / linearisation is reused until it visibly costs iterations (deterministic policy).
             const bool refresh = h->use_coarse && (!h->coarse_valid || h->coarse_last_iters > h->coarse_ref_iters + h->coarse_ref_iters / 4 + 8);
@@ -323,13 +361,16 @@ struct Engine {
                 h->coarse_valid = true;
                 inc_v_kernel<N><<<cdiv(std::max(h->nInc, 1), 4), 128, 0, h->stream>>>(h->nInc, h->inc_lo, h->inc_hi, h->inc_lm, h->l_perm, h->Wm, h->Cinv,
                                                                                   h->Vinc, h->Tinc);
+                DBG_SYNC(h, "inc_v");
                 CUDA_TRY(cudaMemsetAsync(h->E, 0, sizeof(double) * (size_t)nz * nz, h->stream));
                 coarse_blocks_kernel<N><<<cdiv(std::max(h->nDest, 1), 4), 128, 0, h->stream>>>(h->nDest, h->dest_ptr, h->dest_ca, h->dest_cb, h->pair_a,
                                                                                            h->pair_b, h->Vinc, h->Tinc, h->E, nz);
+                DBG_SYNC(h, "coarse_blocks");
                 if (h->rank == 0) coarse_diag_kernel<<<cdiv((int64_t)h->nC * N * N, 256), 256, 0, h->stream>>>(h->nC, N, lambda, h->cl_ptr, h->Bpp, h->E, nz);
                 coarse_k_kernel<<<cdiv(std::max<int64_t>((int64_t)h->nC * N * 6, 36), 256), 256, 0, h->stream>>>(h->nC, N, h->rank == 0 ? 1 : 0, h->cl_ptr, h->cl_inc_ptr,
                                                                                                        h->cl_inc, h->inc_lm, h->Tinc, h->WK, h->BpK, h->SKK, h->E, nz);
                 CUDA_TRY(cudaGetLastError());
+                DBG_SYNC(h, "coarse_diag / coarse_k");
                 h->launches += 5;
                 if (h->world > 1) {   // S_KK is already global; undo its world-fold replication, then sum the shard contributions
                     int rc2 = allreduce(h, h->E, (size_t)nz * nz);
@@ -344,8 +385,13 @@ struct Engine {
                 if (h->prm.pcg_coarse_fp32 && h->Ef) {
                     const size_t nn = (size_t)nz * nz;
                     to_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->E, h->Ef, nn);
-                    if (cusolverDnSpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->Ef, nz, h->workf, h->lworkf, h->flags + 6) != CUSOLVER_STATUS_SUCCESS)
-                        return fail(ASC_ERR_CUDA, "cusolverDnSpotrf failed");
+                    CUDA_TRY(cudaGetLastError());
+                    if (getenv("ASC_DEBUG_SYNC")) { CUDA_TRY(cudaStreamSynchronize(h->stream)); fprintf(stderr, "[asc] pre-potrf ok: E %p Ef %p workf %p lworkf %d flags %p nz %d\n", (void*)h->E, (void*)h->Ef, (void*)h->workf, h->lworkf, (void*)h->flags, nz); }
+                    {
+                        const cusolverStatus_t st = cusolverDnSpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->Ef, nz, h->workf, h->lworkf, h->flags + 6);
+                        if (st != CUSOLVER_STATUS_SUCCESS)
+                            return fail(ASC_ERR_CUDA, "cusolverDnSpotrf failed: status %d, lwork %d, cuda: %s", (int)st, h->lworkf, cudaGetErrorString(cudaGetLastError()));
+                    }
                     if (timing) cudaEventRecord(e1, h->stream);
                     // E^-1 = solve(U^T U, I): two TRSMs run much closer to peak than cuSOLVER's potri
                     identity_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->Einvf, nz);
@@ -901,6 +947,9 @@ int asc_destroy(asc_handle* h) {
     if (h->solver) cusolverDnDestroy(h->solver);
     if (h->blas) cublasDestroy(h->blas);
     free_device(h);
+    if (h->arena) cudaFree(h->arena);
+    if (h->work) cudaFree(h->work);
+    if (h->workf) cudaFree(h->workf);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_ev) cudaEventDestroy(ev);
     if (h->h_status) cudaFreeHost(h->h_status);
@@ -940,9 +989,19 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     if ((M > 0 && (!pose_idx || !lm_idx || !uv)) || !enc || (L > 0 && !lm_prior) || !x_prior) return fail(ASC_ERR_INVALID, "null argument");
     for (int64_t m = 0; m < M; ++m)
         if (pose_idx[m] < 0 || pose_idx[m] >= P || lm_idx[m] < 0 || lm_idx[m] >= L) return fail(ASC_ERR_INVALID, "observation %lld has an out-of-range index", (long long)m);
+    static const bool timing = getenv("ASC_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[asc] set_problem %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     CUDA_TRY(cudaSetDevice(h->dev));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    lap("validate");
     free_device(h);
+    lap("free_device");
     const int N = h->N;
     h->P = P; h->L = L; h->M = M;
     h->values_set = false; h->linearized = false; h->lin_lambda = -1.0;
@@ -964,8 +1023,11 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     for (int64_t m = 0; m < M; ++m) { pose_ptr[pose_idx[m] + 1]++; lm_ptr[lm_idx[m] + 1]++; }
     for (int p = 0; p < P; ++p) pose_ptr[p + 1] += pose_ptr[p];
     for (int j = 0; j < L; ++j) lm_ptr[j + 1] += lm_ptr[j];
-    std::vector<int> p_lm(M), p_pose(M), p_orig(M), pos_of(M), l_pose(M), l_perm(M);
-    std::vector<double> p_uv(2 * M), l_uv(2 * M);
+    // staging buffers persist across calls (no page faults when a graph of similar size is re-packed)
+    static thread_local std::vector<int> p_lm, p_pose, p_orig, pos_of, l_pose, l_perm, run_lo, run_hi;
+    static thread_local std::vector<double> p_uv, l_uv;
+    p_lm.resize(M); p_pose.resize(M); p_orig.resize(M); pos_of.resize(M); l_pose.resize(M); l_perm.resize(M);
+    p_uv.resize(2 * M); l_uv.resize(2 * M);
     {
         std::vector<int> fill(pose_ptr.begin(), pose_ptr.end() - 1);
         for (int64_t m = 0; m < M; ++m) {
@@ -982,13 +1044,14 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             l_uv[2 * k] = uv[2 * m]; l_uv[2 * k + 1] = uv[2 * m + 1];
         }
     }
+    lap("two observation orders");
     // ---- preconditioner clusters: runs of consecutive keyframes that share landmarks
     const int gmax = std::max(1, std::min(pr.pcg_cluster_max, 128 / N));
     h->use_clusters = gmax > 1;
     struct PairRec { long long key; int a, b; };
     std::vector<PairRec> pairs;
     std::vector<int> inc_lo, inc_hi, inc_lm, inc_cl, dest_ptr, dest_ca, dest_cb, pair_a, pair_b, cl_inc_ptr, cl_inc;
-    std::vector<int> cl_ptr, pose_cluster(P, 0), run_lo, run_hi;
+    std::vector<int> cl_ptr, pose_cluster(P, 0);
     std::vector<long long> cl_off;
     if (h->use_clusters) {
         std::vector<double> cnt(2 * (size_t)P, 0.0);   // [shared with previous | own count], as doubles for the all-reduce
@@ -1012,6 +1075,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             CUDA_TRY(cudaStreamSynchronize(h->stream));
             cudaFree(d);
         }
+        lap("covisibility counts + cluster exchange");
         int size = 0;
         for (int p = 0; p < P; ++p) {
             const double mn = p > 0 ? std::min(cnt[P + p], cnt[P + p - 1]) : 0.0;
@@ -1030,7 +1094,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             h->nmax = std::max(h->nmax, (int)n);
         }
         h->scTotal = (size_t)cl_off[h->nC];
-        run_lo.assign(M, 0); run_hi.assign(M, 0);
+        run_lo.resize(M); run_hi.resize(M);
         h->nz = h->nC * N + 6;
         h->use_coarse = pr.pcg_coarse_max_dim > 0 && h->nz <= pr.pcg_coarse_max_dim && h->nC > 1;
         for (int j = 0; j < L; ++j) {
@@ -1049,8 +1113,21 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                     for (size_t ib = first_inc; ib < inc_lo.size(); ++ib)
                         if (inc_cl[ia] >= inc_cl[ib]) pairs.push_back({(long long)inc_cl[ia] * h->nC + inc_cl[ib], (int)ia, (int)ib});
         }
+        lap("runs + incidences + pairs");
         if (h->use_coarse) {
-            std::stable_sort(pairs.begin(), pairs.end(), [](const PairRec& x, const PairRec& y) { return x.key < y.key; });
+            {   // stable LSD radix sort of the pairs by (cluster a, cluster b): two counting passes instead of a comparison sort
+                const int nCl = h->nC;
+                std::vector<PairRec> tmp(pairs.size());
+                std::vector<int> cntv(nCl + 1);
+                for (int pass = 0; pass < 2; ++pass) {
+                    std::fill(cntv.begin(), cntv.end(), 0);
+                    auto digit = [&](const PairRec& r) { return pass == 0 ? (int)(r.key % nCl) : (int)(r.key / nCl); };
+                    for (const PairRec& r : pairs) cntv[digit(r) + 1]++;
+                    for (int c = 0; c < nCl; ++c) cntv[c + 1] += cntv[c];
+                    for (const PairRec& r : pairs) tmp[cntv[digit(r)]++] = r;
+                    pairs.swap(tmp);
+                }
+            }
             for (size_t i = 0; i < pairs.size(); ++i) {
                 if (i == 0 || pairs[i].key != pairs[i - 1].key) {
                     dest_ptr.push_back((int)i);
@@ -1068,13 +1145,14 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             for (size_t i = 0; i < inc_cl.size(); ++i) cl_inc[f[inc_cl[i]]++] = (int)i;
         }
     } else { h->nC = 0; h->nmax = 0; h->scTotal = 0; h->use_coarse = false; }
-    h->h_p_orig = p_orig;
+    lap("pair sort + coarse CSR");
 
     const size_t PN = (size_t)P * N, Mz = (size_t)M;
     h->nCtaPose = cdiv(P, kWarpsPerCta);
     h->nBlkLm = std::max(1, cdiv(L, 128));
-    int rc;
-#define ALLOC(ptr, count) do { if ((rc = dev_alloc(h, &h->ptr, (count)))) return rc; } while (0)
+    int rc = ASC_OK;
+    std::vector<ArenaReq> reqs;
+#define ALLOC(ptr, count) reqs.push_back(ArenaReq{(void**)&h->ptr, sizeof(*h->ptr) * std::max<size_t>((size_t)(count), 1)})
     ALLOC(pose_ptr, P + 1); ALLOC(p_lm, Mz); ALLOC(p_pose, Mz); ALLOC(p_orig, Mz); ALLOC(p_uv, Mz);
     ALLOC(lm_ptr, L + 1); ALLOC(l_pose, Mz); ALLOC(l_perm, Mz); ALLOC(l_uv, Mz);
     ALLOC(enc, PN); ALLOC(lm_prior, (size_t)L * 3);
@@ -1084,12 +1162,10 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     ALLOC(cam, (size_t)P * 12); ALLOC(chain, PN * 6);
     ALLOC(J, (size_t)(N + 3) * Mz); ALLOC(b_dbg, 1);
     ALLOC(poseblk, PN * N + PN * 6 + 36 + PN + 6 + 8);
-    h->Bpp = h->poseblk; h->BpK = h->Bpp + PN * N; h->BKK = h->BpK + PN * 6; h->gr = h->BKK + 36; h->err_lin = h->gr + PN + 6;
     ALLOC(C, (size_t)L * 6); ALLOC(gl, (size_t)L * 3); ALLOC(WK, (size_t)L * 18); ALLOC(Cinv, (size_t)L * 6);
     ALLOC(cg4, (size_t)L * 4); ALLOC(u4, (size_t)L * 4); ALLOC(dl4, (size_t)L * 4); ALLOC(gl4, (size_t)L * 4); ALLOC(v4, Mz * 4);
     h->regionA = std::max(PN * N, h->scTotal);
     ALLOC(precblk, h->regionA + PN + kPartCols);
-    h->Dloc = h->precblk; h->rloc = h->Dloc + h->regionA; h->krow = h->rloc + PN;
     if (h->use_clusters) {
         ALLOC(cl_ptr, h->nC + 1); ALLOC(cl_off, h->nC + 1); ALLOC(pose_cluster, P); ALLOC(p_run_lo, Mz); ALLOC(p_run_hi, Mz);
         ALLOC(Wm, Mz * 3 * N); ALLOC(Mc, h->scTotal);
@@ -1099,26 +1175,12 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         ALLOC(inc_lo, ni); ALLOC(inc_hi, ni); ALLOC(inc_lm, ni); ALLOC(dest_ptr, nd + 1); ALLOC(dest_ca, nd); ALLOC(dest_cb, nd);
         ALLOC(pair_a, np); ALLOC(pair_b, np); ALLOC(cl_inc_ptr, h->nC + 1); ALLOC(cl_inc, ni);
         ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, nz); ALLOC(zc, nz);
+        if (pr.pcg_coarse_fp32) { ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * nz); } else { h->Ef = nullptr; h->Einvf = nullptr; }
         if (!h->solver) {
             if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cusolverDnCreate failed");
             if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cublasCreate failed");
             cusolverDnSetStream(h->solver, h->stream);
             cublasSetStream(h->blas, h->stream);
-        }
-        int lw1 = 0, lw2 = 0;
-        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw1) != CUSOLVER_STATUS_SUCCESS ||
-            cusolverDnDpotri_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw2) != CUSOLVER_STATUS_SUCCESS)
-            return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
-        h->lwork = std::max(lw1, lw2);
-        ALLOC(work, (size_t)h->lwork);
-        if (pr.pcg_coarse_fp32) {
-            ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * nz);
-            int lf1 = 0, lf2 = 0;
-            if (cusolverDnSpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->Ef, h->nz, &lf1) != CUSOLVER_STATUS_SUCCESS ||
-                cusolverDnSpotri_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->Ef, h->nz, &lf2) != CUSOLVER_STATUS_SUCCESS)
-                return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
-            h->lworkf = std::max(lf1, lf2);
-            ALLOC(workf, (size_t)h->lworkf);
         }
     }
     ALLOC(Minv, PN * N); ALLOC(MinvK, 36); ALLOC(rhs, PN + 8);
@@ -1129,8 +1191,36 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
     h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
     ALLOC(errblk, h->nErrBlk);
-    ALLOC(scal, 8); ALLOC(status, 64); ALLOC(flags, 8); ALLOC(cheir, 1); ALLOC(SKK, 36);
+    ALLOC(scal, 8); ALLOC(status, 64); ALLOC(flags, 8); ALLOC(cheir, 1); ALLOC(SKK, 36); ALLOC(stage3, (size_t)L * 3);
 #undef ALLOC
+    rc = commit_arena(h, reqs);
+    if (rc) return rc;
+    h->Bpp = h->poseblk; h->BpK = h->Bpp + PN * N; h->BKK = h->BpK + PN * 6; h->gr = h->BKK + 36; h->err_lin = h->gr + PN + 6;
+    h->Dloc = h->precblk; h->rloc = h->Dloc + h->regionA; h->krow = h->rloc + PN;
+    if (h->use_coarse) {   // cuSOLVER workspaces: separate grow-only allocations
+        int lw1 = 0, lw2 = 0, lf1 = 0;
+        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw1) != CUSOLVER_STATUS_SUCCESS ||
+            cusolverDnDpotri_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw2) != CUSOLVER_STATUS_SUCCESS)
+            return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
+        if (std::max(lw1, lw2) > h->lwork) {
+            if (h->work) cudaFree(h->work);
+            h->lwork = std::max(lw1, lw2);
+            CUDA_TRY(cudaMalloc((void**)&h->work, sizeof(double) * (size_t)h->lwork));
+        }
+        if (pr.pcg_coarse_fp32) {
+            int lf2 = 0;
+            if (cusolverDnSpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->Ef, h->nz, &lf1) != CUSOLVER_STATUS_SUCCESS ||
+                cusolverDnSpotri_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->Ef, h->nz, &lf2) != CUSOLVER_STATUS_SUCCESS)
+                return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
+            lf1 = std::max(std::max(lf1, lf2), 1 << 16);
+            if (lf1 > h->lworkf) {
+                if (h->workf) cudaFree(h->workf);
+                h->lworkf = lf1;
+                CUDA_TRY(cudaMalloc((void**)&h->workf, sizeof(float) * (size_t)h->lworkf));
+            }
+        }
+    }
+    lap("cudaMalloc + memset");
 #define UP(dst, src, bytes) CUDA_TRY(cudaMemcpyAsync(h->dst, src, (bytes), cudaMemcpyHostToDevice, h->stream))
     UP(pose_ptr, pose_ptr.data(), sizeof(int) * (P + 1)); UP(lm_ptr, lm_ptr.data(), sizeof(int) * (L + 1));
     if (M) {
@@ -1154,6 +1244,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     if (has_enc) UP(has_enc, has_enc, P);
 #undef UP
     CUDA_TRY(cudaStreamSynchronize(h->stream));   // host staging vectors go out of scope
+    lap("uploads");
     h->problem_set = true;
     return ASC_OK;
 }
@@ -1163,7 +1254,11 @@ int asc_set_values(asc_handle* h, const double* q, const double* l, const double
     if (!q || (h->L > 0 && !l) || !x) return fail(ASC_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->dev));
     CUDA_TRY(cudaMemcpyAsync(h->q, q, sizeof(double) * h->P * h->N, cudaMemcpyHostToDevice, h->stream));
-    if (h->L) CUDA_TRY(cudaMemcpy2DAsync(h->lm4, 4 * sizeof(double), l, 3 * sizeof(double), 3 * sizeof(double), h->L, cudaMemcpyHostToDevice, h->stream));
+    if (h->L) {   // one contiguous copy + a pad kernel (a pitched 24->32 B copy from pageable memory takes ~13 ms for 90k rows)
+        CUDA_TRY(cudaMemcpyAsync(h->stage3, l, sizeof(double) * 3 * h->L, cudaMemcpyHostToDevice, h->stream));
+        pad3to4_kernel<<<cdiv((int64_t)h->L * 4, 256), 256, 0, h->stream>>>(h->L, h->stage3, h->lm4);
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaMemcpyAsync(h->X, x, sizeof(double) * 12, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->values_set = true;
@@ -1175,7 +1270,11 @@ int asc_get_values(asc_handle* h, double* q, double* l, double* x) {
     int rc = check_ready(h, true);
     if (rc) return rc;
     if (q) CUDA_TRY(cudaMemcpyAsync(q, h->q, sizeof(double) * h->P * h->N, cudaMemcpyDeviceToHost, h->stream));
-    if (l && h->L) CUDA_TRY(cudaMemcpy2DAsync(l, 3 * sizeof(double), h->lm4, 4 * sizeof(double), 3 * sizeof(double), h->L, cudaMemcpyDeviceToHost, h->stream));
+    if (l && h->L) {
+        unpad4to3_kernel<<<cdiv((int64_t)h->L * 3, 256), 256, 0, h->stream>>>(h->L, h->lm4, h->stage3);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(l, h->stage3, sizeof(double) * 3 * h->L, cudaMemcpyDeviceToHost, h->stream));
+    }
     if (x) CUDA_TRY(cudaMemcpyAsync(x, h->X, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return ASC_OK;
@@ -1310,7 +1409,11 @@ int asc_solve_damped(asc_handle* h, double lambda, double* dq, double* dl, doubl
     const size_t PN = (size_t)h->P * h->N;
     if (dq) CUDA_TRY(cudaMemcpyAsync(dq, h->vx, PN * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (dx) CUDA_TRY(cudaMemcpyAsync(dx, h->vx + PN, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (dl && h->L) CUDA_TRY(cudaMemcpy2DAsync(dl, 3 * sizeof(double), h->dl4, 4 * sizeof(double), 3 * sizeof(double), h->L, cudaMemcpyDeviceToHost, h->stream));
+    if (dl && h->L) {
+        unpad4to3_kernel<<<cdiv((int64_t)h->L * 3, 256), 256, 0, h->stream>>>(h->L, h->dl4, h->stage3);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(dl, h->stage3, sizeof(double) * 3 * h->L, cudaMemcpyDeviceToHost, h->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return ASC_OK;
 }

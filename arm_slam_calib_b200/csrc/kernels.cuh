@@ -1661,6 +1661,11 @@ __global__ void pad3to4_kernel(int L, const double* __restrict__ in3, double* __
     if (i < (int64_t)L * 4) { const int c = (int)(i & 3); out4[i] = c == 3 ? 0.0 : in3[3 * (i >> 2) + c]; }
 }
 
+__global__ void unpad4to3_kernel(int L, const double* __restrict__ in4, double* __restrict__ out3) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)L * 3) out3[i] = in4[4 * (i / 3) + i % 3];
+}
+
 // gather pose-major per-observation data back to the caller's observation order (parity accessor)
 template <int N>
 __global__ void unpack_blocks_kernel(int64_t M, const int* __restrict__ p_orig, const double2* __restrict__ J, const double2* __restrict__ b,

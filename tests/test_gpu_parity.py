@@ -127,3 +127,20 @@ def test_run_to_run_determinism(asc, c1_offset_problem):
         opt.close()
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
     assert res[0][3] == res[1][3]
+
+
+def test_repacking_on_a_reused_handle_is_bitwise_identical(asc, c1_offset_problem, small_problem):
+    """asc_set_problem reuses the device arena without clearing it: results must not depend on what was there before."""
+    prm = asc.default_params()
+    fresh = asc.BatchOptimizer(c1_offset_problem, prm)
+    q0, l0, x0 = fresh.optimize(0)
+    e0 = fresh.error()
+    fresh.close()
+    opt = asc.BatchOptimizer(small_problem, prm)      # different sizes first
+    opt.optimize(1)
+    for _ in range(2):
+        opt.set_problem(c1_offset_problem)
+        opt.set_values(c1_offset_problem.q0, c1_offset_problem.l0, c1_offset_problem.x0)
+        q, l, x = opt.optimize(0)
+        assert np.array_equal(q, q0) and np.array_equal(l, l0) and np.array_equal(x, x0) and opt.error() == e0
+    opt.close()
