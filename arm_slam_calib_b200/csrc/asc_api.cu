@@ -113,7 +113,7 @@ struct asc_handle {
     char* arena = nullptr;          // one grow-only device arena: re-packing a graph does not cudaFree/cudaMalloc
     size_t arena_bytes = 0;
     int *pose_ptr = nullptr, *p_lm = nullptr, *p_pose = nullptr, *p_orig = nullptr;
-    int *lm_ptr = nullptr, *l_pose = nullptr, *l_perm = nullptr;
+    int *lm_ptr = nullptr, *l_pose = nullptr, *l_perm = nullptr, *p_inv = nullptr;
     double2 *p_uv = nullptr, *l_uv = nullptr, *J = nullptr, *b_dbg = nullptr;
     double *enc = nullptr, *lm_prior = nullptr;
     uint8_t* has_enc = nullptr;
@@ -432,14 +432,14 @@ struct Engine {
         prof_start(h, 3);
         if (update_p)
             schur_pass_a_kernel<N, true><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4,
-                                                                                   h->use_coarse ? h->zc : nullptr, h->pose_cluster);
+                                                                                   h->use_coarse ? h->zc : nullptr, h->pose_cluster, h->p_inv);
         else
             schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4, nullptr,
-                                                                                    nullptr);
+                                                                                    nullptr, h->p_inv);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 3);
         prof_start(h, 4);
-        schur_pass_b_kernel<false><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->l_perm, h->v4, h->WK, h->Cinv, x + (size_t)h->P * N, done,
+        schur_pass_b_kernel<false><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, x + (size_t)h->P * N, done,
                                                                     nullptr, h->u4, h->partB);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 4);
@@ -535,9 +535,9 @@ struct Engine {
     static int backsub(asc_handle* h) {
         h->launches += 2;
         schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, h->vx, nullptr, nullptr, nullptr, h->v4, nullptr,
-                                                                                nullptr);
+                                                                                nullptr, h->p_inv);
         CUDA_TRY(cudaGetLastError());
-        schur_pass_b_kernel<true><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->l_perm, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
+        schur_pass_b_kernel<true><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
                                                                    h->cg4, h->dl4, nullptr);
         CUDA_TRY(cudaGetLastError());
         return ASC_OK;
@@ -1040,7 +1040,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         for (int64_t kp = 0; kp < M; ++kp) {
             const int m = p_orig[kp];
             const int k = fl[lm_idx[m]]++;
-            l_pose[k] = pose_idx[m]; l_perm[k] = (int)kp;
+            l_pose[k] = pose_idx[m]; l_perm[k] = (int)kp; pos_of[kp] = k;   // pos_of now: pose-major -> landmark-major
             l_uv[2 * k] = uv[2 * m]; l_uv[2 * k + 1] = uv[2 * m + 1];
         }
     }
@@ -1154,7 +1154,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     std::vector<ArenaReq> reqs;
 #define ALLOC(ptr, count) reqs.push_back(ArenaReq{(void**)&h->ptr, sizeof(*h->ptr) * std::max<size_t>((size_t)(count), 1)})
     ALLOC(pose_ptr, P + 1); ALLOC(p_lm, Mz); ALLOC(p_pose, Mz); ALLOC(p_orig, Mz); ALLOC(p_uv, Mz);
-    ALLOC(lm_ptr, L + 1); ALLOC(l_pose, Mz); ALLOC(l_perm, Mz); ALLOC(l_uv, Mz);
+    ALLOC(lm_ptr, L + 1); ALLOC(l_pose, Mz); ALLOC(l_perm, Mz); ALLOC(l_uv, Mz); ALLOC(p_inv, Mz);
     ALLOC(enc, PN); ALLOC(lm_prior, (size_t)L * 3);
     if (has_enc) { ALLOC(has_enc, P); } else { h->has_enc = nullptr; }
     ALLOC(q, PN); ALLOC(q_try, PN); ALLOC(lm4, (size_t)L * 4); ALLOC(lm4_try, (size_t)L * 4); ALLOC(X, 12); ALLOC(X_try, 12);
@@ -1226,7 +1226,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     if (M) {
         UP(p_lm, p_lm.data(), sizeof(int) * Mz); UP(p_pose, p_pose.data(), sizeof(int) * Mz); UP(p_orig, p_orig.data(), sizeof(int) * Mz);
         UP(p_uv, p_uv.data(), sizeof(double) * 2 * Mz); UP(l_pose, l_pose.data(), sizeof(int) * Mz); UP(l_perm, l_perm.data(), sizeof(int) * Mz);
-        UP(l_uv, l_uv.data(), sizeof(double) * 2 * Mz);
+        UP(l_uv, l_uv.data(), sizeof(double) * 2 * Mz); UP(p_inv, pos_of.data(), sizeof(int) * Mz);
     }
     if (h->use_clusters) {
         UP(cl_ptr, cl_ptr.data(), sizeof(int) * (h->nC + 1)); UP(cl_off, cl_off.data(), sizeof(long long) * (h->nC + 1));

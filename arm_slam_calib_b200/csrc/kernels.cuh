@@ -566,7 +566,7 @@ template <int N>
 __device__ __forceinline__ void load_planes(const double2* __restrict__ J, int64_t M, int k, double (&f)[2 * N + 6]) {
 #pragma unroll
     for (int i = 0; i < N + 3; ++i) {
-        const double2 t = ldg2(J + (size_t)i * M + k);
+        const double2 t = __ldcs(J + (size_t)i * M + k);   // read once per pass: stream through, keep L2 for the gathered tables
         f[2 * i] = t.x; f[2 * i + 1] = t.y;
     }
 }
@@ -1030,7 +1030,7 @@ template <int N, bool UPDATE_P>
 __global__ void __launch_bounds__(kCtaThreads)
 schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const double2* __restrict__ J, double* __restrict__ x,
                     const double* __restrict__ z, const double* __restrict__ scal, const int* __restrict__ done, double* __restrict__ v4,
-                    const double* __restrict__ zc, const int* __restrict__ pose_cluster) {
+                    const double* __restrict__ zc, const int* __restrict__ pose_cluster, const int* __restrict__ p_inv) {
     if (done && *done) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * kWarpsPerCta + warp;
@@ -1056,7 +1056,8 @@ schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const do
 #pragma unroll
         for (int i = 0; i < N; ++i) { s0 = fma(f[i], xp[i], s0); s1 = fma(f[N + i], xp[i], s1); }
         const double* jl = f + 2 * N;
-        double2* o = reinterpret_cast<double2*>(v4 + 4 * (size_t)k);
+        // v goes straight to its landmark-major slot (one full 32-byte sector), so pass B reads its segment contiguously
+        double2* o = reinterpret_cast<double2*>(v4 + 4 * (size_t)__ldg(p_inv + k));
         o[0] = make_double2(jl[0] * s0 + jl[3] * s1, jl[1] * s0 + jl[4] * s1);
         o[1] = make_double2(jl[2] * s0 + jl[5] * s1, 0.0);
     }
@@ -1066,7 +1067,7 @@ schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const do
 // block partials of sum_j W_Kj u_j.   One thread per landmark.
 template <bool BACKSUB>
 __global__ void __launch_bounds__(128)
-schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const int* __restrict__ l_perm, const double* __restrict__ v4,
+schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const double* __restrict__ v4,
                     const double* __restrict__ WK, const double* __restrict__ Cinv, const double* __restrict__ xK,
                     const int* __restrict__ done, const double* __restrict__ cg4, double* __restrict__ u4, double* __restrict__ blk_part) {
     if (done && *done) return;
@@ -1076,9 +1077,8 @@ schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const int* __restrict
         double tx = 0, ty = 0, tz = 0;
         const int k0 = lm_ptr[j], k1 = lm_ptr[j + 1];
         for (int k = k0; k < k1; ++k) {
-            const int pk = __ldg(l_perm + k);
-            const double2 a = ldg2(reinterpret_cast<const double2*>(v4 + 4 * (size_t)pk));
-            const double c = __ldg(v4 + 4 * (size_t)pk + 2);
+            const double2 a = ldg2(reinterpret_cast<const double2*>(v4 + 4 * (size_t)k));
+            const double c = __ldg(v4 + 4 * (size_t)k + 2);
             tx += a.x; ty += a.y; tz += c;
         }
         double W[18], xk[6];
