@@ -287,6 +287,88 @@ __device__ __forceinline__ void gram_finish(double (&acc)[GramCfg<D>::H]) {
     }
 }
 
+// Register-blocked variant used by the linearise kernel: the D x D Gram matrix is cut into 4x4 blocks, one lane per
+// lower-triangular block pair; per observation row a lane loads 2 x 4 values (LDS.128, broadcast across lanes that share
+// a block) and issues 16 FMAs.  The per-pair variant above is shared-memory-bandwidth bound (1 LDS per FMA); this one is
+// balanced between the LDS and the fp64 pipe.  Rows are padded to Dp = 4*ceil(D/4) with zeros.
+template <int D>
+struct GramBlk {
+    static constexpr int Dp = (D + 3) / 4 * 4;
+    static constexpr int NB = Dp / 4;
+    static constexpr int NPAIR = NB * (NB + 1) / 2;
+    static constexpr int G = NPAIR <= 16 ? 2 : 1;    // two half-warps split the two residual rows when they fit
+    static constexpr int GS = 32 / G;
+    static constexpr int LD = Dp + 2;                // LD/2 odd: 16-byte chunks of consecutive lanes fall in distinct bank groups
+    static_assert(NPAIR <= 32, "DOF too large for one warp of block pairs");
+};
+
+template <int D>
+__device__ __forceinline__ void gram4_pair(int lane, int& bi, int& bj, bool& active) {
+    const int q = lane % GramBlk<D>::GS;
+    active = q < GramBlk<D>::NPAIR;
+    bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
+    bj = q - bi * (bi + 1) / 2;
+    if (!active) { bi = 0; bj = 0; }
+}
+
+template <int D>
+__device__ __forceinline__ void gram4_tile(const double* __restrict__ A, int count, int lane, int bi, int bj, bool active, double (&acc)[16]) {
+    typedef GramBlk<D> Cf;
+    if (!active) return;
+    const int g = lane / Cf::GS;
+    for (int o = 0; o < count; ++o) {
+#pragma unroll
+        for (int rr = 0; rr < 2 / Cf::G; ++rr) {
+            const int r = Cf::G == 2 ? g : rr;
+            const double* row = A + (r * 32 + o) * Cf::LD;
+            const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * bi), a23 = *reinterpret_cast<const double2*>(row + 4 * bi + 2);
+            const double2 b01 = *reinterpret_cast<const double2*>(row + 4 * bj), b23 = *reinterpret_cast<const double2*>(row + 4 * bj + 2);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[4 * x + y] = fma(a[x], b[y], acc[4 * x + y]);
+        }
+    }
+}
+
+// ---- Gram accumulation without shared memory: every lane forms the D(D+1)/2 products of ITS OWN factor rows in
+// registers, and 32 products at a time are summed across the warp by a butterfly "transpose-reduce" (31 shuffles for
+// 32 sums, fixed tree): afterwards lane l holds the warp total of product number l.  Measured background: the
+// shared-memory tile variants of this step were LDS-wavefront bound (20 wavefronts per factor, ncu l1tex 83 %).
+template <int D>
+__host__ __device__ constexpr int tri_row(int e) { int a = 0, rem = e; while (rem >= D - a) { rem -= D - a; ++a; } return a; }
+template <int D>
+__host__ __device__ constexpr int tri_col(int e) { int a = 0, rem = e; while (rem >= D - a) { rem -= D - a; ++a; } return a + rem; }
+
+template <int D>
+struct TriTable {   // compile-time (row, col) of the e-th upper-triangular entry, row-major
+    int row[D * (D + 1) / 2 + 32], col[D * (D + 1) / 2 + 32];
+    __host__ __device__ constexpr TriTable() : row(), col() {
+        int e = 0;
+        for (int a = 0; a < D; ++a)
+            for (int b = a; b < D; ++b) { row[e] = a; col[e] = b; ++e; }
+        for (; e < D * (D + 1) / 2 + 32; ++e) { row[e] = 0; col[e] = 0; }
+    }
+};
+
+template <int W>
+__device__ __forceinline__ void butterfly_step(double (&v)[32], int lane) {
+    const bool upper = (lane & W) != 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double lo = v[i], hi = v[i + W];
+        const double send = upper ? lo : hi, keep = upper ? hi : lo;
+        v[i] = keep + __shfl_xor_sync(kFull, send, W);
+    }
+}
+// v[i] on every lane -> return sum over lanes of v[lane]
+__device__ __forceinline__ double transpose_reduce32(double (&v)[32], int lane) {
+    butterfly_step<16>(v, lane); butterfly_step<8>(v, lane); butterfly_step<4>(v, lane); butterfly_step<2>(v, lane); butterfly_step<1>(v, lane);
+    return v[0];
+}
+
 // ------------------------------------------------------------------ K1 (+K2b): linearise, pose-major
 // One warp per keyframe.  The keyframe's FK row (camera pose + joint axes/origins) is staged in shared
 // memory once; each lane then evaluates one projection factor per tile: residual, J_q, J_l, J_K,
@@ -296,13 +378,14 @@ __device__ __forceinline__ void gram_finish(double (&acc)[GramCfg<D>::H]) {
 template <int N>
 struct LinSmem {
     static constexpr int D = N + 7;
-    static constexpr int LD = GramCfg<D>::LD;
-    static constexpr int kPerWarpDoubles = 12 + 6 * N + 2 * 32 * LD + kPartCols;
+    static constexpr int NE = D * (D + 1) / 2;          // unique entries of the Gram matrix of [J_q | J_K | b]
+    static constexpr int NBATCH = (NE + 31) / 32;
+    static constexpr int kPerWarpDoubles = 12 + 6 * N + kPartCols;
     static constexpr size_t kBytes = sizeof(double) * kPerWarpDoubles * kWarpsPerCta;
 };
 
 template <int N, bool STORE_B>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kCtaThreads, 3)
 linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
                       const double2* __restrict__ p_uv, const double* __restrict__ cam, const double* __restrict__ chain,
                       const double* __restrict__ lm4, const double* __restrict__ q, const double* __restrict__ enc,
@@ -310,79 +393,93 @@ linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __r
                       double* __restrict__ BpK, double* __restrict__ gp, double* __restrict__ cta_part, double2* __restrict__ b_out,
                       unsigned long long* __restrict__ cheir_count) {
     constexpr int D = N + 7;
-    typedef GramCfg<D> Cf;
+    constexpr int NE = LinSmem<N>::NE, NBATCH = LinSmem<N>::NBATCH;
+    constexpr TriTable<D> tri = TriTable<D>();
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* sw_ = smem + (size_t)warp * LinSmem<N>::kPerWarpDoubles;
     double* s_cam = sw_;                 // 12
     double* s_chain = sw_ + 12;          // 6N
-    double* s_A = s_chain + 6 * N;       // [2][32][LD]
-    double* s_part = s_A + 2 * 32 * Cf::LD;   // kPartCols
+    double* s_part = s_chain + 6 * N;    // kPartCols
     const int p = blockIdx.x * kWarpsPerCta + warp;
     if (lane < kPartCols) s_part[lane] = 0.0;
     if (p < P) {
         for (int i = lane; i < 12; i += 32) s_cam[i] = cam[(size_t)p * 12 + i];
         for (int i = lane; i < 6 * N; i += 32) s_chain[i] = chain[(size_t)p * 6 * N + i];
         __syncwarp();
-        double acc[Cf::H];
+        double acc[NBATCH];   // lane l: warp totals of Gram entries l, l+32, ...
 #pragma unroll
-        for (int t = 0; t < Cf::H; ++t) acc[t] = 0.0;
+        for (int t = 0; t < NBATCH; ++t) acc[t] = 0.0;
         unsigned ncheir = 0;
         const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+        // software pipeline: the landmark gather of tile t+1 (index -> position, two dependent loads) is issued before
+        // the arithmetic of tile t; with ~6 tiles per keyframe and few resident warps the kernel was latency-bound
+        const int klast = max(k1 - 1, k0);
+        int j_nxt = (k1 > k0) ? __ldg(p_lm + min(k0 + lane, klast)) : 0;
+        double2 z_nxt = (k1 > k0) ? ldg2(p_uv + min(k0 + lane, klast)) : make_double2(0.0, 0.0);
+        double2 l01_nxt = (k1 > k0) ? ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j_nxt)) : make_double2(0.0, 0.0);
+        double lz_nxt = (k1 > k0) ? __ldg(lm4 + 4 * (size_t)j_nxt + 2) : 0.0;
+        int j_nxt2 = (k1 > k0) ? __ldg(p_lm + min(k0 + 32 + lane, klast)) : 0;
         for (int base = k0; base < k1; base += 32) {
             const int k = base + lane;
-            const int count = min(32, k1 - base);
+            const double2 z = z_nxt, l01 = l01_nxt;
+            const double lz = lz_nxt;
+            {   // prefetch tile t+1 (clamped indices keep the loads in range; values of inactive lanes are not used)
+                z_nxt = ldg2(p_uv + min(k + 32, klast));
+                l01_nxt = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j_nxt2));
+                lz_nxt = __ldg(lm4 + 4 * (size_t)j_nxt2 + 2);
+                j_nxt2 = __ldg(p_lm + min(k + 64, klast));
+            }
+            double r0[D], r1[D];   // the two whitened rows [J_q (N) | J_K (6) | b] of this lane's factor (zero if none)
+#pragma unroll
+            for (int i = 0; i < D; ++i) { r0[i] = 0.0; r1[i] = 0.0; }
             if (k < k1) {
-                const double2 z = ldg2(p_uv + k);
-                const int j = __ldg(p_lm + k);
-                const double2 l01 = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j));
-                const double lz = __ldg(lm4 + 4 * (size_t)j + 2);
                 ProjOut o;
                 project_factor<true, true>(cm, s_cam, s_cam + 9, l01.x, l01.y, lz, z.x, z.y, o);
                 ncheir += o.cheir ? 1u : 0u;
-                double jq[2 * N];
 #pragma unroll
                 for (int i = 0; i < N; ++i) {   // column i of getLinearJacobian: a_i x (l - o_i)   (:240)
                     const double* a = s_chain + 6 * i;
                     const double rx = l01.x - a[3], ry = l01.y - a[4], rz = lz - a[5];
                     const double cx = a[1] * rz - a[2] * ry, cy = a[2] * rx - a[0] * rz, cz = a[0] * ry - a[1] * rx;
-                    jq[i] = -(o.jl[0] * cx + o.jl[1] * cy + o.jl[2] * cz);       // J1 = -(Dpoint * Jrobot)   (:245)
-                    jq[N + i] = -(o.jl[3] * cx + o.jl[4] * cy + o.jl[5] * cz);
+                    r0[i] = -(o.jl[0] * cx + o.jl[1] * cy + o.jl[2] * cz);       // J1 = -(Dpoint * Jrobot)   (:245)
+                    r1[i] = -(o.jl[3] * cx + o.jl[4] * cy + o.jl[5] * cz);
                 }
                 // packed planes [jq row0 | jq row1 | jl row0 | jl row1]
                 double flat[2 * N + 6];
 #pragma unroll
-                for (int i = 0; i < 2 * N; ++i) flat[i] = jq[i];
+                for (int i = 0; i < N; ++i) { flat[i] = r0[i]; flat[N + i] = r1[i]; }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) flat[2 * N + i] = o.jl[i];
 #pragma unroll
-                for (int i = 0; i < N + 3; ++i) J[(size_t)i * M + k] = make_double2(flat[2 * i], flat[2 * i + 1]);
+                for (int i = 0; i < N + 3; ++i) __stcs(J + (size_t)i * M + k, make_double2(flat[2 * i], flat[2 * i + 1]));
                 if (STORE_B) b_out[k] = make_double2(o.b0, o.b1);
-                double* a0 = s_A + (0 * 32 + lane) * Cf::LD;
-                double* a1 = s_A + (1 * 32 + lane) * Cf::LD;
 #pragma unroll
-                for (int i = 0; i < N; ++i) { a0[i] = jq[i]; a1[i] = jq[N + i]; }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) { a0[N + i] = o.jk[i]; a1[N + i] = o.jk[6 + i]; }
-                a0[N + 6] = o.b0; a1[N + 6] = o.b1;
+                for (int i = 0; i < 6; ++i) { r0[N + i] = o.jk[i]; r1[N + i] = o.jk[6 + i]; }
+                r0[N + 6] = o.b0; r1[N + 6] = o.b1;
             }
-            __syncwarp();
-            gram_tile<D, true>(s_A, s_A, count, lane, acc);
-            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < NBATCH; ++t) {
+                double v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int e = 32 * t + i;   // compile-time after unrolling: the table lookups fold to register names
+                    v[i] = e < NE ? fma(r0[tri.row[e]], r0[tri.col[e]], r1[tri.row[e]] * r1[tri.col[e]]) : 0.0;
+                }
+                acc[t] += transpose_reduce32(v, lane);
+            }
         }
-        gram_finish<D>(acc);
-        // scatter the D(D+1)/2 entries to their blocks (lanes of group 0)
-        if (lane < D) {
-            const int c = lane;
+        // scatter: lane l owns entries l + 32 t
+        {
             double* B = Bpp + (size_t)p * N * N;
             double* BK = BpK + (size_t)p * N * 6;
             double* g = gp + (size_t)p * N;
             const bool with_enc = add_priors && (has_enc == nullptr || has_enc[p]);
 #pragma unroll
-            for (int t = 0; t < Cf::H; ++t) {
-                int c2 = c + t;
-                if (c2 >= D) c2 -= D;
-                const int lo = min(c, c2), hi = max(c, c2);
+            for (int t = 0; t < NBATCH; ++t) {
+                const int e = 32 * t + lane;
+                if (e >= NE) continue;
+                const int lo = tri_row<D>(e), hi = tri_col<D>(e);
                 double v = acc[t];
                 if (hi < N) {
                     if (lo == hi && with_enc) v += pc.inv_sigma_enc[lo] * pc.inv_sigma_enc[lo];
@@ -418,7 +515,7 @@ linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __r
     if (threadIdx.x < kPartCols) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerCta; ++w) s += smem[(size_t)w * LinSmem<N>::kPerWarpDoubles + 12 + 6 * N + 2 * 32 * Cf::LD + threadIdx.x];
+        for (int w = 0; w < kWarpsPerCta; ++w) s += smem[(size_t)w * LinSmem<N>::kPerWarpDoubles + 12 + 6 * N + threadIdx.x];
         cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
     }
 }
