@@ -158,6 +158,10 @@ struct asc_handle {
     bool coarse_fresh = false;      // ... computed for exactly the current system
     int coarse_ref_iters = 0;       // PCG iterations of the solve that followed the last refresh
     int coarse_last_iters = 0;
+    int outer_iteration = 0;
+    // CUDA graph of one chunk of PCG iterations (single GPU; all kernel arguments are handle-lifetime pointers)
+    cudaGraphExec_t pcg_graph = nullptr;
+    int pcg_graph_key = -1, pcg_graph_launches = 0;        // LM/Dogleg iterate() count inside the running asc_optimize call
     cusolverDnHandle_t solver = nullptr;
     cublasHandle_t blas = nullptr;
     double* h_status = nullptr;  // pinned: status(32) + scal(8)
@@ -427,7 +431,7 @@ struct Engine {
     }
 
     // one application y = S x written into ybuf; K rows handled by the caller's kernels
-    static int schur_apply_launch(asc_handle* h, double lambda, bool update_p, double* x, const int* done) {
+    static int schur_apply_launch(asc_handle* h, double lambda, bool update_p, double* x, const int* done, const double* lambda_dev = nullptr) {
         h->launches += 3;
         prof_start(h, 3);
         if (update_p)
@@ -445,7 +449,7 @@ struct Engine {
         prof_stop(h, 4);
         prof_start(h, 5);
         schur_pass_c_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, h->rank == 0 ? 1 : 0, h->pose_ptr, h->p_lm, h->J, h->u4, x,
-                                                                         h->Bpp, h->BpK, done, h->ybuf, h->partC);
+                                                                         h->Bpp, h->BpK, done, h->ybuf, h->partC, lambda_dev);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 5);
         return ASC_OK;
@@ -478,48 +482,77 @@ struct Engine {
                                                       rc_ ? rc_ + (size_t)h->nC * N : nullptr);
             CUDA_TRY(cudaGetLastError());
             if (h->use_coarse) { int rc3 = coarse_apply(h, nullptr); if (rc3) return rc3; }
-            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN);
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN, lambda);
         } else {
             pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
             CUDA_TRY(cudaGetLastError());
-            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr);
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr, lambda);
         }
         CUDA_TRY(cudaGetLastError());
         const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
         const int chunk = 8;
         int launched = 0;
-        for (;;) {
-            for (int c = 0; c < chunk; ++c) {
-                int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags);
+        const double* lam_dev = h->scal + 8;
+        auto one_iteration = [&]() -> int {
+            int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev);
+            if (rc) return rc;
+            const double* pc_ = h->partC;
+            const double* pb_ = h->partB;
+            int nC = h->nCtaPose, nB = h->nBlkLm;
+            if (h->world > 1) {
+                double* rowC = h->ybuf + PN + 8;
+                double* rowB = rowC + kPartCols;
+                reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, h->nCtaPose, rowC);
+                reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partB, h->nBlkLm, 6, kPcgCols, h->nBlkLm, rowB);
+                CUDA_TRY(cudaGetLastError());
+                rc = allreduce(h, h->ybuf, PN + 8 + 2 * kPartCols);
                 if (rc) return rc;
-                const double* pc_ = h->partC;
-                const double* pb_ = h->partB;
-                int nC = h->nCtaPose, nB = h->nBlkLm;
-                if (h->world > 1) {
-                    double* rowC = h->ybuf + PN + 8;
-                    double* rowB = rowC + kPartCols;
-                    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, h->nCtaPose, rowC);
-                    reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partB, h->nBlkLm, 6, kPcgCols, h->nBlkLm, rowB);
-                    CUDA_TRY(cudaGetLastError());
-                    rc = allreduce(h, h->ybuf, PN + 8 + 2 * kPartCols);
-                    if (rc) return rc;
-                    pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
+                pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
+            }
+            pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, lam_dev, pc_, nC, pb_, nB, h->BKK, h->MinvK, h->vp, h->vx, h->vr, h->vz,
+                                                    h->ybuf + PN, h->scal, h->flags, h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr);
+            CUDA_TRY(cudaGetLastError());
+            if (h->use_clusters) {
+                pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
+                                                                      h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr);
+                if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags); if (rc3) return rc3; }
+            } else {
+                pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
+            }
+            CUDA_TRY(cudaGetLastError());
+            h->launches += 3;
+            pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, h->partA, nUpd, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags,
+                                                    h->use_coarse ? h->rc : nullptr, h->zc, h->nz);
+            CUDA_TRY(cudaGetLastError());
+            return ASC_OK;
+        };
+        // one chunk = `chunk` iterations; kernels return immediately once the device-side done flag is set
+        static const bool no_graph = getenv("ASC_NO_GRAPH") != nullptr;
+        const bool profiling = h->prof_id != 0 && 2 * h->prof_n + 1 < (int)h->prof_ev.size();   // event-bracketed launches cannot be captured
+        const bool can_graph = !no_graph && h->world == 1 && !profiling && (!h->use_coarse || h->coarse_f32_active);
+        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0);
+        for (;;) {
+            if (can_graph) {
+                if (!h->pcg_graph || h->pcg_graph_key != graph_key) {
+                    if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }
+                    const long long before = h->launches;
+                    cudaGraph_t graph = nullptr;
+                    CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                    int rc = ASC_OK;
+                    for (int c = 0; c < chunk && !rc; ++c) rc = one_iteration();
+                    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                    if (ce != cudaSuccess) return fail(ASC_ERR_CUDA, "PCG graph capture failed: %s", cudaGetErrorString(ce));
+                    CUDA_TRY(cudaGraphInstantiate(&h->pcg_graph, graph, 0));
+                    cudaGraphDestroy(graph);
+                    h->pcg_graph_launches = (int)(h->launches - before);
+                    h->launches = before;
+                    h->pcg_graph_key = graph_key;
                 }
-                pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, pc_, nC, pb_, nB, h->BKK, h->MinvK, h->vp, h->vx, h->vr, h->vz,
-                                                        h->ybuf + PN, h->scal, h->flags, h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr);
-                CUDA_TRY(cudaGetLastError());
-                if (h->use_clusters) {
-                    pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
-                                                                          h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr);
-                    if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags); if (rc3) return rc3; }
-                }
-                else
-                    pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
-                CUDA_TRY(cudaGetLastError());
-                h->launches += 3;
-                pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, h->partA, nUpd, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags,
-                                                        h->use_coarse ? h->rc : nullptr, h->zc, h->nz);
-                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaGraphLaunch(h->pcg_graph, h->stream));
+                h->launches += h->pcg_graph_launches;
+            } else {
+                for (int c = 0; c < chunk; ++c) { int rc = one_iteration(); if (rc) return rc; }
             }
             launched += chunk;
             CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -615,7 +648,7 @@ int dispatch_schur_c(asc_handle* h, double lambda, double* x, double* u4_in) {
 #define X(n)                                                                                                                      \
     case n:                                                                                                                       \
         schur_pass_c_kernel<n><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, 0, h->pose_ptr, h->p_lm, h->J, u4_in, x, \
-                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC);             \
+                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr);    \
         break;
     switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
 #undef X
@@ -749,7 +782,9 @@ int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
         if (ok) {
             accept_try(h);
             // a step that changed the error a lot changed the robust weights (hence S) a lot: rebuild the coarse operator
-            if ((*error - new_error) > 0.01 * *error) h->coarse_valid = false;
+            // (C2: a stale operator costs ~1000 extra PCG iterations after a 30 % drop, ~15 after a 20 % drop; a rebuild costs ~110)
+            // and the first steps from an initial estimate re-weight almost every factor even when the error barely moves
+            if ((*error - new_error) > 0.25 * *error || h->outer_iteration < 2) h->coarse_valid = false;
             *error = new_error;
             *lambda = std::max(*lambda / p.lambda_factor, p.lambda_lower_bound);
             lg->accepted = 1;
@@ -936,6 +971,7 @@ int asc_set_params(asc_handle* h, const asc_params* params) {
     const int dev = h->prm.device;
     h->prm = *params;
     h->prm.device = dev;
+    if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }   // tolerances are baked into the graph
     return ASC_OK;
 }
 
@@ -944,6 +980,7 @@ int asc_destroy(asc_handle* h) {
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     if (h->solver) cusolverDnDestroy(h->solver);
     if (h->blas) cublasDestroy(h->blas);
     free_device(h);
@@ -1006,6 +1043,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     h->P = P; h->L = L; h->M = M;
     h->values_set = false; h->linearized = false; h->lin_lambda = -1.0;
     h->coarse_valid = false; h->coarse_ref_iters = 0; h->coarse_last_iters = 0;
+    if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }
     // constants
     const asc_params& pr = h->prm;
     h->cm.inv_sigma_px = 1.0 / pr.sigma_px;
@@ -1191,7 +1229,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
     h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
     ALLOC(errblk, h->nErrBlk);
-    ALLOC(scal, 8); ALLOC(status, 64); ALLOC(flags, 8); ALLOC(cheir, 1); ALLOC(SKK, 36); ALLOC(stage3, (size_t)L * 3);
+    ALLOC(scal, 16); ALLOC(status, 64); ALLOC(flags, 8); ALLOC(cheir, 1); ALLOC(SKK, 36); ALLOC(stage3, (size_t)L * 3);
 #undef ALLOC
     rc = commit_arena(h, reqs);
     if (rc) return rc;
@@ -1321,6 +1359,7 @@ int asc_optimize(asc_handle* h, int32_t mode, asc_iter_log* log, int32_t log_cap
             e_old = error;
             asc_iter_log lg;
             std::memset(&lg, 0, sizeof lg);
+            h->outer_iteration = iterations;
             rc = mode == ASC_BATCH_LM ? lm_iterate(h, &error, &lambda, &lg) : dogleg_iterate(h, &error, &Delta, &lg);
             if (rc) break;
             ++iterations;

@@ -1205,10 +1205,12 @@ schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const double* __restr
 // CTA partial row: [ sum_p B_pK^T x_p (6) | sum_p x_p . y_p (1) ]
 template <int N>
 __global__ void __launch_bounds__(kCtaThreads)
-schur_pass_c_kernel(int P, int64_t M, double lambda, int add_diag, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
+schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
                     const double2* __restrict__ J, const double* __restrict__ u4, const double* __restrict__ x, const double* __restrict__ Bpp,
-                    const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part) {
+                    const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part,
+                    const double* __restrict__ lambda_dev) {
     if (done && *done) return;
+    const double lambda = lambda_dev ? *lambda_dev : lambda_val;   // device-resident inside the captured PCG graph
     __shared__ double s_part[kWarpsPerCta][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * kWarpsPerCta + warp;
@@ -1314,11 +1316,13 @@ __device__ inline double block_reduce_rows(const double* __restrict__ part, int 
 //   partB: block partials of pass B [nB][32] (cols 0..5 = sum W_Kj u_j)
 // Multi-GPU: the partial sums have been all-reduced already and arrive as a single row each (nC = nB = 1).
 __global__ void __launch_bounds__(kReduceThreads)
-pcg_mid_kernel(int P, int N, double lambda, const double* __restrict__ partC, int nC, const double* __restrict__ partB, int nB,
+pcg_mid_kernel(int P, int N, double lambda_val, const double* __restrict__ lambda_dev, const double* __restrict__ partC, int nC,
+               const double* __restrict__ partB, int nB,
                const double* __restrict__ BKK, const double* __restrict__ MinvK, double* __restrict__ p, double* __restrict__ x,
                double* __restrict__ r, double* __restrict__ z, double* __restrict__ yK_out, double* __restrict__ scal, int* __restrict__ done,
                double* __restrict__ rcK) {
     if (*done) return;
+    const double lambda = lambda_dev ? *lambda_dev : lambda_val;
     __shared__ double scratch[kReduceThreads];
     __shared__ double sc[kPcgCols], sb[kPcgCols];
     __shared__ double sh[16];
@@ -1488,7 +1492,7 @@ pcg_init_kernel(int P, const double* __restrict__ rhs, const double* __restrict_
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __restrict__ kdot, double* __restrict__ scal,
                     int* __restrict__ done, const double* __restrict__ rc, const double* __restrict__ zc, int nz, double* __restrict__ zK,
-                    double* __restrict__ pK) {
+                    double* __restrict__ pK, double lambda) {
     __shared__ double scratch[kReduceThreads];
     __shared__ double so[1];
     block_sum_cols<1>(part, nPart, so, scratch);
@@ -1507,6 +1511,7 @@ pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __
     if (threadIdx.x == 0) {
         if (kdot) t += *kdot;
         scal[0] = 0.0; scal[1] = 0.0; scal[2] = t; scal[3] = t; scal[4] = 0.0; scal[5] = 0.0; scal[6] = 0.0; scal[7] = 0.0;
+        scal[8] = lambda;   // read by the kernels of the captured PCG graph
         *done = (t > 0.0) ? 0 : 1;   // zero right-hand side: nothing to do
     }
 }
