@@ -139,7 +139,8 @@ struct asc_handle {
     std::vector<cudaEvent_t> prof_ev;
     double *q_save = nullptr, *lm4_save = nullptr, *X_save = nullptr, *stage3 = nullptr;
     // cluster-Jacobi preconditioner
-    bool use_clusters = false;
+    bool use_clusters = false, dup_obs = false;   // dup_obs: some landmark is observed twice from one keyframe
+    int gmax = 1;
     int nC = 0, nmax = 0;
     size_t scTotal = 0, regionA = 0;
     int *cl_ptr = nullptr, *pose_cluster = nullptr, *p_run_lo = nullptr, *p_run_hi = nullptr;
@@ -252,6 +253,7 @@ struct Engine {
         CUDA_TRY(cudaFuncSetAttribute(linearize_pose_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<N>::kBytes));
         CUDA_TRY(cudaFuncSetAttribute(pose_schur_diag_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PrecSmem<N>::kBytes));
         CUDA_TRY(cudaFuncSetAttribute(cluster_schur_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(cluster_schur_cta_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(cluster_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         done = true;
         return ASC_OK;
@@ -324,7 +326,12 @@ struct Engine {
         landmark_invert_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->L, lambda, h->C, h->gl, h->WK, h->Cinv, h->cg4, h->partL, h->flags + 1);
         CUDA_TRY(cudaGetLastError());
         DBG_SYNC(h, "landmark_invert");
-        if (h->use_clusters) {
+        if (h->use_clusters && !h->dup_obs) {
+            const size_t sm = sizeof(double) * ((size_t)h->nmax * (h->nmax | 1) + h->nmax + 2 * (size_t)h->gmax * 3 * N) + sizeof(int) * (h->gmax + 2);
+            cluster_schur_cta_kernel<N><<<h->nC, 256, sm, h->stream>>>(lambda, h->rank == 0 ? 1 : 0, h->gmax, h->cl_ptr, h->cl_off, h->cl_inc_ptr, h->cl_inc,
+                                                                      h->inc_lo, h->inc_hi, h->inc_lm, h->l_pose, h->l_perm, h->Wm, h->Cinv, h->cg4, h->Bpp,
+                                                                      h->Dloc, h->rloc);
+        } else if (h->use_clusters) {
             const size_t sm = sizeof(double) * kWarpsPerCta * ((size_t)N * h->nmax + 3 * N);
             cluster_schur_kernel<N><<<h->nCtaPose, kCtaThreads, sm, h->stream>>>(h->P, lambda, h->rank == 0 ? 1 : 0, h->nmax, h->pose_ptr, h->p_lm,
                                                                                h->p_run_lo, h->p_run_hi, h->l_pose, h->l_perm, h->Wm, h->Cinv, h->cg4,
@@ -1085,6 +1092,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     lap("two observation orders");
     // ---- preconditioner clusters: runs of consecutive keyframes that share landmarks
     const int gmax = std::max(1, std::min(pr.pcg_cluster_max, 128 / N));
+    h->gmax = gmax;
     h->use_clusters = gmax > 1;
     struct PairRec { long long key; int a, b; };
     std::vector<PairRec> pairs;
@@ -1133,6 +1141,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         }
         h->scTotal = (size_t)cl_off[h->nC];
         run_lo.resize(M); run_hi.resize(M);
+        h->dup_obs = false;
         h->nz = h->nC * N + 6;
         h->use_coarse = pr.pcg_coarse_max_dim > 0 && h->nz <= pr.pcg_coarse_max_dim && h->nC > 1;
         for (int j = 0; j < L; ++j) {
@@ -1143,7 +1152,8 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 const int cid = pose_cluster[l_pose[a]];
                 while (b < lm_ptr[j + 1] && pose_cluster[l_pose[b]] == cid) ++b;
                 for (int kk = a; kk < b; ++kk) { run_lo[l_perm[kk]] = a; run_hi[l_perm[kk]] = b; }
-                if (h->use_coarse) { inc_lo.push_back(a); inc_hi.push_back(b); inc_lm.push_back(j); inc_cl.push_back(cid); }
+                inc_lo.push_back(a); inc_hi.push_back(b); inc_lm.push_back(j); inc_cl.push_back(cid);
+                for (int kk = a + 1; kk < b; ++kk) if (l_pose[kk] == l_pose[kk - 1]) h->dup_obs = true;
                 a = b;
             }
             if (h->use_coarse)   // block updates of E = Z^T S Z: lower triangle of cluster pairs, in landmark order
@@ -1174,11 +1184,14 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 pair_a.push_back(pairs[i].a); pair_b.push_back(pairs[i].b);
             }
             dest_ptr.push_back((int)pairs.size());
-            h->nInc = (int)inc_lo.size(); h->nDest = (int)dest_ca.size();
-            cl_inc_ptr.assign(h->nC + 1, 0);
-            for (int c : inc_cl) cl_inc_ptr[c + 1]++;
-            for (int c = 0; c < h->nC; ++c) cl_inc_ptr[c + 1] += cl_inc_ptr[c];
-            cl_inc.assign(inc_cl.size(), 0);
+            h->nDest = (int)dest_ca.size();
+        }
+        h->nInc = (int)inc_lo.size();
+        cl_inc_ptr.assign(h->nC + 1, 0);
+        for (int c : inc_cl) cl_inc_ptr[c + 1]++;
+        for (int c = 0; c < h->nC; ++c) cl_inc_ptr[c + 1] += cl_inc_ptr[c];
+        cl_inc.assign(inc_cl.size(), 0);
+        {
             std::vector<int> f(cl_inc_ptr.begin(), cl_inc_ptr.end() - 1);
             for (size_t i = 0; i < inc_cl.size(); ++i) cl_inc[f[inc_cl[i]]++] = (int)i;
         }
@@ -1207,11 +1220,12 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     if (h->use_clusters) {
         ALLOC(cl_ptr, h->nC + 1); ALLOC(cl_off, h->nC + 1); ALLOC(pose_cluster, P); ALLOC(p_run_lo, Mz); ALLOC(p_run_hi, Mz);
         ALLOC(Wm, Mz * 3 * N); ALLOC(Mc, h->scTotal);
+        ALLOC(inc_lo, h->nInc); ALLOC(inc_hi, h->nInc); ALLOC(inc_lm, h->nInc); ALLOC(cl_inc_ptr, h->nC + 1); ALLOC(cl_inc, h->nInc);
     }
     if (h->use_coarse) {
         const size_t ni = h->nInc, nd = h->nDest, np = pair_a.size(), nz = h->nz;
-        ALLOC(inc_lo, ni); ALLOC(inc_hi, ni); ALLOC(inc_lm, ni); ALLOC(dest_ptr, nd + 1); ALLOC(dest_ca, nd); ALLOC(dest_cb, nd);
-        ALLOC(pair_a, np); ALLOC(pair_b, np); ALLOC(cl_inc_ptr, h->nC + 1); ALLOC(cl_inc, ni);
+        ALLOC(dest_ptr, nd + 1); ALLOC(dest_ca, nd); ALLOC(dest_cb, nd);
+        ALLOC(pair_a, np); ALLOC(pair_b, np);
         ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, nz); ALLOC(zc, nz);
         if (pr.pcg_coarse_fp32) { ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * nz); } else { h->Ef = nullptr; h->Einvf = nullptr; }
         if (!h->solver) {
@@ -1271,11 +1285,16 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         UP(pose_cluster, pose_cluster.data(), sizeof(int) * P);
         if (M) { UP(p_run_lo, run_lo.data(), sizeof(int) * Mz); UP(p_run_hi, run_hi.data(), sizeof(int) * Mz); }
     }
-    if (h->use_coarse && h->nInc) {
-        UP(inc_lo, inc_lo.data(), sizeof(int) * h->nInc); UP(inc_hi, inc_hi.data(), sizeof(int) * h->nInc); UP(inc_lm, inc_lm.data(), sizeof(int) * h->nInc);
+    if (h->use_clusters) {
+        UP(cl_inc_ptr, cl_inc_ptr.data(), sizeof(int) * (h->nC + 1));
+        if (h->nInc) {
+            UP(inc_lo, inc_lo.data(), sizeof(int) * h->nInc); UP(inc_hi, inc_hi.data(), sizeof(int) * h->nInc); UP(inc_lm, inc_lm.data(), sizeof(int) * h->nInc);
+            UP(cl_inc, cl_inc.data(), sizeof(int) * h->nInc);
+        }
+    }
+    if (h->use_coarse && h->nDest) {
         UP(dest_ptr, dest_ptr.data(), sizeof(int) * (h->nDest + 1)); UP(dest_ca, dest_ca.data(), sizeof(int) * h->nDest); UP(dest_cb, dest_cb.data(), sizeof(int) * h->nDest);
         UP(pair_a, pair_a.data(), sizeof(int) * pair_a.size()); UP(pair_b, pair_b.data(), sizeof(int) * pair_b.size());
-        UP(cl_inc_ptr, cl_inc_ptr.data(), sizeof(int) * (h->nC + 1)); UP(cl_inc, cl_inc.data(), sizeof(int) * h->nInc);
     }
     UP(enc, enc, sizeof(double) * PN);
     if (L) UP(lm_prior, lm_prior, sizeof(double) * 3 * L);

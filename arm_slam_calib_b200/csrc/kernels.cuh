@@ -871,6 +871,76 @@ cluster_schur_kernel(int P, double lambda, int add_diag, int nmax, const int* __
     if (lane < N) rloc[(size_t)p * N + lane] = -racc;
 }
 
+// Cluster-major variant of the same computation: one CTA per cluster walks the cluster's (landmark, cluster) incidences
+// in a fixed order and accumulates the whole n x n block (and the cluster's share of the reduced right-hand side) in shared
+// memory.  Inside one incidence every S entry is touched by exactly one thread (the host checks that a landmark is seen at
+// most once per keyframe), so the result is deterministic.  ~10x faster than the keyframe-major kernel above, whose
+// pair loop is a chain of dependent gathers.
+template <int N>
+__global__ void __launch_bounds__(256)
+cluster_schur_cta_kernel(double lambda, int add_diag, int gmax, const int* __restrict__ cl_ptr, const long long* __restrict__ cl_off,
+                         const int* __restrict__ cl_inc_ptr, const int* __restrict__ cl_inc, const int* __restrict__ inc_lo,
+                         const int* __restrict__ inc_hi, const int* __restrict__ inc_lm, const int* __restrict__ l_pose,
+                         const int* __restrict__ l_perm, const double* __restrict__ Wm, const double* __restrict__ Cinv,
+                         const double* __restrict__ cg4, const double* __restrict__ Bpp, double* __restrict__ Sc, double* __restrict__ rloc) {
+    extern __shared__ double sm[];
+    const int c = blockIdx.x, c0 = cl_ptr[c], npose = cl_ptr[c + 1] - c0, n = npose * N, ld = n | 1;
+    double* S = sm;                         // [n][ld]
+    double* rl = S + (size_t)n * ld;        // [n]
+    double* Wb = rl + n;                    // [gmax][3N]
+    double* Yb = Wb + gmax * 3 * N;         // [gmax][3N]
+    int* pp = reinterpret_cast<int*>(Yb + gmax * 3 * N);   // [gmax]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n * ld; i += 256) S[i] = 0.0;
+    for (int i = tid; i < n; i += 256) rl[i] = 0.0;
+    __syncthreads();
+    if (add_diag)
+        for (int i = tid; i < npose * N * N; i += 256) {
+            const int p = i / (N * N), a = (i / N) % N, b = i % N;
+            S[(p * N + a) * ld + p * N + b] = Bpp[(size_t)(c0 + p) * N * N + a * N + b] + (a == b ? lambda : 0.0);
+        }
+    __syncthreads();
+    for (int q = cl_inc_ptr[c]; q < cl_inc_ptr[c + 1]; ++q) {
+        const int inc = cl_inc[q];
+        const int lo = inc_lo[inc], r = inc_hi[inc] - lo, j = inc_lm[inc];
+        for (int t = tid; t < r * 3 * N; t += 256) Wb[t] = Wm[(size_t)__ldg(l_perm + lo + t / (3 * N)) * 3 * N + t % (3 * N)];
+        if (tid < r) pp[tid] = __ldg(l_pose + lo + tid) - c0;
+        __syncthreads();
+        const double* ci = Cinv + 6 * (size_t)j;
+        for (int t = tid; t < r * 3 * N; t += 256) {
+            const int base = t - t % 3, cc = t % 3;
+            const double c0_ = cc == 0 ? ci[0] : (cc == 1 ? ci[1] : ci[2]);
+            const double c1_ = cc == 0 ? ci[1] : (cc == 1 ? ci[3] : ci[4]);
+            const double c2_ = cc == 0 ? ci[2] : (cc == 1 ? ci[4] : ci[5]);
+            Yb[t] = Wb[base] * c0_ + Wb[base + 1] * c1_ + Wb[base + 2] * c2_;
+        }
+        if (tid < r * N) {   // reduced right-hand side: - W_m (Cinv g)_j
+            const int i = tid / N, a = tid % N;
+            const double* g = cg4 + 4 * (size_t)j;
+            rl[pp[i] * N + a] -= Wb[i * 3 * N + 3 * a] * g[0] + Wb[i * 3 * N + 3 * a + 1] * g[1] + Wb[i * 3 * N + 3 * a + 2] * g[2];
+        }
+        __syncthreads();
+        {   // thread = fixed (a, b) entry of the N x N block; thread groups stride over the r*r keyframe pairs
+            constexpr int NN = N * N, NGRP = 256 / NN > 0 ? 256 / NN : 1;
+            const int ab = tid % NN, grp = tid / NN, a = ab / N, b = ab % N;
+            if (grp < NGRP)
+                for (int i = 0; i < r; ++i) {
+                    const double* y = Yb + i * 3 * N + 3 * a;
+                    const double y0 = y[0], y1 = y[1], y2 = y[2];
+                    double* Srow = S + (pp[i] * N + a) * ld + b;
+                    for (int i2 = grp; i2 < r; i2 += NGRP) {
+                        const double* w = Wb + i2 * 3 * N + 3 * b;
+                        Srow[pp[i2] * N] -= y0 * w[0] + y1 * w[1] + y2 * w[2];
+                    }
+                }
+        }
+        __syncthreads();
+    }
+    double* out = Sc + cl_off[c];
+    for (int i = tid; i < n * n; i += 256) out[i] = S[(i / n) * ld + i % n];
+    for (int i = tid; i < n; i += 256) rloc[(size_t)c0 * N + i] = rl[i];
+}
+
 // In-place Gauss-Jordan inverse of one cluster block (SPD, no pivoting) in shared memory; one CTA per cluster.
 // Also forms the reduced right-hand side of the cluster: rhs = g + rsum.
 __global__ void __launch_bounds__(256)
