@@ -30,12 +30,12 @@ def build(force=False, verbose=False, dof_list=None):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3", "-shared", "-o", LIB]
+           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3,-fopenmp", "-shared", "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     if dof_list:
         cmd += ["-DASC_DOF_LIST(X)=" + " ".join("X(%d)" % n for n in dof_list)]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lcusolver", "-lcublas", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lgomp", "-lcusolver", "-lcublas", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

@@ -6,6 +6,7 @@
 #include <cusolverDn.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types only; the library is dlopen()ed when a communicator is requested
+#include <omp.h>
 
 #include <algorithm>
 #include <chrono>
@@ -85,6 +86,40 @@ int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
             if (e__ != cudaSuccess) return fail(ASC_ERR_CUDA, "kernel %s failed: %s", name, cudaGetErrorString(e__)); \
         }                                                                                                             \
     } while (0)
+
+}  // namespace
+
+namespace {
+
+// Stable parallel counting sort: dest[i] = position of element i when elements are grouped by key(i) (ties keep their
+// order); ptr[b] = start of bucket b.  Host packing of a 2M-observation graph is on the end-to-end path of every optimize().
+template <typename KeyFn>
+void parallel_bucket_sort(int64_t n, int nb, KeyFn key, std::vector<int>& ptr, int* dest) {
+    const int T = std::max(1, std::min(omp_get_max_threads(), 16));
+    std::vector<int> hist((size_t)T * nb, 0);
+    ptr.assign((size_t)nb + 1, 0);
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num();
+        const int64_t lo = n * t / T, hi = n * (t + 1) / T;
+        int* h = hist.data() + (size_t)t * nb;
+        for (int64_t i = lo; i < hi; ++i) h[key(i)]++;
+#pragma omp barrier
+#pragma omp for schedule(static)
+        for (int b = 0; b < nb; ++b) {
+            int s = 0;
+            for (int u = 0; u < T; ++u) { const int c = hist[(size_t)u * nb + b]; hist[(size_t)u * nb + b] = s; s += c; }
+            ptr[b + 1] = s;   // bucket total for now
+        }
+#pragma omp single
+        {
+            int run = 0;
+            for (int b = 0; b < nb; ++b) { const int c = ptr[b + 1]; ptr[b] = run; run += c; }
+            ptr[nb] = run;
+        }
+        for (int64_t i = lo; i < hi; ++i) { const int b = key(i); dest[i] = ptr[b] + h[b]++; }
+    }
+}
 
 }  // namespace
 
@@ -1064,30 +1099,31 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     h->pc.use_dead_band = pr.use_dead_band; h->pc.dead_band = pr.dead_band; h->pc.chart = pr.pose3_chart;
 
     // ---- the two observation orders (stable counting sorts: list order kept inside each segment)
-    std::vector<int> pose_ptr(P + 1, 0), lm_ptr(L + 1, 0);
-    for (int64_t m = 0; m < M; ++m) { pose_ptr[pose_idx[m] + 1]++; lm_ptr[lm_idx[m] + 1]++; }
-    for (int p = 0; p < P; ++p) pose_ptr[p + 1] += pose_ptr[p];
-    for (int j = 0; j < L; ++j) lm_ptr[j + 1] += lm_ptr[j];
+    std::vector<int> pose_ptr, lm_ptr;
     // staging buffers persist across calls (no page faults when a graph of similar size is re-packed)
-    static thread_local std::vector<int> p_lm, p_pose, p_orig, pos_of, l_pose, l_perm, run_lo, run_hi;
-    static thread_local std::vector<double> p_uv, l_uv;
-    p_lm.resize(M); p_pose.resize(M); p_orig.resize(M); pos_of.resize(M); l_pose.resize(M); l_perm.resize(M);
+    // (thread_local objects resolve per OpenMP worker, so the parallel loops below go through plain references)
+    static thread_local std::vector<int> tl_i[9];
+    static thread_local std::vector<double> tl_d[2];
+    std::vector<int>&p_lm = tl_i[0], &p_pose = tl_i[1], &p_orig = tl_i[2], &pos_of = tl_i[3], &l_pose = tl_i[4], &l_perm = tl_i[5], &run_lo = tl_i[6],
+                    &run_hi = tl_i[7], &dest1 = tl_i[8];
+    std::vector<double>&p_uv = tl_d[0], &l_uv = tl_d[1];
+    p_lm.resize(M); p_pose.resize(M); p_orig.resize(M); pos_of.resize(M); l_pose.resize(M); l_perm.resize(M); dest1.resize(M);
     p_uv.resize(2 * M); l_uv.resize(2 * M);
-    {
-        std::vector<int> fill(pose_ptr.begin(), pose_ptr.end() - 1);
-        for (int64_t m = 0; m < M; ++m) {
-            const int k = fill[pose_idx[m]]++;
-            p_lm[k] = lm_idx[m]; p_pose[k] = pose_idx[m]; p_orig[k] = (int)m; pos_of[m] = k;
-            p_uv[2 * k] = uv[2 * m]; p_uv[2 * k + 1] = uv[2 * m + 1];
-        }
-        // landmark-major: inside a landmark, observations ordered by keyframe (then by list order)
-        std::vector<int> fl(lm_ptr.begin(), lm_ptr.end() - 1);
-        for (int64_t kp = 0; kp < M; ++kp) {
-            const int m = p_orig[kp];
-            const int k = fl[lm_idx[m]]++;
-            l_pose[k] = pose_idx[m]; l_perm[k] = (int)kp; pos_of[kp] = k;   // pos_of now: pose-major -> landmark-major
-            l_uv[2 * k] = uv[2 * m]; l_uv[2 * k + 1] = uv[2 * m + 1];
-        }
+    // pose-major: stable by list order
+    parallel_bucket_sort(M, P, [&](int64_t m) { return pose_idx[m]; }, pose_ptr, dest1.data());
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < M; ++m) {
+        const int k = dest1[m];
+        p_lm[k] = lm_idx[m]; p_pose[k] = pose_idx[m]; p_orig[k] = (int)m;
+        p_uv[2 * k] = uv[2 * m]; p_uv[2 * k + 1] = uv[2 * m + 1];
+    }
+    // landmark-major: inside a landmark, observations ordered by keyframe (then by list order); pos_of = pose-major -> landmark-major
+    parallel_bucket_sort(M, std::max(L, 1), [&](int64_t kp) { return p_lm[kp]; }, lm_ptr, pos_of.data());
+#pragma omp parallel for schedule(static)
+    for (int64_t kp = 0; kp < M; ++kp) {
+        const int k = pos_of[kp], m = p_orig[kp];
+        l_pose[k] = p_pose[kp]; l_perm[k] = (int)kp;
+        l_uv[2 * k] = uv[2 * m]; l_uv[2 * k + 1] = uv[2 * m + 1];
     }
     lap("two observation orders");
     // ---- preconditioner clusters: runs of consecutive keyframes that share landmarks
@@ -1144,44 +1180,69 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         h->dup_obs = false;
         h->nz = h->nC * N + 6;
         h->use_coarse = pr.pcg_coarse_max_dim > 0 && h->nz <= pr.pcg_coarse_max_dim && h->nC > 1;
-        for (int j = 0; j < L; ++j) {
-            int a = lm_ptr[j];
-            const size_t first_inc = inc_lo.size();
-            while (a < lm_ptr[j + 1]) {
-                int b = a + 1;
-                const int cid = pose_cluster[l_pose[a]];
-                while (b < lm_ptr[j + 1] && pose_cluster[l_pose[b]] == cid) ++b;
-                for (int kk = a; kk < b; ++kk) { run_lo[l_perm[kk]] = a; run_hi[l_perm[kk]] = b; }
-                inc_lo.push_back(a); inc_hi.push_back(b); inc_lm.push_back(j); inc_cl.push_back(cid);
-                for (int kk = a + 1; kk < b; ++kk) if (l_pose[kk] == l_pose[kk - 1]) h->dup_obs = true;
-                a = b;
+        {   // incidences = (landmark, cluster) runs of the landmark-major list; built per thread over landmark ranges, then concatenated
+            const int T = std::max(1, std::min(omp_get_max_threads(), 16));
+            struct Local { std::vector<int> lo, hi, lm, cl; std::vector<PairRec> pairs; bool dup = false; };
+            std::vector<Local> loc(T);
+#pragma omp parallel num_threads(T)
+            {
+                const int t = omp_get_thread_num();
+                Local& Lc = loc[t];
+                const int j0 = (int)((int64_t)L * t / T), j1 = (int)((int64_t)L * (t + 1) / T);
+                for (int j = j0; j < j1; ++j) {
+                    int a = lm_ptr[j];
+                    const size_t first_inc = Lc.lo.size();
+                    while (a < lm_ptr[j + 1]) {
+                        int b = a + 1;
+                        const int cid = pose_cluster[l_pose[a]];
+                        while (b < lm_ptr[j + 1] && pose_cluster[l_pose[b]] == cid) ++b;
+                        for (int kk = a; kk < b; ++kk) { run_lo[l_perm[kk]] = a; run_hi[l_perm[kk]] = b; }
+                        Lc.lo.push_back(a); Lc.hi.push_back(b); Lc.lm.push_back(j); Lc.cl.push_back(cid);
+                        for (int kk = a + 1; kk < b; ++kk) if (l_pose[kk] == l_pose[kk - 1]) Lc.dup = true;
+                        a = b;
+                    }
+                    if (h->use_coarse)   // block updates of E = Z^T S Z: lower triangle of cluster pairs, in landmark order (local incidence ids)
+                        for (size_t ia = first_inc; ia < Lc.lo.size(); ++ia)
+                            for (size_t ib = first_inc; ib < Lc.lo.size(); ++ib)
+                                if (Lc.cl[ia] >= Lc.cl[ib]) Lc.pairs.push_back({(long long)Lc.cl[ia] * h->nC + Lc.cl[ib], (int)ia, (int)ib});
+                }
             }
-            if (h->use_coarse)   // block updates of E = Z^T S Z: lower triangle of cluster pairs, in landmark order
-                for (size_t ia = first_inc; ia < inc_lo.size(); ++ia)
-                    for (size_t ib = first_inc; ib < inc_lo.size(); ++ib)
-                        if (inc_cl[ia] >= inc_cl[ib]) pairs.push_back({(long long)inc_cl[ia] * h->nC + inc_cl[ib], (int)ia, (int)ib});
+            size_t ninc = 0, npair = 0;
+            std::vector<size_t> inc_off(T + 1, 0), pair_off(T + 1, 0);
+            for (int t = 0; t < T; ++t) { inc_off[t] = ninc; pair_off[t] = npair; ninc += loc[t].lo.size(); npair += loc[t].pairs.size(); h->dup_obs = h->dup_obs || loc[t].dup; }
+            inc_lo.resize(ninc); inc_hi.resize(ninc); inc_lm.resize(ninc); inc_cl.resize(ninc); pairs.resize(npair);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int t = 0; t < T; ++t) {
+                const Local& Lc = loc[t];
+                std::copy(Lc.lo.begin(), Lc.lo.end(), inc_lo.begin() + inc_off[t]); std::copy(Lc.hi.begin(), Lc.hi.end(), inc_hi.begin() + inc_off[t]);
+                std::copy(Lc.lm.begin(), Lc.lm.end(), inc_lm.begin() + inc_off[t]); std::copy(Lc.cl.begin(), Lc.cl.end(), inc_cl.begin() + inc_off[t]);
+                for (size_t i = 0; i < Lc.pairs.size(); ++i) {
+                    PairRec r = Lc.pairs[i];
+                    r.a += (int)inc_off[t]; r.b += (int)inc_off[t];
+                    pairs[pair_off[t] + i] = r;
+                }
+            }
         }
         lap("runs + incidences + pairs");
         if (h->use_coarse) {
-            {   // stable LSD radix sort of the pairs by (cluster a, cluster b): two counting passes instead of a comparison sort
+            {   // stable LSD radix sort of the pairs by (cluster a, cluster b): two parallel counting passes
                 const int nCl = h->nC;
                 std::vector<PairRec> tmp(pairs.size());
-                std::vector<int> cntv(nCl + 1);
+                std::vector<int> bptr, dst(pairs.size());
                 for (int pass = 0; pass < 2; ++pass) {
-                    std::fill(cntv.begin(), cntv.end(), 0);
-                    auto digit = [&](const PairRec& r) { return pass == 0 ? (int)(r.key % nCl) : (int)(r.key / nCl); };
-                    for (const PairRec& r : pairs) cntv[digit(r) + 1]++;
-                    for (int c = 0; c < nCl; ++c) cntv[c + 1] += cntv[c];
-                    for (const PairRec& r : pairs) tmp[cntv[digit(r)]++] = r;
+                    parallel_bucket_sort((int64_t)pairs.size(), nCl, [&](int64_t i) { return pass == 0 ? (int)(pairs[i].key % nCl) : (int)(pairs[i].key / nCl); }, bptr, dst.data());
+#pragma omp parallel for schedule(static)
+                    for (int64_t i = 0; i < (int64_t)pairs.size(); ++i) tmp[dst[i]] = pairs[i];
                     pairs.swap(tmp);
                 }
             }
+            pair_a.resize(pairs.size()); pair_b.resize(pairs.size());
             for (size_t i = 0; i < pairs.size(); ++i) {
                 if (i == 0 || pairs[i].key != pairs[i - 1].key) {
                     dest_ptr.push_back((int)i);
                     dest_ca.push_back((int)(pairs[i].key / h->nC)); dest_cb.push_back((int)(pairs[i].key % h->nC));
                 }
-                pair_a.push_back(pairs[i].a); pair_b.push_back(pairs[i].b);
+                pair_a[i] = pairs[i].a; pair_b[i] = pairs[i].b;
             }
             dest_ptr.push_back((int)pairs.size());
             h->nDest = (int)dest_ca.size();
