@@ -186,10 +186,11 @@ struct asc_handle {
     int nz = 0, nInc = 0, nDest = 0;
     int *inc_lo = nullptr, *inc_hi = nullptr, *inc_lm = nullptr, *dest_ptr = nullptr, *dest_ca = nullptr, *dest_cb = nullptr;
     int *pair_a = nullptr, *pair_b = nullptr, *cl_inc_ptr = nullptr, *cl_inc = nullptr;
-    double *Vinc = nullptr, *Tinc = nullptr, *E = nullptr, *rc = nullptr, *zc = nullptr, *SKK = nullptr, *work = nullptr;
+    double *Vinc = nullptr, *Tinc = nullptr, *E = nullptr, *rc = nullptr, *zc = nullptr, *yc = nullptr, *SKK = nullptr, *work = nullptr;
     int lwork = 0, lworkf = 0;
     float *Ef = nullptr, *workf = nullptr, *Einvf = nullptr;
     bool coarse_f32_active = false;   // E^-1 currently lives in Ef (fp32) rather than in E (fp64)
+    bool coarse_refit = false;      // this solve reuses an older inverse: fit its scalar against the freshly assembled E
     bool coarse_valid = false;      // E holds a factorised inverse (possibly from an earlier lambda / linearisation)
     bool coarse_fresh = false;      // ... computed for exactly the current system
     int coarse_ref_iters = 0;       // PCG iterations of the solve that followed the last refresh
@@ -401,10 +402,11 @@ struct Engine {
             // earlier lambda / linearisation is reused until it visibly costs iterations (deterministic policy).
             const bool refresh = h->use_coarse && (!h->coarse_valid || h->coarse_last_iters > h->coarse_ref_iters + h->coarse_ref_iters / 4 + 8);
             h->coarse_fresh = refresh;
-            if (refresh) {
+            h->coarse_refit = false;
+            if (refresh || (h->use_coarse && h->coarse_f32_active)) {
+                // E = Z^T S Z for the CURRENT system: needed for a rebuild, and (cheap, <1 ms) for re-fitting a reused inverse
                 CUDA_TRY(cudaGetLastError());
                 const int nz = h->nz;
-                h->coarse_valid = true;
                 inc_v_kernel<N><<<cdiv(std::max(h->nInc, 1), 4), 128, 0, h->stream>>>(h->nInc, h->inc_lo, h->inc_hi, h->inc_lm, h->l_perm, h->Wm, h->Cinv,
                                                                                   h->Vinc, h->Tinc);
                 DBG_SYNC(h, "inc_v");
@@ -424,6 +426,11 @@ struct Engine {
                     // every rank wrote the same S_KK: rescale the 6x6 corner
                     scale_block_kernel<<<1, 64, 0, h->stream>>>(h->E, nz, h->nC * N, 1.0 / h->world);
                 }
+                h->coarse_refit = !refresh;
+            }
+            if (refresh) {
+                const int nz = h->nz;
+                h->coarse_valid = true;
                 static const bool timing = getenv("ASC_TIMING") != nullptr;
                 cudaEvent_t e0, e1, e2;
                 if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, h->stream); }
@@ -501,7 +508,7 @@ struct Engine {
     static int coarse_apply(asc_handle* h, const int* done) {
         h->launches += 1;
         if (h->coarse_f32_active) {
-            coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, h->rc, h->zc, h->nz, done);
+            coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, h->rc, h->zc, h->nz, done, h->scal + 9);
             CUDA_TRY(cudaGetLastError());
         } else {
             const double one = 1.0, zero = 0.0;
@@ -523,7 +530,19 @@ struct Engine {
             pcg_init_k_kernel<<<1, 32, 0, h->stream>>>((int64_t)PN, h->rhs, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->status + 40,
                                                       rc_ ? rc_ + (size_t)h->nC * N : nullptr);
             CUDA_TRY(cudaGetLastError());
-            if (h->use_coarse) { int rc3 = coarse_apply(h, nullptr); if (rc3) return rc3; }
+            if (h->use_coarse) {
+                set_scalar_kernel<<<1, 1, 0, h->stream>>>(h->scal + 9, 1.0);
+                int rc3 = coarse_apply(h, nullptr);
+                if (rc3) return rc3;
+                if (h->coarse_refit && h->coarse_f32_active) {   // reused inverse: alpha = (rc.zc)/(zc.E zc) against the current E
+                    const double one = 1.0, zero = 0.0;
+                    if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->zc, 1, &zero, h->yc, 1) != CUBLAS_STATUS_SUCCESS)
+                        return fail(ASC_ERR_CUDA, "cublasDsymv failed");
+                    coarse_refit_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->rc, h->zc, h->yc, h->nz, h->scal + 9);
+                    CUDA_TRY(cudaGetLastError());
+                    h->launches += 2;
+                }
+            }
             pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN, lambda);
         } else {
             pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
@@ -826,6 +845,7 @@ int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
             // a step that changed the error a lot changed the robust weights (hence S) a lot: rebuild the coarse operator
             // (C2: a stale operator costs ~1000 extra PCG iterations after a 30 % drop, ~15 after a 20 % drop; a rebuild costs ~110)
             // and the first steps from an initial estimate re-weight almost every factor even when the error barely moves
+            // (a reused inverse is additionally re-fitted by a scalar, which narrows but does not close that gap)
             if ((*error - new_error) > 0.25 * *error || h->outer_iteration < 2) h->coarse_valid = false;
             *error = new_error;
             *lambda = std::max(*lambda / p.lambda_factor, p.lambda_lower_bound);
@@ -1287,7 +1307,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         const size_t ni = h->nInc, nd = h->nDest, np = pair_a.size(), nz = h->nz;
         ALLOC(dest_ptr, nd + 1); ALLOC(dest_ca, nd); ALLOC(dest_cb, nd);
         ALLOC(pair_a, np); ALLOC(pair_b, np);
-        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, nz); ALLOC(zc, nz);
+        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, nz); ALLOC(zc, nz); ALLOC(yc, nz);
         if (pr.pcg_coarse_fp32) { ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * nz); } else { h->Ef = nullptr; h->Einvf = nullptr; }
         if (!h->solver) {
             if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cusolverDnCreate failed");

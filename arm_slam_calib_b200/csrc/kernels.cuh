@@ -1143,8 +1143,9 @@ __global__ void __launch_bounds__(256) mirror_lower_f32_kernel(float* __restrict
 
 // zc = Einv(fp32, full symmetric, row-major) * rc, one warp per row, fp64 accumulation
 __global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
-                                                              int n, const int* __restrict__ done) {
+                                                              int n, const int* __restrict__ done, const double* __restrict__ alpha) {
     if (done && *done) return;
+    const double scale = alpha ? *alpha : 1.0;   // scalar re-fit of a reused (stale) coarse inverse, see coarse_refit_kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + warp;
     if (row >= n) return;
@@ -1162,8 +1163,29 @@ __global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __res
         if (i + 1 < n) acc0 = fma((double)a[i + 1], x[i + 1], acc0);
     }
     const double t = warp_sum(acc0 + acc1);
-    if (lane == 0) y[row] = t;
+    if (lane == 0) y[row] = scale * t;
 }
+
+// A coarse inverse kept from an earlier linearisation is mostly off by a scalar (the robust weights move together while the
+// optimiser converges).  Given zc = Einv_old rc and y = E_new zc, the best scalar is alpha = (rc.zc) / (zc.y): the exact line
+// search of the coarse correction in the E_new norm.  Writes alpha and rescales zc in place.  One block of 1024 threads.
+__global__ void __launch_bounds__(kReduceThreads) coarse_refit_kernel(const double* __restrict__ rc, double* __restrict__ zc,
+                                                                    const double* __restrict__ y, int n, double* __restrict__ alpha) {
+    __shared__ double s1[kReduceThreads], s2[kReduceThreads];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += kReduceThreads) { a += rc[i] * zc[i]; b += zc[i] * y[i]; }
+    s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = kReduceThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    const double al = (s2[0] > 0.0 && s1[0] > 0.0) ? s1[0] / s2[0] : 1.0;
+    for (int i = threadIdx.x; i < n; i += kReduceThreads) zc[i] *= al;
+    if (threadIdx.x == 0) *alpha = al;
+}
+
+__global__ void set_scalar_kernel(double* p, double v) { *p = v; }
 
 __global__ void scale_block_kernel(double* E, int nz, int off, double s) {
     const int i = threadIdx.x;
