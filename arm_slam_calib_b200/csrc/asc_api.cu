@@ -196,6 +196,8 @@ struct asc_handle {
     int coarse_ref_iters = 0;       // PCG iterations of the solve that followed the last refresh
     int coarse_last_iters = 0;
     int outer_iteration = 0;
+    bool warm_ok = false;           // vx holds the solution of an earlier damping value of the SAME linearisation
+    double warm_rz_ref = 0.0;       // preconditioned norm^2 of that first right-hand side
     // CUDA graph of one chunk of PCG iterations (single GPU; all kernel arguments are handle-lifetime pointers)
     cudaGraphExec_t pcg_graph = nullptr;
     int pcg_graph_key = -1, pcg_graph_launches = 0;        // LM/Dogleg iterate() count inside the running asc_optimize call
@@ -345,6 +347,7 @@ struct Engine {
         CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
         h->linearized = true;
         h->lin_lambda = -1.0;
+        h->warm_ok = false;
         if (ms_lin || ms_asm) {
             CUDA_TRY(cudaEventSynchronize(h->ev[2]));
             if (ms_lin) CUDA_TRY(cudaEventElapsedTime(ms_lin, h->ev[0], h->ev[1]));
@@ -523,12 +526,23 @@ struct Engine {
         const size_t PN = (size_t)h->P * N;
         const int nUpd = h->use_clusters ? h->nC : h->nCtaPose;
         h->launches += 3;
+        const double tol2_ = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
+        // A rejected LM step is re-solved with a 10x larger lambda on the same linearisation; while lambda is far below the
+        // spectrum of S the solution hardly moves, so start from it (GTSAM refactorises from scratch each time).
+        const bool warm = h->warm_ok && h->use_clusters && h->world == 1 && h->warm_rz_ref > 0.0;
+        if (warm) {
+            int rcw = schur_apply_launch(h, lambda, false, h->vx, nullptr, nullptr);   // ybuf = S x0 (keyframe rows)
+            if (rcw) return rcw;
+            schur_k_rows_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, h->partC, h->nCtaPose, h->partB, h->nBlkLm, h->BKK, h->vx, h->ybuf + PN);
+            CUDA_TRY(cudaGetLastError());
+            h->launches += 1;
+        }
         if (h->use_clusters) {
             double* rc_ = h->use_coarse ? h->rc : nullptr;
-            pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(1, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp, h->scal,
+            pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(warm ? 2 : 1, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp, h->scal,
                                                                   h->flags, h->partA, rc_);
             pcg_init_k_kernel<<<1, 32, 0, h->stream>>>((int64_t)PN, h->rhs, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->status + 40,
-                                                      rc_ ? rc_ + (size_t)h->nC * N : nullptr);
+                                                      rc_ ? rc_ + (size_t)h->nC * N : nullptr, warm ? h->ybuf + PN : nullptr);
             CUDA_TRY(cudaGetLastError());
             if (h->use_coarse) {
                 set_scalar_kernel<<<1, 1, 0, h->stream>>>(h->scal + 9, 1.0);
@@ -543,11 +557,12 @@ struct Engine {
                     h->launches += 2;
                 }
             }
-            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN, lambda);
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN, lambda,
+                                                         warm ? h->warm_rz_ref : 0.0, tol2_);
         } else {
             pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
             CUDA_TRY(cudaGetLastError());
-            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr, lambda);
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr, lambda, 0.0, tol2_);
         }
         CUDA_TRY(cudaGetLastError());
         const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
@@ -622,6 +637,7 @@ struct Engine {
             if (h->h_flags[0] || launched >= h->prm.pcg_max_iters + chunk) break;
         }
         if (iters) *iters = (int)h->h_status[32 + 5];
+        if (!warm) h->warm_rz_ref = h->h_status[32 + 3];
         return ASC_OK;
     }
 
@@ -652,6 +668,7 @@ struct Engine {
         if (h->h_flags[3] != big) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "extrinsic block is not positive definite"); }
         if (h->use_coarse && (h->h_flags[4] != 0 || h->h_flags[5] != 0)) { h->fail_kind = 'q'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "coarse-level factorisation failed (info %d/%d)", h->h_flags[4], h->h_flags[5]); }
         if (h->h_status[32 + 6] != 0.0) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "PCG breakdown: p^T S p <= 0"); }
+        h->warm_ok = true;
         return backsub(h);
     }
 

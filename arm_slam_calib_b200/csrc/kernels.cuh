@@ -992,7 +992,8 @@ pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const
     double rm = 0.0;
     if (t < n) {
         const size_t i = base + t;
-        if (init) { rm = rhs[i]; x[i] = 0.0; }
+        if (init == 1) { rm = rhs[i]; x[i] = 0.0; }
+        else if (init == 2) { rm = rhs[i] - y[i]; }   // warm start: x holds the previous solution, y = S x
         else { const double alpha = scal[0]; x[i] += alpha * p[i]; rm = r[i] - alpha * y[i]; }
         r[i] = rm;
     }
@@ -1019,16 +1020,16 @@ pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const
 // K rows at PCG start: x_K = 0, r_K = rhs_K, z_K = MinvK r_K, p_K = z_K; scal[7] = r_K . z_K   (one warp)
 __global__ void pcg_init_k_kernel(int64_t PN, const double* __restrict__ rhs, const double* __restrict__ MinvK, double* __restrict__ x,
                                   double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ kdot,
-                                  double* __restrict__ rcK) {
+                                  double* __restrict__ rcK, const double* __restrict__ yK) {
     const int lane = threadIdx.x;
-    const double rk = lane < 6 ? rhs[PN + lane] : 0.0;
+    const double rk = lane < 6 ? rhs[PN + lane] - (yK ? yK[lane] : 0.0) : 0.0;   // yK != null: warm start, x_K kept
     double zk = 0.0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         const double ri = __shfl_sync(kFull, rk, i);
         if (lane < 6) zk = fma(MinvK[6 * lane + i], ri, zk);
     }
-    if (lane < 6) { x[PN + lane] = 0.0; r[PN + lane] = rk; z[PN + lane] = zk; p[PN + lane] = zk; if (rcK) rcK[lane] = rk; }
+    if (lane < 6) { if (!yK) x[PN + lane] = 0.0; r[PN + lane] = rk; z[PN + lane] = zk; p[PN + lane] = zk; if (rcK) rcK[lane] = rk; }
     const double d = warp_sum(lane < 6 ? rk * zk : 0.0);
     if (lane == 0) *kdot = d;
 }
@@ -1459,6 +1460,22 @@ pcg_mid_kernel(int P, int N, double lambda_val, const double* __restrict__ lambd
     }
 }
 
+// K rows of y = S x from the pass B / pass C partial sums (used for the warm-start residual).  One block of 1024 threads.
+__global__ void __launch_bounds__(kReduceThreads)
+schur_k_rows_kernel(int P, int N, double lambda, const double* __restrict__ partC, int nC, const double* __restrict__ partB, int nB,
+                    const double* __restrict__ BKK, const double* __restrict__ x, double* __restrict__ yK) {
+    __shared__ double scratch[kReduceThreads];
+    __shared__ double sc[kPcgCols], sb[kPcgCols];
+    block_sum_cols<kPcgCols>(partC, nC, sc, scratch);
+    block_sum_cols<kPcgCols>(partB, nB, sb, scratch);
+    if (threadIdx.x < 6) {
+        const double* xK = x + (size_t)P * N;
+        double yk = lambda * xK[threadIdx.x] + sc[threadIdx.x] - sb[threadIdx.x];
+        for (int i = 0; i < 6; ++i) yk += BKK[6 * threadIdx.x + i] * xK[i];
+        yK[threadIdx.x] = yk;
+    }
+}
+
 // x_p += alpha p_p; r_p -= alpha y_p; z_p = Minv_p r_p; CTA partial of r_p . z_p.  One warp per keyframe.
 template <int N>
 __global__ void __launch_bounds__(kCtaThreads)
@@ -1584,7 +1601,7 @@ pcg_init_kernel(int P, const double* __restrict__ rhs, const double* __restrict_
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __restrict__ kdot, double* __restrict__ scal,
                     int* __restrict__ done, const double* __restrict__ rc, const double* __restrict__ zc, int nz, double* __restrict__ zK,
-                    double* __restrict__ pK, double lambda) {
+                    double* __restrict__ pK, double lambda, double rz_ref, double tol2) {
     __shared__ double scratch[kReduceThreads];
     __shared__ double so[1];
     block_sum_cols<1>(part, nPart, so, scratch);
@@ -1602,9 +1619,11 @@ pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __
     }
     if (threadIdx.x == 0) {
         if (kdot) t += *kdot;
-        scal[0] = 0.0; scal[1] = 0.0; scal[2] = t; scal[3] = t; scal[4] = 0.0; scal[5] = 0.0; scal[6] = 0.0; scal[7] = 0.0;
+        // rz_ref > 0: warm start, convergence is measured against the preconditioned norm of the first right-hand side
+        const double ref = rz_ref > 0.0 ? rz_ref : t;
+        scal[0] = 0.0; scal[1] = 0.0; scal[2] = t; scal[3] = ref; scal[4] = 0.0; scal[5] = 0.0; scal[6] = 0.0; scal[7] = 0.0;
         scal[8] = lambda;   // read by the kernels of the captured PCG graph
-        *done = (t > 0.0) ? 0 : 1;   // zero right-hand side: nothing to do
+        *done = (t > tol2 * ref && t > 0.0) ? 0 : 1;   // nothing to do (zero rhs, or the warm start already meets the tolerance)
     }
 }
 
