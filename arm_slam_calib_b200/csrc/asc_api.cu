@@ -164,6 +164,8 @@ struct asc_handle {
     double *ybuf = nullptr;      // [y (PN) | yK(6) pad to 8 | rowC(32) | rowB(32)]
     double *partA = nullptr, *partB = nullptr, *partC = nullptr, *partL = nullptr, *partR = nullptr, *errblk = nullptr;
     int nCtaPose = 0, nBlkLm = 0, nErrBlk = 0;
+    int nBlkLmK2 = 0;            // CTAs of landmark_blocks_kernel (kLmPerBlock landmarks each)
+    double* lmerr = nullptr;     // their landmark-prior error partials
     double *scal = nullptr, *status = nullptr;
     int *flags = nullptr;        // [0] pcg done, [1] landmark fail idx, [2] pose fail idx, [3] K fail
     unsigned long long* cheir = nullptr;
@@ -287,8 +289,6 @@ struct Engine {
     static int setup_attrs() {
         static bool done = false;
         if (done) return ASC_OK;
-        CUDA_TRY(cudaFuncSetAttribute(linearize_pose_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<N>::kBytes));
-        CUDA_TRY(cudaFuncSetAttribute(linearize_pose_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LinSmem<N>::kBytes));
         CUDA_TRY(cudaFuncSetAttribute(pose_schur_diag_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PrecSmem<N>::kBytes));
         CUDA_TRY(cudaFuncSetAttribute(cluster_schur_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(cluster_schur_cta_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -307,29 +307,38 @@ struct Engine {
         rc = fk(h, h->q, h->X, true);
         if (rc) return rc;
         prof_start(h, 1);
+        const int nCtaLin = cdiv(h->P, LinCfg<N>::KF);
         if (store_b)
-            linearize_pose_kernel<N, true><<<h->nCtaPose, kCtaThreads, LinSmem<N>::kBytes, h->stream>>>(
+            linearize_pose_kernel<N, true><<<nCtaLin, LinCfg<N>::kThreads, LinCfg<N>::kBytes, h->stream>>>(
                 h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
                 h->J, h->Bpp, h->BpK, h->gr, h->partA, h->b_dbg, h->cheir);
         else
-            linearize_pose_kernel<N, false><<<h->nCtaPose, kCtaThreads, LinSmem<N>::kBytes, h->stream>>>(
+            linearize_pose_kernel<N, false><<<nCtaLin, LinCfg<N>::kThreads, LinCfg<N>::kBytes, h->stream>>>(
                 h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
                 h->J, h->Bpp, h->BpK, h->gr, h->partA, nullptr, h->cheir);
         CUDA_TRY(cudaGetLastError());
         DBG_SYNC(h, "fk + linearize_pose");
         prof_stop(h, 1);
         CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+        // extrinsic block B_KK, g_K and the projection error: flat pass, partial rows appended after K1's
+        const int nKk = std::max(1, std::min(cdiv(h->M, kKkThreads), 148 * 4));
+        prof_start(h, 7);
+        proj_kk_kernel<<<nKk, kKkThreads, 0, h->stream>>>(h->cm, h->M, h->p_pose, h->p_lm, h->p_uv, h->cam, h->lm4, h->partA + (size_t)nCtaLin * kPartCols);
+        CUDA_TRY(cudaGetLastError());
+        DBG_SYNC(h, "proj_kk");
+        prof_stop(h, 7);
         prof_start(h, 2);
-        landmark_blocks_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->cm, h->L, h->lm_ptr, h->l_pose, h->l_uv, h->cam, h->lm4, h->lm_prior, h->C,
-                                                                h->gl, h->WK, h->errblk);
+        landmark_blocks_kernel<<<h->nBlkLmK2, 128, 0, h->stream>>>(h->cm, h->L, h->lm_ptr, h->l_pose, h->l_uv, h->cam, h->lm4, h->lm_prior, h->C,
+                                                                  h->gl, h->WK, h->lmerr);
         CUDA_TRY(cudaGetLastError());
         DBG_SYNC(h, "landmark_blocks");
         prof_stop(h, 2);
-        h->launches += 8;
-        const int nR1 = std::min(64, h->nCtaPose), rpb = cdiv(h->nCtaPose, nR1);
-        reduce_rows_kernel<<<cdiv(h->nCtaPose, rpb), 256, 0, h->stream>>>(h->partA, h->nCtaPose, 28, kPartCols, rpb, h->partR);
+        h->launches += 9;
+        const int nRows = nCtaLin + nKk;
+        const int nR1 = std::min(64, nRows), rpb = cdiv(nRows, nR1);
+        reduce_rows_kernel<<<cdiv(nRows, rpb), 256, 0, h->stream>>>(h->partA, nRows, 28, kPartCols, rpb, h->partR);
         CUDA_TRY(cudaGetLastError());
-        linearize_finish_kernel<<<1, 256, 0, h->stream>>>(h->pc, add_priors, h->X, h->partR, cdiv(h->nCtaPose, rpb), h->errblk, h->nBlkLm, h->BKK,
+        linearize_finish_kernel<<<1, 256, 0, h->stream>>>(h->pc, add_priors, h->X, h->partR, cdiv(nRows, rpb), h->lmerr, h->nBlkLmK2, h->BKK,
                                                          h->gr + (size_t)h->P * N, h->err_lin);
         CUDA_TRY(cudaGetLastError());
         if (h->world > 1) {
@@ -1299,6 +1308,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     const size_t PN = (size_t)P * N, Mz = (size_t)M;
     h->nCtaPose = cdiv(P, kWarpsPerCta);
     h->nBlkLm = std::max(1, cdiv(L, 128));
+    h->nBlkLmK2 = std::max(1, cdiv(L, kLmPerBlock));
     int rc = ASC_OK;
     std::vector<ArenaReq> reqs;
 #define ALLOC(ptr, count) reqs.push_back(ArenaReq{(void**)&h->ptr, sizeof(*h->ptr) * std::max<size_t>((size_t)(count), 1)})
@@ -1337,10 +1347,10 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     ALLOC(vx, PN + 8); ALLOC(vr, PN + 8); ALLOC(vz, PN + 8); ALLOC(vp, PN + 8);
     ALLOC(ybuf, PN + 8 + 2 * kPartCols);
     const size_t nStep = (size_t)cdiv(std::max<int64_t>((int64_t)PN + 6, (int64_t)L * 4), 256);
-    ALLOC(partA, std::max<size_t>(std::max<size_t>(h->nCtaPose, nStep), (size_t)h->nC) * kPartCols); ALLOC(partC, (size_t)h->nCtaPose * kPartCols);
+    ALLOC(partA, std::max<size_t>(std::max<size_t>((size_t)P + 1024, nStep), (size_t)h->nC) * kPartCols); ALLOC(partC, (size_t)h->nCtaPose * kPartCols);
     ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
     h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
-    ALLOC(errblk, h->nErrBlk);
+    ALLOC(errblk, h->nErrBlk); ALLOC(lmerr, h->nBlkLmK2);
     ALLOC(scal, 16); ALLOC(status, 64); ALLOC(flags, 8); ALLOC(cheir, 1); ALLOC(SKK, 36); ALLOC(stage3, (size_t)L * 3);
 #undef ALLOC
     rc = commit_arena(h, reqs);
@@ -1620,7 +1630,7 @@ int asc_timer_stop(asc_handle* h, double* elapsed_ms) {
 }
 
 int asc_profile_begin(asc_handle* h, int32_t kernel_id, int32_t max_samples) {
-    if (!h || kernel_id < 0 || kernel_id > 6 || max_samples < 0) return fail(ASC_ERR_INVALID, "bad profile request");
+    if (!h || kernel_id < 0 || kernel_id > 7 || max_samples < 0) return fail(ASC_ERR_INVALID, "bad profile request");
     CUDA_TRY(cudaSetDevice(h->dev));
     while ((int)h->prof_ev.size() < 2 * max_samples) {
         cudaEvent_t e;

@@ -370,82 +370,93 @@ __device__ __forceinline__ double transpose_reduce32(double (&v)[32], int lane) 
 }
 
 // ------------------------------------------------------------------ K1 (+K2b): linearise, pose-major
-// One warp per keyframe.  The keyframe's FK row (camera pose + joint axes/origins) is staged in shared
-// memory once; each lane then evaluates one projection factor per tile: residual, J_q, J_l, J_K,
-// Robust-Cauchy whitening (RobotProjectionFactor.h:96-259 + SURVEY rows A1-A3).  J_q/J_l go to HBM as
-// double2 planes; [J_q | J_K | b] goes to a shared-memory tile from which the warp accumulates the
-// keyframe's blocks B_pp, B_pK, g_p and its share of B_KK, g_K and the error, in a fixed order.
+// One warp per keyframe (W warps for N >= 7).  The warp stages the keyframe's FK row (camera pose + joint axes /
+// origins) in shared memory and walks the keyframe's observations 32 at a time, one projection factor per lane:
+// residual, J_q, J_l, J_K, Robust-Cauchy whitening (RobotProjectionFactor.h:96-259 + SURVEY rows A1-A3).  J_q / J_l go
+// to HBM as double2 planes.  The keyframe's blocks B_pp = sum J_q^T J_q, B_pK = sum J_q^T J_K, g_p = sum J_q^T b are
+// the first NEq entries (rows 0..N-1) of the upper triangle of the Gram matrix of the whitened rows [J_q | J_K | b];
+// every lane accumulates the products of ITS OWN factors for the warp's slice of those entries in registers across
+// all tiles, and one butterfly transpose-reduce per 32 entries at the END of the keyframe (fixed tree) leaves entry
+// l + 32 t on lane l.  The remaining 28 entries (B_KK, g_K, projection error) are global sums, not per-keyframe
+// ones: proj_kk_kernel below accumulates them over a flat grid.
+// History (profiles/README.md): reducing across the warp once per TILE -- shared-memory tiles, 4x4 register blocks,
+// per-tile transpose-reduce -- was bound by LDS wavefronts / shuffle issue at ~1240 warp instructions per tile
+// (31 % of the HBM roofline); splitting the 91 entries over two warps that both evaluate the factor doubled the
+// fp64 work.  Per-lane accumulation needs 2 DFMAs per entry and tile and nothing else.
 template <int N>
-struct LinSmem {
+struct LinCfg {
     static constexpr int D = N + 7;
     static constexpr int NE = D * (D + 1) / 2;          // unique entries of the Gram matrix of [J_q | J_K | b]
-    static constexpr int NBATCH = (NE + 31) / 32;
-    static constexpr int kPerWarpDoubles = 12 + 6 * N + kPartCols;
-    static constexpr size_t kBytes = sizeof(double) * kPerWarpDoubles * kWarpsPerCta;
+    static constexpr int NEq = N * D - N * (N - 1) / 2; // ... of its rows 0..N-1 (the per-keyframe blocks)
+    static constexpr int W = (NEq + 63) / 64;           // warps per keyframe (<= 64 accumulators per lane)
+    static constexpr int EPW = (NEq + W - 1) / W;       // entries per warp
+    static constexpr int NB = (EPW + 31) / 32;          // transpose-reduce batches at the end of a keyframe
+    static constexpr int KF = W <= 2 ? 4 / W : 1;       // keyframes per CTA
+    static constexpr int kWarps = W * KF;
+    static constexpr int kThreads = 32 * kWarps;
+    static constexpr int kPerWarpDoubles = 12 + 6 * N;
+    static constexpr size_t kBytes = sizeof(double) * (kPerWarpDoubles * kWarps + KF);
 };
 
-template <int N, bool STORE_B>
-__global__ void __launch_bounds__(kCtaThreads, 3)
-linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
-                      const double2* __restrict__ p_uv, const double* __restrict__ cam, const double* __restrict__ chain,
-                      const double* __restrict__ lm4, const double* __restrict__ q, const double* __restrict__ enc,
-                      const uint8_t* __restrict__ has_enc, int add_priors, double2* __restrict__ J, double* __restrict__ Bpp,
-                      double* __restrict__ BpK, double* __restrict__ gp, double* __restrict__ cta_part, double2* __restrict__ b_out,
-                      unsigned long long* __restrict__ cheir_count) {
-    constexpr int D = N + 7;
-    constexpr int NE = LinSmem<N>::NE, NBATCH = LinSmem<N>::NBATCH;
+// whitened EncoderFactor residual of joint i (EncoderFactor.h:60-99): (q - enc) / sigma, SO(2)-wrapped if continuous
+__device__ __forceinline__ double encoder_residual(const PriorConst& pc, double qq, double ee, int i) {
+    double d = qq - ee;
+    if ((pc.continuous_mask >> i) & 1) d = atan2(sin(qq - ee), cos(qq - ee));
+    if (pc.use_dead_band) d = fabs(d) < pc.dead_band ? 0.0 : (d < 0 ? d + pc.dead_band : d - pc.dead_band);
+    return d * pc.inv_sigma_enc[i];
+}
+
+template <int N, int ROLE, bool STORE_B>
+__device__ __forceinline__ void linearize_role(const Camera& cm, const PriorConst& pc, int p, int64_t M, const int* __restrict__ pose_ptr,
+                                               const int* __restrict__ p_lm, const double2* __restrict__ p_uv, const double* __restrict__ lm4,
+                                               const double* __restrict__ q, const double* __restrict__ enc, bool with_enc,
+                                               double2* __restrict__ J, double* __restrict__ Bpp, double* __restrict__ BpK, double* __restrict__ gp,
+                                               double2* __restrict__ b_out, unsigned long long* __restrict__ cheir_count,
+                                               const double* s_cam, const double* s_chain, int lane) {
+    typedef LinCfg<N> Cf;
+    constexpr int D = Cf::D, NEq = Cf::NEq, E0 = ROLE * Cf::EPW, E1 = (E0 + Cf::EPW < NEq) ? E0 + Cf::EPW : NEq, CNT = E1 - E0;
+    constexpr bool kStore = ROLE == Cf::W - 1;           // this role writes the Jacobian planes
     constexpr TriTable<D> tri = TriTable<D>();
-    extern __shared__ double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* sw_ = smem + (size_t)warp * LinSmem<N>::kPerWarpDoubles;
-    double* s_cam = sw_;                 // 12
-    double* s_chain = sw_ + 12;          // 6N
-    double* s_part = s_chain + 6 * N;    // kPartCols
-    const int p = blockIdx.x * kWarpsPerCta + warp;
-    if (lane < kPartCols) s_part[lane] = 0.0;
-    if (p < P) {
-        for (int i = lane; i < 12; i += 32) s_cam[i] = cam[(size_t)p * 12 + i];
-        for (int i = lane; i < 6 * N; i += 32) s_chain[i] = chain[(size_t)p * 6 * N + i];
-        __syncwarp();
-        double acc[NBATCH];   // lane l: warp totals of Gram entries l, l+32, ...
+    double acc[CNT > 0 ? CNT : 1];
 #pragma unroll
-        for (int t = 0; t < NBATCH; ++t) acc[t] = 0.0;
-        unsigned ncheir = 0;
-        const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
-        // software pipeline: the landmark gather of tile t+1 (index -> position, two dependent loads) is issued before
-        // the arithmetic of tile t; with ~6 tiles per keyframe and few resident warps the kernel was latency-bound
-        const int klast = max(k1 - 1, k0);
-        int j_nxt = (k1 > k0) ? __ldg(p_lm + min(k0 + lane, klast)) : 0;
-        double2 z_nxt = (k1 > k0) ? ldg2(p_uv + min(k0 + lane, klast)) : make_double2(0.0, 0.0);
-        double2 l01_nxt = (k1 > k0) ? ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j_nxt)) : make_double2(0.0, 0.0);
-        double lz_nxt = (k1 > k0) ? __ldg(lm4 + 4 * (size_t)j_nxt + 2) : 0.0;
-        int j_nxt2 = (k1 > k0) ? __ldg(p_lm + min(k0 + 32 + lane, klast)) : 0;
-        for (int base = k0; base < k1; base += 32) {
-            const int k = base + lane;
-            const double2 z = z_nxt, l01 = l01_nxt;
-            const double lz = lz_nxt;
-            {   // prefetch tile t+1 (clamped indices keep the loads in range; values of inactive lanes are not used)
-                z_nxt = ldg2(p_uv + min(k + 32, klast));
-                l01_nxt = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j_nxt2));
-                lz_nxt = __ldg(lm4 + 4 * (size_t)j_nxt2 + 2);
-                j_nxt2 = __ldg(p_lm + min(k + 64, klast));
+    for (int i = 0; i < CNT; ++i) acc[i] = 0.0;
+    unsigned ncheir = 0;
+    const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+    // software pipeline: the landmark gather of tile t+1 (index -> position, two dependent loads) is issued before the
+    // arithmetic of tile t
+    const int klast = max(k1 - 1, k0);
+    const bool any = k1 > k0;
+    int j_nxt = any ? __ldg(p_lm + min(k0 + lane, klast)) : 0;
+    double2 z_nxt = any ? ldg2(p_uv + min(k0 + lane, klast)) : make_double2(0.0, 0.0);
+    double2 l01_nxt = any ? ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j_nxt)) : make_double2(0.0, 0.0);
+    double lz_nxt = any ? __ldg(lm4 + 4 * (size_t)j_nxt + 2) : 0.0;
+    int j_nxt2 = any ? __ldg(p_lm + min(k0 + 32 + lane, klast)) : 0;
+    for (int base = k0; base < k1; base += 32) {
+        const int k = base + lane;
+        const double2 z = z_nxt, l01 = l01_nxt;
+        const double lz = lz_nxt;
+        {   // prefetch tile t+1 (clamped indices keep the loads in range; values of inactive lanes are not used)
+            z_nxt = ldg2(p_uv + min(k + 32, klast));
+            l01_nxt = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j_nxt2));
+            lz_nxt = __ldg(lm4 + 4 * (size_t)j_nxt2 + 2);
+            j_nxt2 = __ldg(p_lm + min(k + 64, klast));
+        }
+        double r0[D], r1[D];   // the two whitened rows [J_q (N) | J_K (6) | b] of this lane's factor (zero if none)
+#pragma unroll
+        for (int i = 0; i < D; ++i) { r0[i] = 0.0; r1[i] = 0.0; }
+        if (k < k1) {
+            ProjOut o;
+            project_factor<true, true>(cm, s_cam, s_cam + 9, l01.x, l01.y, lz, z.x, z.y, o);
+            if (ROLE == 0) ncheir += o.cheir ? 1u : 0u;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {   // column i of getLinearJacobian: a_i x (l - o_i)   (:240)
+                const double* a = s_chain + 6 * i;
+                const double rx = l01.x - a[3], ry = l01.y - a[4], rz = lz - a[5];
+                const double cx = a[1] * rz - a[2] * ry, cy = a[2] * rx - a[0] * rz, cz = a[0] * ry - a[1] * rx;
+                r0[i] = -(o.jl[0] * cx + o.jl[1] * cy + o.jl[2] * cz);       // J1 = -(Dpoint * Jrobot)   (:245)
+                r1[i] = -(o.jl[3] * cx + o.jl[4] * cy + o.jl[5] * cz);
             }
-            double r0[D], r1[D];   // the two whitened rows [J_q (N) | J_K (6) | b] of this lane's factor (zero if none)
-#pragma unroll
-            for (int i = 0; i < D; ++i) { r0[i] = 0.0; r1[i] = 0.0; }
-            if (k < k1) {
-                ProjOut o;
-                project_factor<true, true>(cm, s_cam, s_cam + 9, l01.x, l01.y, lz, z.x, z.y, o);
-                ncheir += o.cheir ? 1u : 0u;
-#pragma unroll
-                for (int i = 0; i < N; ++i) {   // column i of getLinearJacobian: a_i x (l - o_i)   (:240)
-                    const double* a = s_chain + 6 * i;
-                    const double rx = l01.x - a[3], ry = l01.y - a[4], rz = lz - a[5];
-                    const double cx = a[1] * rz - a[2] * ry, cy = a[2] * rx - a[0] * rz, cz = a[0] * ry - a[1] * rx;
-                    r0[i] = -(o.jl[0] * cx + o.jl[1] * cy + o.jl[2] * cz);       // J1 = -(Dpoint * Jrobot)   (:245)
-                    r1[i] = -(o.jl[3] * cx + o.jl[4] * cy + o.jl[5] * cz);
-                }
-                // packed planes [jq row0 | jq row1 | jl row0 | jl row1]
+            if (kStore) {   // packed planes [jq row0 | jq row1 | jl row0 | jl row1]
                 double flat[2 * N + 6];
 #pragma unroll
                 for (int i = 0; i < N; ++i) { flat[i] = r0[i]; flat[N + i] = r1[i]; }
@@ -454,69 +465,160 @@ linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __r
 #pragma unroll
                 for (int i = 0; i < N + 3; ++i) __stcs(J + (size_t)i * M + k, make_double2(flat[2 * i], flat[2 * i + 1]));
                 if (STORE_B) b_out[k] = make_double2(o.b0, o.b1);
-#pragma unroll
-                for (int i = 0; i < 6; ++i) { r0[N + i] = o.jk[i]; r1[N + i] = o.jk[6 + i]; }
-                r0[N + 6] = o.b0; r1[N + 6] = o.b1;
             }
 #pragma unroll
-            for (int t = 0; t < NBATCH; ++t) {
-                double v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int e = 32 * t + i;   // compile-time after unrolling: the table lookups fold to register names
-                    v[i] = e < NE ? fma(r0[tri.row[e]], r0[tri.col[e]], r1[tri.row[e]] * r1[tri.col[e]]) : 0.0;
-                }
-                acc[t] += transpose_reduce32(v, lane);
-            }
+            for (int i = 0; i < 6; ++i) { r0[N + i] = o.jk[i]; r1[N + i] = o.jk[6 + i]; }
+            r0[N + 6] = o.b0; r1[N + 6] = o.b1;
         }
-        // scatter: lane l owns entries l + 32 t
-        {
-            double* B = Bpp + (size_t)p * N * N;
-            double* BK = BpK + (size_t)p * N * 6;
-            double* g = gp + (size_t)p * N;
-            const bool with_enc = add_priors && (has_enc == nullptr || has_enc[p]);
 #pragma unroll
-            for (int t = 0; t < NBATCH; ++t) {
-                const int e = 32 * t + lane;
-                if (e >= NE) continue;
-                const int lo = tri_row<D>(e), hi = tri_col<D>(e);
-                double v = acc[t];
-                if (hi < N) {
-                    if (lo == hi && with_enc) v += pc.inv_sigma_enc[lo] * pc.inv_sigma_enc[lo];
-                    B[lo * N + hi] = v; B[hi * N + lo] = v;
-                } else if (lo < N && hi < N + 6) BK[lo * 6 + (hi - N)] = v;
-                else if (lo < N) g[lo] = v;                 // hi == N+6: J_q^T b   (encoder part added below)
-                else if (hi < N + 6) { const int a = lo - N, bb = hi - N; s_part[a * 6 - a * (a - 1) / 2 + (bb - a)] = v; }
-                else if (lo < N + 6) s_part[21 + lo - N] = v;
-                else s_part[27] = 0.5 * v;
-            }
+        for (int i = 0; i < CNT; ++i) {   // indices are compile-time after unrolling: the table lookups fold to register names
+            const int e = E0 + i;
+            acc[i] = fma(r0[tri.row[e]], r0[tri.col[e]], fma(r1[tri.row[e]], r1[tri.col[e]], acc[i]));
         }
-        __syncwarp();
-        // EncoderFactor (EncoderFactor.h:60-99): residual q - enc (SO(2)-wrapped if continuous), J = I
-        if (add_priors && (has_enc == nullptr || has_enc[p])) {
-            double e2 = 0.0;
-            if (lane < N) {
-                const double qq = q[(size_t)p * N + lane], ee = enc[(size_t)p * N + lane];
-                double d = qq - ee;
-                if ((pc.continuous_mask >> lane) & 1) d = atan2(sin(qq - ee), cos(qq - ee));
-                if (pc.use_dead_band) d = fabs(d) < pc.dead_band ? 0.0 : (d < 0 ? d + pc.dead_band : d - pc.dead_band);
-                const double is = pc.inv_sigma_enc[lane], wr = d * is;
-                gp[(size_t)p * N + lane] += -wr * is;
-                e2 = 0.5 * wr * wr;
-            }
-            e2 = warp_sum(e2);
-            if (lane == 0) s_part[27] += e2;
+    }
+    // warp totals: lane l ends up with entries E0 + l + 32 t
+    double tot[Cf::NB];
+#pragma unroll
+    for (int t = 0; t < Cf::NB; ++t) {
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (32 * t + i < CNT) ? acc[(32 * t + i < CNT) ? 32 * t + i : 0] : 0.0;
+        tot[t] = transpose_reduce32(v, lane);
+    }
+    double* B = Bpp + (size_t)p * N * N;
+    double* BK = BpK + (size_t)p * N * 6;
+    double* g = gp + (size_t)p * N;
+#pragma unroll
+    for (int t = 0; t < Cf::NB; ++t) {
+        const int e = E0 + 32 * t + lane;
+        if (32 * t + lane >= CNT) continue;
+        const int lo = tri_row<D>(e), hi = tri_col<D>(e);   // lo < N for every entry of this kernel
+        double v = tot[t];
+        if (hi < N) {
+            if (lo == hi && with_enc) v += pc.inv_sigma_enc[lo] * pc.inv_sigma_enc[lo];
+            B[lo * N + hi] = v; B[hi * N + lo] = v;
+        } else if (hi < N + 6) BK[lo * 6 + (hi - N)] = v;
+        else {                                               // hi == N+6: J_q^T b, plus the encoder factor's -J^T r (J = I)
+            if (with_enc) v -= encoder_residual(pc, q[(size_t)p * N + lo], enc[(size_t)p * N + lo], lo) * pc.inv_sigma_enc[lo];
+            g[lo] = v;
         }
+    }
+    if (ROLE == 0) {
         ncheir = __reduce_add_sync(kFull, ncheir);
         if (lane == 0 && ncheir) atomicAdd(cheir_count, (unsigned long long)ncheir);   // statistics only
+    }
+}
+
+template <int N, int ROLE, bool STORE_B>
+struct LinRoleDispatch {
+    template <typename... A>
+    static __device__ __forceinline__ void run(int role, A&&... a) {
+        if (role == ROLE) linearize_role<N, ROLE, STORE_B>(a...);
+        else if constexpr (ROLE + 1 < LinCfg<N>::W) LinRoleDispatch<N, ROLE + 1, STORE_B>::run(role, a...);
+    }
+};
+
+// cta_part row of this kernel: column 27 = the CTA's encoder-factor error, all other columns zero (the projection part
+// of B_KK / g_K / error comes from proj_kk_kernel, in rows of the same layout)
+template <int N, bool STORE_B>
+__global__ void __launch_bounds__(LinCfg<N>::kThreads, 2)
+linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
+                      const double2* __restrict__ p_uv, const double* __restrict__ cam, const double* __restrict__ chain,
+                      const double* __restrict__ lm4, const double* __restrict__ q, const double* __restrict__ enc,
+                      const uint8_t* __restrict__ has_enc, int add_priors, double2* __restrict__ J, double* __restrict__ Bpp,
+                      double* __restrict__ BpK, double* __restrict__ gp, double* __restrict__ cta_part, double2* __restrict__ b_out,
+                      unsigned long long* __restrict__ cheir_count) {
+    typedef LinCfg<N> Cf;
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kf = warp / Cf::W, role = warp % Cf::W;
+    double* s_cam = smem + (size_t)warp * Cf::kPerWarpDoubles;   // 12
+    double* s_chain = s_cam + 12;                                 // 6N
+    double* s_enc = smem + (size_t)Cf::kWarps * Cf::kPerWarpDoubles;   // [KF] encoder-factor error of each keyframe
+    const int p = blockIdx.x * Cf::KF + kf;
+    if (role == 0 && lane == 0) s_enc[kf] = 0.0;
+    if (p < P) {
+        for (int i = lane; i < 12; i += 32) s_cam[i] = cam[(size_t)p * 12 + i];
+        for (int i = lane; i < 6 * N; i += 32) s_chain[i] = chain[(size_t)p * 6 * N + i];
+        __syncwarp();
+        const bool with_enc = add_priors && (has_enc == nullptr || has_enc[p]);
+        LinRoleDispatch<N, 0, STORE_B>::run(role, cm, pc, p, M, pose_ptr, p_lm, p_uv, lm4, q, enc, with_enc, J, Bpp, BpK, gp, b_out, cheir_count,
+                                             s_cam, s_chain, lane);
+        if (role == 0 && with_enc) {   // EncoderFactor error 0.5 |r / sigma|^2
+            double e2 = 0.0;
+            if (lane < N) { const double wr = encoder_residual(pc, q[(size_t)p * N + lane], enc[(size_t)p * N + lane], lane); e2 = 0.5 * wr * wr; }
+            e2 = warp_sum(e2);
+            if (lane == 0) s_enc[kf] = e2;
+        }
     }
     __syncthreads();
     // fixed-order combine of the CTA's keyframes -> one partial row per CTA
     if (threadIdx.x < kPartCols) {
         double s = 0.0;
+        if (threadIdx.x == 27)
 #pragma unroll
-        for (int w = 0; w < kWarpsPerCta; ++w) s += smem[(size_t)w * LinSmem<N>::kPerWarpDoubles + 12 + 6 * N + threadIdx.x];
+            for (int w = 0; w < Cf::KF; ++w) s += s_enc[w];
         cta_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------ K1b: extrinsic block of the normal equations
+// B_KK = sum J_K^T J_K (21 unique), g_K = sum J_K^T b (6) and the projection error sum 0.5 |b|^2 (1) are sums over
+// ALL projection factors.  Flat grid-stride loop over the pose-major observation list (neighbouring lanes share the
+// camera row, so its gather is an L1 broadcast); every thread keeps the 28 sums of its own factors in registers; one
+// transpose-reduce per warp and a fixed-order combine per CTA at the end.  Row layout = linearize_finish_kernel's:
+// [B_KK upper triangle row-major (21) | g_K (6) | error (1) | 0 ...].
+constexpr int kKkThreads = 256;
+__global__ void __launch_bounds__(kKkThreads)
+proj_kk_kernel(Camera cm, int64_t M, const int* __restrict__ p_pose, const int* __restrict__ p_lm, const double2* __restrict__ p_uv,
+               const double* __restrict__ cam, const double* __restrict__ lm4, double* __restrict__ blk_part) {
+    constexpr TriTable<7> tri = TriTable<7>();
+    double v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * kKkThreads;
+    for (int64_t k = (int64_t)blockIdx.x * kKkThreads + threadIdx.x; k < M; k += stride) {
+        const int p = __ldg(p_pose + k), j = __ldg(p_lm + k);
+        const double2 z = ldg2(p_uv + k);
+        double R[12];
+        const double2* cp = reinterpret_cast<const double2*>(cam + (size_t)p * 12);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { const double2 t = ldg2(cp + i); R[2 * i] = t.x; R[2 * i + 1] = t.y; }
+        const double2 l01 = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j));
+        const double lz = __ldg(lm4 + 4 * (size_t)j + 2);
+        ProjOut o;
+        project_factor<true, true>(cm, R, R + 9, l01.x, l01.y, lz, z.x, z.y, o);
+        double r0[7], r1[7];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { r0[i] = o.jk[i]; r1[i] = o.jk[6 + i]; }
+        r0[6] = o.b0; r1[6] = o.b1;
+#pragma unroll
+        for (int e = 0; e < 28; ++e) v[e] = fma(r0[tri.row[e]], r0[tri.col[e]], fma(r1[tri.row[e]], r1[tri.col[e]], v[e]));
+    }
+    // TriTable<7> order: row a < 6 holds (a, a..5) then (a, 6); remap to [B_KK (21) | g_K (6) | err] while reducing
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = 0.0;
+    {
+        int nk = 0;
+#pragma unroll
+        for (int e = 0; e < 28; ++e) {
+            const int a = tri.row[e], b = tri.col[e];
+            if (b < 6) { w[nk] = v[e]; ++nk; }
+            else if (a < 6) w[21 + a] = v[e];
+            else w[27] = 0.5 * v[e];
+        }
+    }
+    const double tot = transpose_reduce32(w, lane);   // lane l: warp total of column l
+    __shared__ double s[kKkThreads / 32][32];
+    s[warp][lane] = tot;
+    __syncthreads();
+    if (threadIdx.x < kPartCols) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < kKkThreads / 32; ++i) t += s[i][threadIdx.x];
+        blk_part[(size_t)blockIdx.x * kPartCols + threadIdx.x] = t;
     }
 }
 
@@ -542,22 +644,42 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------ K2a: landmark blocks (landmark-major)
-// One thread per landmark: C_j = sum J_l^T J_l + prior, g_j = sum J_l^T b + prior, W_Kj = sum J_K^T J_l.
-// The camera-side Jacobians are recomputed here from the [P][12] camera table (L2-resident) so that
-// nothing per-observation has to be stored or permuted for this pass.
+// C_j = sum J_l^T J_l + prior, g_j = sum J_l^T b + prior, W_Kj = sum J_K^T J_l.
+// EIGHT lanes per landmark (four landmarks per warp): lane s takes observations s, s+8, ... of the landmark's
+// landmark-major segment (coalesced 128-byte reads of l_uv / l_pose), accumulates the 27 block entries of its own
+// observations in registers, and a three-step fold over the 8 lanes (fixed tree, 28 shuffles) leaves entries
+// 4s..4s+3 on lane s, which writes them.  The camera-side Jacobians are recomputed here from the [P][12] camera
+// table (L2-resident) so that nothing per-observation has to be stored or permuted for this pass.
+// (The first version ran one thread per landmark: 22 dependent gather round trips per thread, 7 % of the HBM roofline.)
+constexpr int kLmLanes = 8;
+constexpr int kLmPerBlock = 128 / kLmLanes;
+
+template <int W, int LANEBIT>
+__device__ __forceinline__ void fold_step(double (&v)[32], int lane) {
+    const bool upper = (lane & LANEBIT) != 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double lo = v[i], hi = v[i + W];
+        const double send = upper ? lo : hi, keep = upper ? hi : lo;
+        v[i] = keep + __shfl_xor_sync(kFull, send, LANEBIT);
+    }
+}
+
 __global__ void __launch_bounds__(128)
 landmark_blocks_kernel(Camera cm, int L, const int* __restrict__ lm_ptr, const int* __restrict__ l_pose, const double2* __restrict__ l_uv,
                        const double* __restrict__ cam, const double* __restrict__ lm4, const double* __restrict__ lm_prior,
                        double* __restrict__ C, double* __restrict__ gl, double* __restrict__ WK, double* __restrict__ blk_err) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    double err = 0.0;
-    if (j < L) {
-        const double lx = lm4[4 * (size_t)j], ly = lm4[4 * (size_t)j + 1], lz = lm4[4 * (size_t)j + 2];
-        double c[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, wk[18];
+    const int j = blockIdx.x * kLmPerBlock + (threadIdx.x >> 3);
+    const int sub = threadIdx.x & 7, lane = threadIdx.x & 31;
+    double v[32];   // [c (6) | g (3) | wk (18) | pad]
 #pragma unroll
-        for (int i = 0; i < 18; ++i) wk[i] = 0.0;
+    for (int i = 0; i < 32; ++i) v[i] = 0.0;
+    double lx = 0.0, ly = 0.0, lz = 0.0;
+    if (j < L) {
+        const double2 l01 = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j));
+        lx = l01.x; ly = l01.y; lz = __ldg(lm4 + 4 * (size_t)j + 2);
         const int k0 = lm_ptr[j], k1 = lm_ptr[j + 1];
-        for (int k = k0; k < k1; ++k) {
+        for (int k = k0 + sub; k < k1; k += kLmLanes) {
             const int p = __ldg(l_pose + k);
             const double2 z = ldg2(l_uv + k);
             double R[12];
@@ -566,30 +688,38 @@ landmark_blocks_kernel(Camera cm, int L, const int* __restrict__ lm_ptr, const i
             for (int i = 0; i < 6; ++i) { const double2 t = ldg2(cp + i); R[2 * i] = t.x; R[2 * i + 1] = t.y; }
             ProjOut o;
             project_factor<true, true>(cm, R, R + 9, lx, ly, lz, z.x, z.y, o);
-            c[0] += o.jl[0] * o.jl[0] + o.jl[3] * o.jl[3]; c[1] += o.jl[0] * o.jl[1] + o.jl[3] * o.jl[4];
-            c[2] += o.jl[0] * o.jl[2] + o.jl[3] * o.jl[5]; c[3] += o.jl[1] * o.jl[1] + o.jl[4] * o.jl[4];
-            c[4] += o.jl[1] * o.jl[2] + o.jl[4] * o.jl[5]; c[5] += o.jl[2] * o.jl[2] + o.jl[5] * o.jl[5];
+            v[0] += o.jl[0] * o.jl[0] + o.jl[3] * o.jl[3]; v[1] += o.jl[0] * o.jl[1] + o.jl[3] * o.jl[4];
+            v[2] += o.jl[0] * o.jl[2] + o.jl[3] * o.jl[5]; v[3] += o.jl[1] * o.jl[1] + o.jl[4] * o.jl[4];
+            v[4] += o.jl[1] * o.jl[2] + o.jl[4] * o.jl[5]; v[5] += o.jl[2] * o.jl[2] + o.jl[5] * o.jl[5];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) g[a] += o.jl[a] * o.b0 + o.jl[3 + a] * o.b1;
+            for (int a = 0; a < 3; ++a) v[6 + a] += o.jl[a] * o.b0 + o.jl[3 + a] * o.b1;
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int a = 0; a < 3; ++a) wk[3 * r + a] += o.jk[r] * o.jl[a] + o.jk[6 + r] * o.jl[3 + a];
+                for (int a = 0; a < 3; ++a) v[9 + 3 * r + a] += o.jk[r] * o.jl[a] + o.jk[6 + r] * o.jl[3 + a];
         }
+    }
+    fold_step<16, 4>(v, lane); fold_step<8, 2>(v, lane); fold_step<4, 1>(v, lane);   // lane sub now holds entries 4 sub .. 4 sub + 3
+    double err = 0.0;
+    if (j < L) {
         // PriorFactor<Point3> with Robust(Cauchy k, Diagonal sigma_lm)  (ArmSlamCalib.cpp:705, :1648-1651)
         const double r0 = (lx - lm_prior[3 * (size_t)j]) * cm.inv_sigma_lm, r1 = (ly - lm_prior[3 * (size_t)j + 1]) * cm.inv_sigma_lm,
                      r2 = (lz - lm_prior[3 * (size_t)j + 2]) * cm.inv_sigma_lm;
         const double n2 = r0 * r0 + r1 * r1 + r2 * r2, w = cm.k2 / (cm.k2 + n2);
         const double d = w * cm.inv_sigma_lm * cm.inv_sigma_lm;
-        c[0] += d; c[3] += d; c[5] += d;
-        g[0] -= w * r0 * cm.inv_sigma_lm; g[1] -= w * r1 * cm.inv_sigma_lm; g[2] -= w * r2 * cm.inv_sigma_lm;
-        err = 0.5 * w * n2;
+        if (sub == 0) err = 0.5 * w * n2;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) C[6 * (size_t)j + i] = c[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) gl[3 * (size_t)j + i] = g[i];
-#pragma unroll
-        for (int i = 0; i < 18; ++i) WK[18 * (size_t)j + i] = wk[i];
+        for (int i = 0; i < 4; ++i) {
+            const int e = 4 * sub + i;
+            double t = v[i];
+            if (e == 0 || e == 3 || e == 5) t += d;
+            if (e == 6) t -= w * r0 * cm.inv_sigma_lm;
+            if (e == 7) t -= w * r1 * cm.inv_sigma_lm;
+            if (e == 8) t -= w * r2 * cm.inv_sigma_lm;
+            if (e < 6) C[6 * (size_t)j + e] = t;
+            else if (e < 9) gl[3 * (size_t)j + (e - 6)] = t;
+            else if (e < 27) WK[18 * (size_t)j + (e - 9)] = t;
+        }
     }
     // block partial of the prior error (fixed tree)
     __shared__ double s[4];

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 KERNEL_NAMES = {1: "linearize_pose (K1+K2b)", 2: "landmark_blocks (K2a)", 3: "schur_pass_a (K3)", 4: "schur_pass_b (K3)",
-                5: "schur_pass_c (K3)", 6: "error_proj (K1e)"}
+                5: "schur_pass_c (K3)", 6: "error_proj (K1e)", 7: "proj_kk (K1b)"}
 
 
 def hbm_peak():
@@ -46,7 +46,7 @@ def algorithmic_bytes(kid, N, P, L, M):
         return M * (32 + 4) + L * 8 * (18 + 6) + L * 32
     if kid == 5:   # planes + landmark index in; u table in; B_pp, B_pK, x in, y out
         return M * (planes + 4) + L * 32 + P * 8 * (N * N + 6 * N + 2 * N)
-    if kid == 6:   # uv + 2 indices in; camera rows + landmark table in
+    if kid in (6, 7):   # uv + 2 indices in; camera rows + landmark table in
         return M * (16 + 8) + P * 96 + L * 32
     return 0
 
@@ -55,15 +55,18 @@ LM_ITERATIONS_PER_STEP = 3   # the bounded sample both arms run: first 3 LM iter
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The sampler is started before
+    the warm-up steps (nvidia-smi needs ~1 s to deliver its first row) and only rows that arrive inside the timed
+    window are kept; when the window is too short to catch two rows, the warm-up rows (same workload) are used and the
+    JSON says so."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, None
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -71,15 +74,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first_row(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        t_end = time.perf_counter()
+        time.sleep(0.06)   # let the row that covers the end of the window arrive
         self.proc.terminate()
+        rows = [r for t, r in self.rows if self.t_mark is None or self.t_mark <= t <= t_end + 0.06]
+        window = "timed region"
+        if len(rows) < 2:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than two sampling periods)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -88,7 +105,8 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def make_workload(n_gpus):
@@ -206,11 +224,13 @@ def main():
         opt.optimize(asc.ASC_BATCH_LM)
         return opt.iterations()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(args.warmup):
         step()
-    clocks = ClockSampler(local_rank)
+    clocks.wait_first_row()
     barrier()
-    clocks.start()
+    clocks.mark()
     launches0 = opt.launch_count()
     opt.profile_begin(3, 128)   # first 128 launches of the dominant kernel are event-bracketed; the rest of the region runs as CUDA graphs
     opt.timer_start()
@@ -264,9 +284,9 @@ def main():
     peak, peak_src = hbm_peak()
     kernels = {}
     opt.set_values(pb.q0, pb.l0, pb.x0)
-    for kid in (1, 2, 6, 4, 5):
+    for kid in (1, 7, 2, 6, 4, 5):
         opt.profile_begin(kid, 64)
-        if kid in (1, 2):
+        if kid in (1, 2, 7):
             for _ in range(8):
                 opt.linearize()
         elif kid == 6:
