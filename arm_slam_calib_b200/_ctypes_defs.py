@@ -35,6 +35,7 @@ class AscParams(C.Structure):
         ("pcg_cluster_covis", C.c_double),
         ("pcg_coarse_max_dim", C.c_int32),
         ("pcg_coarse_fp32", C.c_int32),
+        ("pcg_coarse_agg", C.c_int32),
     ]
 
 

@@ -154,6 +154,7 @@ struct asc_handle {
     uint8_t* has_enc = nullptr;
     double *q = nullptr, *lm4 = nullptr, *X = nullptr, *q_try = nullptr, *lm4_try = nullptr, *X_try = nullptr;
     double *cam = nullptr, *chain = nullptr;
+    double *lml = nullptr;       // landmark positions at the linearisation point (stable pointer: lm4 / lm4_try swap on accept)
     double *poseblk = nullptr;   // [Bpp | BpK | BKK(36) | gp | gK(6) | err | pad]   (one all-reduce)
     double *Bpp = nullptr, *BpK = nullptr, *BKK = nullptr, *gr = nullptr, *err_lin = nullptr;
     double *C = nullptr, *gl = nullptr, *WK = nullptr, *Cinv = nullptr, *cg4 = nullptr, *u4 = nullptr, *v4 = nullptr, *dl4 = nullptr, *gl4 = nullptr;
@@ -186,6 +187,9 @@ struct asc_handle {
     // coarse level (two-level additive preconditioner)
     bool use_coarse = false;
     int nz = 0, nInc = 0, nDest = 0;
+    int nA = 0, aggS = 1;           // coarse aggregates: aggS consecutive clusters each
+    int *agg_pose_ptr = nullptr, *agg_inc_ptr = nullptr, *pose_agg = nullptr;
+    double* rca = nullptr;          // aggregated restriction (length nz)
     int *inc_lo = nullptr, *inc_hi = nullptr, *inc_lm = nullptr, *dest_ptr = nullptr, *dest_ca = nullptr, *dest_cb = nullptr;
     int *pair_a = nullptr, *pair_b = nullptr, *cl_inc_ptr = nullptr, *cl_inc = nullptr;
     double *Vinc = nullptr, *Tinc = nullptr, *E = nullptr, *rc = nullptr, *zc = nullptr, *yc = nullptr, *SKK = nullptr, *work = nullptr;
@@ -348,6 +352,7 @@ struct Engine {
         }
         pad3to4_kernel<<<cdiv((int64_t)h->L * 4, 256), 256, 0, h->stream>>>(h->L, h->gl, h->gl4);
         CUDA_TRY(cudaGetLastError());
+        if (h->L) CUDA_TRY(cudaMemcpyAsync(h->lml, h->lm4, sizeof(double) * 4 * h->L, cudaMemcpyDeviceToDevice, h->stream));
         if (h->use_clusters && h->M) {
             obs_w_kernel<N><<<cdiv(h->M, 256), 256, 0, h->stream>>>(h->M, h->J, h->Wm);
             CUDA_TRY(cudaGetLastError());
@@ -426,8 +431,8 @@ struct Engine {
                 coarse_blocks_kernel<N><<<cdiv(std::max(h->nDest, 1), 4), 128, 0, h->stream>>>(h->nDest, h->dest_ptr, h->dest_ca, h->dest_cb, h->pair_a,
                                                                                            h->pair_b, h->Vinc, h->Tinc, h->E, nz);
                 DBG_SYNC(h, "coarse_blocks");
-                if (h->rank == 0) coarse_diag_kernel<<<cdiv((int64_t)h->nC * N * N, 256), 256, 0, h->stream>>>(h->nC, N, lambda, h->cl_ptr, h->Bpp, h->E, nz);
-                coarse_k_kernel<<<cdiv(std::max<int64_t>((int64_t)h->nC * N * 6, 36), 256), 256, 0, h->stream>>>(h->nC, N, h->rank == 0 ? 1 : 0, h->cl_ptr, h->cl_inc_ptr,
+                if (h->rank == 0) coarse_diag_kernel<<<cdiv((int64_t)h->nA * N * N, 256), 256, 0, h->stream>>>(h->nA, N, lambda, h->agg_pose_ptr, h->Bpp, h->E, nz);
+                coarse_k_kernel<<<cdiv(std::max<int64_t>((int64_t)h->nA * N * 6, 36), 256), 256, 0, h->stream>>>(h->nA, N, h->rank == 0 ? 1 : 0, h->agg_pose_ptr, h->agg_inc_ptr,
                                                                                                        h->cl_inc, h->inc_lm, h->Tinc, h->WK, h->BpK, h->SKK, h->E, nz);
                 CUDA_TRY(cudaGetLastError());
                 DBG_SYNC(h, "coarse_diag / coarse_k");
@@ -436,7 +441,7 @@ struct Engine {
                     int rc2 = allreduce(h, h->E, (size_t)nz * nz);
                     if (rc2) return rc2;
                     // every rank wrote the same S_KK: rescale the 6x6 corner
-                    scale_block_kernel<<<1, 64, 0, h->stream>>>(h->E, nz, h->nC * N, 1.0 / h->world);
+                    scale_block_kernel<<<1, 64, 0, h->stream>>>(h->E, nz, h->nA * N, 1.0 / h->world);
                 }
                 h->coarse_refit = !refresh;
             }
@@ -496,11 +501,11 @@ struct Engine {
         h->launches += 3;
         prof_start(h, 3);
         if (update_p)
-            schur_pass_a_kernel<N, true><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4,
-                                                                                   h->use_coarse ? h->zc : nullptr, h->pose_cluster, h->p_inv);
+            schur_pass_a_kernel<N, true><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->p_lm, h->J, x, h->vz, h->scal, done, h->v4,
+                                                                                   h->use_coarse ? h->zc : nullptr, h->pose_agg, h->p_inv, h->chain, h->lml);
         else
-            schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, x, h->vz, h->scal, done, h->v4, nullptr,
-                                                                                    nullptr, h->p_inv);
+            schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->p_lm, h->J, x, h->vz, h->scal, done, h->v4, nullptr,
+                                                                                    nullptr, h->p_inv, h->chain, h->lml);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 3);
         prof_start(h, 4);
@@ -510,21 +515,27 @@ struct Engine {
         prof_stop(h, 4);
         prof_start(h, 5);
         schur_pass_c_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, h->rank == 0 ? 1 : 0, h->pose_ptr, h->p_lm, h->J, h->u4, x,
-                                                                         h->Bpp, h->BpK, done, h->ybuf, h->partC, lambda_dev);
+                                                                         h->Bpp, h->BpK, done, h->ybuf, h->partC, lambda_dev, h->chain, h->lml);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 5);
         return ASC_OK;
     }
 
-    // zc = E^-1 rc (coarse correction of the preconditioner)
+    // zc = E^-1 (A rc) (coarse correction of the preconditioner; A sums the per-cluster restriction over each aggregate)
+    static const double* coarse_rhs(const asc_handle* h) { return h->aggS > 1 ? h->rca : h->rc; }
     static int coarse_apply(asc_handle* h, const int* done) {
         h->launches += 1;
+        if (h->aggS > 1) {
+            coarse_aggregate_kernel<<<cdiv(h->nz, 256), 256, 0, h->stream>>>(h->rc, h->rca, h->nz, h->nA, h->nC, N, h->aggS, done);
+            CUDA_TRY(cudaGetLastError());
+            h->launches += 1;
+        }
         if (h->coarse_f32_active) {
-            coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, h->rc, h->zc, h->nz, done, h->scal + 9);
+            coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9);
             CUDA_TRY(cudaGetLastError());
         } else {
             const double one = 1.0, zero = 0.0;
-            if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->rc, 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
+            if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, coarse_rhs(h), 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
                 return fail(ASC_ERR_CUDA, "cublasDsymv failed");
         }
         return ASC_OK;
@@ -561,17 +572,17 @@ struct Engine {
                     const double one = 1.0, zero = 0.0;
                     if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->zc, 1, &zero, h->yc, 1) != CUBLAS_STATUS_SUCCESS)
                         return fail(ASC_ERR_CUDA, "cublasDsymv failed");
-                    coarse_refit_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->rc, h->zc, h->yc, h->nz, h->scal + 9);
+                    coarse_refit_kernel<<<1, kReduceThreads, 0, h->stream>>>(coarse_rhs(h), h->zc, h->yc, h->nz, h->scal + 9);
                     CUDA_TRY(cudaGetLastError());
                     h->launches += 2;
                 }
             }
             pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN, lambda,
-                                                         warm ? h->warm_rz_ref : 0.0, tol2_);
+                                                         warm ? h->warm_rz_ref : 0.0, tol2_, h->nC, h->nA, N, h->aggS);
         } else {
             pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
             CUDA_TRY(cudaGetLastError());
-            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr, lambda, 0.0, tol2_);
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr, lambda, 0.0, tol2_, 0, 0, N, 1);
         }
         CUDA_TRY(cudaGetLastError());
         const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
@@ -587,9 +598,9 @@ struct Engine {
             if (h->world > 1) {
                 double* rowC = h->ybuf + PN + 8;
                 double* rowB = rowC + kPartCols;
-                reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, h->nCtaPose, rowC);
-                reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partB, h->nBlkLm, 6, kPcgCols, h->nBlkLm, rowB);
+                reduce_rows_pair_kernel<<<2, 1024, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, rowC, h->partB, h->nBlkLm, 6, kPcgCols, rowB, h->flags);
                 CUDA_TRY(cudaGetLastError());
+                h->launches += 1;
                 rc = allreduce(h, h->ybuf, PN + 8 + 2 * kPartCols);
                 if (rc) return rc;
                 pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
@@ -607,14 +618,17 @@ struct Engine {
             CUDA_TRY(cudaGetLastError());
             h->launches += 3;
             pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, h->partA, nUpd, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags,
-                                                    h->use_coarse ? h->rc : nullptr, h->zc, h->nz);
+                                                    h->use_coarse ? h->rc : nullptr, h->zc, h->nz, h->nC, h->nA, h->aggS);
             CUDA_TRY(cudaGetLastError());
             return ASC_OK;
         };
         // one chunk = `chunk` iterations; kernels return immediately once the device-side done flag is set
         static const bool no_graph = getenv("ASC_NO_GRAPH") != nullptr;
         const bool profiling = h->prof_id != 0 && 2 * h->prof_n + 1 < (int)h->prof_ev.size();   // event-bracketed launches cannot be captured
-        const bool can_graph = !no_graph && h->world == 1 && !profiling && (!h->use_coarse || h->coarse_f32_active);
+        // multi-GPU: the per-iteration ncclAllReduce is captured with the kernels (NCCL supports stream capture; every rank
+        // captures and launches the same sequence); ASC_NO_GRAPH_MGPU=1 falls back to plain launches
+        static const bool no_graph_mgpu = getenv("ASC_NO_GRAPH_MGPU") != nullptr;
+        const bool can_graph = !no_graph && (h->world == 1 || !no_graph_mgpu) && !profiling && (!h->use_coarse || h->coarse_f32_active);
         const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0);
         for (;;) {
             if (can_graph) {
@@ -653,8 +667,8 @@ struct Engine {
     // delta_l = Cinv (g_l - W^T delta_r) -> dl4
     static int backsub(asc_handle* h) {
         h->launches += 2;
-        schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->J, h->vx, nullptr, nullptr, nullptr, h->v4, nullptr,
-                                                                                nullptr, h->p_inv);
+        schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->p_lm, h->J, h->vx, nullptr, nullptr, nullptr, h->v4, nullptr,
+                                                                                nullptr, h->p_inv, h->chain, h->lml);
         CUDA_TRY(cudaGetLastError());
         schur_pass_b_kernel<true><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
                                                                    h->cg4, h->dl4, nullptr);
@@ -735,7 +749,7 @@ int dispatch_schur_c(asc_handle* h, double lambda, double* x, double* u4_in) {
 #define X(n)                                                                                                                      \
     case n:                                                                                                                       \
         schur_pass_c_kernel<n><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, 0, h->pose_ptr, h->p_lm, h->J, u4_in, x, \
-                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr);    \
+                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr, h->chain, h->lml); \
         break;
     switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
 #undef X
@@ -1024,6 +1038,7 @@ void asc_default_params(asc_params* p) {
     p->pcg_cluster_covis = 0.25;
     p->pcg_coarse_max_dim = 16384;
     p->pcg_coarse_fp32 = 1;
+    p->pcg_coarse_agg = 1;
 }
 
 const char* asc_last_error(void) { return g_last_error.c_str(); }
@@ -1224,7 +1239,9 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         h->scTotal = (size_t)cl_off[h->nC];
         run_lo.resize(M); run_hi.resize(M);
         h->dup_obs = false;
-        h->nz = h->nC * N + 6;
+        h->aggS = std::max(1, pr.pcg_coarse_agg);
+        h->nA = cdiv(h->nC, h->aggS);
+        h->nz = h->nA * N + 6;
         h->use_coarse = pr.pcg_coarse_max_dim > 0 && h->nz <= pr.pcg_coarse_max_dim && h->nC > 1;
         {   // incidences = (landmark, cluster) runs of the landmark-major list; built per thread over landmark ranges, then concatenated
             const int T = std::max(1, std::min(omp_get_max_threads(), 16));
@@ -1250,7 +1267,8 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                     if (h->use_coarse)   // block updates of E = Z^T S Z: lower triangle of cluster pairs, in landmark order (local incidence ids)
                         for (size_t ia = first_inc; ia < Lc.lo.size(); ++ia)
                             for (size_t ib = first_inc; ib < Lc.lo.size(); ++ib)
-                                if (Lc.cl[ia] >= Lc.cl[ib]) Lc.pairs.push_back({(long long)Lc.cl[ia] * h->nC + Lc.cl[ib], (int)ia, (int)ib});
+                                if (Lc.cl[ia] / h->aggS >= Lc.cl[ib] / h->aggS)
+                                    Lc.pairs.push_back({(long long)(Lc.cl[ia] / h->aggS) * h->nA + Lc.cl[ib] / h->aggS, (int)ia, (int)ib});
                 }
             }
             size_t ninc = 0, npair = 0;
@@ -1272,7 +1290,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         lap("runs + incidences + pairs");
         if (h->use_coarse) {
             {   // stable LSD radix sort of the pairs by (cluster a, cluster b): two parallel counting passes
-                const int nCl = h->nC;
+                const int nCl = h->nA;
                 std::vector<PairRec> tmp(pairs.size());
                 std::vector<int> bptr, dst(pairs.size());
                 for (int pass = 0; pass < 2; ++pass) {
@@ -1286,7 +1304,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             for (size_t i = 0; i < pairs.size(); ++i) {
                 if (i == 0 || pairs[i].key != pairs[i - 1].key) {
                     dest_ptr.push_back((int)i);
-                    dest_ca.push_back((int)(pairs[i].key / h->nC)); dest_cb.push_back((int)(pairs[i].key % h->nC));
+                    dest_ca.push_back((int)(pairs[i].key / h->nA)); dest_cb.push_back((int)(pairs[i].key % h->nA));
                 }
                 pair_a[i] = pairs[i].a; pair_b[i] = pairs[i].b;
             }
@@ -1302,7 +1320,16 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             std::vector<int> f(cl_inc_ptr.begin(), cl_inc_ptr.end() - 1);
             for (size_t i = 0; i < inc_cl.size(); ++i) cl_inc[f[inc_cl[i]]++] = (int)i;
         }
-    } else { h->nC = 0; h->nmax = 0; h->scTotal = 0; h->use_coarse = false; }
+    } else { h->nC = 0; h->nmax = 0; h->scTotal = 0; h->use_coarse = false; h->nA = 0; h->aggS = 1; }
+    std::vector<int> agg_pose_ptr, agg_inc_ptr, pose_agg;
+    if (h->use_coarse) {
+        agg_pose_ptr.resize(h->nA + 1); agg_inc_ptr.resize(h->nA + 1); pose_agg.resize(P);
+        for (int a = 0; a <= h->nA; ++a) {
+            const int c = std::min(a * h->aggS, h->nC);
+            agg_pose_ptr[a] = cl_ptr[c]; agg_inc_ptr[a] = cl_inc_ptr[c];
+        }
+        for (int p = 0; p < P; ++p) pose_agg[p] = pose_cluster[p] / h->aggS;
+    }
     lap("pair sort + coarse CSR");
 
     const size_t PN = (size_t)P * N, Mz = (size_t)M;
@@ -1318,7 +1345,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     if (has_enc) { ALLOC(has_enc, P); } else { h->has_enc = nullptr; }
     ALLOC(q, PN); ALLOC(q_try, PN); ALLOC(lm4, (size_t)L * 4); ALLOC(lm4_try, (size_t)L * 4); ALLOC(X, 12); ALLOC(X_try, 12);
     ALLOC(q_save, PN); ALLOC(lm4_save, (size_t)L * 4); ALLOC(X_save, 12);
-    ALLOC(cam, (size_t)P * 12); ALLOC(chain, PN * 6);
+    ALLOC(cam, (size_t)P * 12); ALLOC(chain, PN * 6); ALLOC(lml, (size_t)L * 4);
     ALLOC(J, (size_t)(N + 3) * Mz); ALLOC(b_dbg, 1);
     ALLOC(poseblk, PN * N + PN * 6 + 36 + PN + 6 + 8);
     ALLOC(C, (size_t)L * 6); ALLOC(gl, (size_t)L * 3); ALLOC(WK, (size_t)L * 18); ALLOC(Cinv, (size_t)L * 6);
@@ -1334,7 +1361,8 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         const size_t ni = h->nInc, nd = h->nDest, np = pair_a.size(), nz = h->nz;
         ALLOC(dest_ptr, nd + 1); ALLOC(dest_ca, nd); ALLOC(dest_cb, nd);
         ALLOC(pair_a, np); ALLOC(pair_b, np);
-        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, nz); ALLOC(zc, nz); ALLOC(yc, nz);
+        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, (size_t)h->nC * N + 6); ALLOC(zc, nz); ALLOC(yc, nz); ALLOC(rca, nz);
+        ALLOC(agg_pose_ptr, h->nA + 1); ALLOC(agg_inc_ptr, h->nA + 1); ALLOC(pose_agg, P);
         if (pr.pcg_coarse_fp32) { ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * nz); } else { h->Ef = nullptr; h->Einvf = nullptr; }
         if (!h->solver) {
             if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cusolverDnCreate failed");
@@ -1399,6 +1427,10 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             UP(inc_lo, inc_lo.data(), sizeof(int) * h->nInc); UP(inc_hi, inc_hi.data(), sizeof(int) * h->nInc); UP(inc_lm, inc_lm.data(), sizeof(int) * h->nInc);
             UP(cl_inc, cl_inc.data(), sizeof(int) * h->nInc);
         }
+    }
+    if (h->use_coarse) {
+        UP(agg_pose_ptr, agg_pose_ptr.data(), sizeof(int) * (h->nA + 1)); UP(agg_inc_ptr, agg_inc_ptr.data(), sizeof(int) * (h->nA + 1));
+        UP(pose_agg, pose_agg.data(), sizeof(int) * P);
     }
     if (h->use_coarse && h->nDest) {
         UP(dest_ptr, dest_ptr.data(), sizeof(int) * (h->nDest + 1)); UP(dest_ca, dest_ca.data(), sizeof(int) * h->nDest); UP(dest_cb, dest_cb.data(), sizeof(int) * h->nDest);

@@ -643,6 +643,32 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const double* __restri
     }
 }
 
+// Two independent row reductions in one launch (block 0: A, block 1: B); each sums all rows of its input, fixed order.
+__global__ void __launch_bounds__(1024) reduce_rows_pair_kernel(const double* __restrict__ inA, int RA, int CA, int ldA, double* __restrict__ outA,
+                                                                const double* __restrict__ inB, int RB, int CB, int ldB, double* __restrict__ outB,
+                                                                const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double s[32][kPartCols];
+    const double* in = blockIdx.x == 0 ? inA : inB;
+    const int R = blockIdx.x == 0 ? RA : RB, C = blockIdx.x == 0 ? CA : CB, ld = blockIdx.x == 0 ? ldA : ldB;
+    double* out = blockIdx.x == 0 ? outA : outB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double a0 = 0.0, a1 = 0.0;
+    if (lane < C) {
+        int r = warp;
+        for (; r + 32 < R; r += 64) { a0 += in[(size_t)r * ld + lane]; a1 += in[(size_t)(r + 32) * ld + lane]; }
+        if (r < R) a0 += in[(size_t)r * ld + lane];
+    }
+    s[warp][lane] = a0 + a1;
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) t += s[w][lane];
+        out[lane] = lane < C ? t : 0.0;
+    }
+}
+
 // ------------------------------------------------------------------ K2a: landmark blocks (landmark-major)
 // C_j = sum J_l^T J_l + prior, g_j = sum J_l^T b + prior, W_Kj = sum J_K^T J_l.
 // EIGHT lanes per landmark (four landmarks per warp): lane s takes observations s, s+8, ... of the landmark's
@@ -1272,7 +1298,16 @@ __global__ void __launch_bounds__(256) mirror_lower_f32_kernel(float* __restrict
     }
 }
 
-// zc = Einv(fp32, full symmetric, row-major) * rc, one warp per row, fp64 accumulation
+// Coarse-space index maps.  The restriction Z^T r is produced per CLUSTER (rc, length nC N + 6, by the cluster update
+// kernel); the coarse unknowns live per AGGREGATE of S consecutive clusters (length nz = nA N + 6).
+__device__ __forceinline__ int coarse_index_of(int i, int nC, int nA, int N, int S) {   // cluster-vector index -> coarse index
+    if (i >= nC * N) return nA * N + (i - nC * N);
+    const int c = i / N;
+    return (c / S) * N + (i - c * N);
+}
+
+// zc = Einv(fp32, full symmetric, row-major) * x, one warp per row, fp64 accumulation.  x is the restriction itself
+// (one cluster per aggregate) or its aggregated copy written by coarse_aggregate_kernel.
 __global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
                                                               int n, const int* __restrict__ done, const double* __restrict__ alpha) {
     if (done && *done) return;
@@ -1295,6 +1330,23 @@ __global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __res
     }
     const double t = warp_sum(acc0 + acc1);
     if (lane == 0) y[row] = scale * t;
+}
+
+// aggregated restriction A rc (only launched when an aggregate holds more than one cluster)
+__global__ void __launch_bounds__(256) coarse_aggregate_kernel(const double* __restrict__ rc, double* __restrict__ rca, int n, int nA, int nC, int N, int S,
+                                                                const int* __restrict__ done) {
+    if (done && *done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v;
+    if (i >= nA * N) v = rc[nC * N + (i - nA * N)];
+    else {
+        const int a = i / N, t = i - a * N;
+        const int c1 = min((a + 1) * S, nC);
+        v = 0.0;
+        for (int c = a * S; c < c1; ++c) v += rc[c * N + t];
+    }
+    rca[i] = v;
 }
 
 // A coarse inverse kept from an earlier linearisation is mostly off by a scalar (the robust weights move together while the
@@ -1345,37 +1397,58 @@ __global__ void coarse_k_kernel(int nC, int N, int add_diag, const int* __restri
 }
 
 // ------------------------------------------------------------------ K3: implicit Schur complement  y = S x
+// J_q is never read back in the PCG passes.  Column i of an observation's J_q is -J_l (a_i x (l - o_i))
+// (RobotProjectionFactor.h:240-245), so with the keyframe's joint axes a_i / origins o_i (FK table, `chain`) and the
+// landmark position l at the linearisation point (`lml`):
+//   J_q x_p            = -J_l (A x l - B),            A = sum_i x_i a_i,  B = sum_i x_i (a_i x o_i)      (per keyframe)
+//   sum_m J_q^T e_m    :  component i = -(a_i . U - m_i . T),  U = sum_m l_m x t_m,  T = sum_m t_m,  t_m = J_l^T e_m,  m_i = a_i x o_i
+// Per observation the passes read the three J_l planes (48 B) and one 32-byte landmark sector instead of all N+3
+// planes (16 (N+3) B): at N = 6 the implicit product moves 0.36 GB per PCG iteration instead of 0.74 GB.
+template <int N>
+__device__ __forceinline__ void load_jl(const double2* __restrict__ J, int64_t M, int k, double (&jl)[6]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double2 t = __ldcs(J + (size_t)(N + i) * M + k);   // read once per pass: stream through
+        jl[2 * i] = t.x; jl[2 * i + 1] = t.y;
+    }
+}
+
 // pass A (pose-major): v_k = J_l^T (J_q x_p)            [optionally first p_p <- z_p + beta p_p]
 template <int N, bool UPDATE_P>
 __global__ void __launch_bounds__(kCtaThreads)
-schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const double2* __restrict__ J, double* __restrict__ x,
-                    const double* __restrict__ z, const double* __restrict__ scal, const int* __restrict__ done, double* __restrict__ v4,
-                    const double* __restrict__ zc, const int* __restrict__ pose_cluster, const int* __restrict__ p_inv) {
+schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm, const double2* __restrict__ J,
+                    double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ scal, const int* __restrict__ done,
+                    double* __restrict__ v4, const double* __restrict__ zc, const int* __restrict__ pose_agg, const int* __restrict__ p_inv,
+                    const double* __restrict__ chain, const double* __restrict__ lml) {
     if (done && *done) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * kWarpsPerCta + warp;
     if (p >= P) return;
-    double mine = 0.0;
+    double ab[6] = {0, 0, 0, 0, 0, 0};   // lane i < N: x_i a_i | x_i (a_i x o_i)
     if (lane < N) {
-        mine = x[(size_t)p * N + lane];
+        double mine = x[(size_t)p * N + lane];
         if (UPDATE_P) {   // p <- z + beta p  (z = cluster part + coarse part Z zc); scal[1] = beta
             double zz = z[(size_t)p * N + lane];
-            if (zc) zz += zc[(size_t)pose_cluster[p] * N + lane];
+            if (zc) zz += zc[(size_t)pose_agg[p] * N + lane];
             mine = zz + scal[1] * mine;
             x[(size_t)p * N + lane] = mine;
         }
+        const double* c = chain + (size_t)p * 6 * N + 6 * lane;
+        const double a0 = c[0], a1 = c[1], a2 = c[2], o0 = c[3], o1 = c[4], o2 = c[5];
+        ab[0] = mine * a0; ab[1] = mine * a1; ab[2] = mine * a2;
+        ab[3] = mine * (a1 * o2 - a2 * o1); ab[4] = mine * (a2 * o0 - a0 * o2); ab[5] = mine * (a0 * o1 - a1 * o0);
     }
-    double xp[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) xp[i] = __shfl_sync(kFull, mine, i);
+    for (int i = 0; i < 6; ++i) ab[i] = warp_sum(ab[i]);
     const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
     for (int k = k0 + lane; k < k1; k += 32) {
-        double f[2 * N + 6];
-        load_planes<N>(J, M, k, f);
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) { s0 = fma(f[i], xp[i], s0); s1 = fma(f[N + i], xp[i], s1); }
-        const double* jl = f + 2 * N;
+        double jl[6];
+        load_jl<N>(J, M, k, jl);
+        const int j = __ldg(p_lm + k);
+        const double2 l01 = ldg2(reinterpret_cast<const double2*>(lml + 4 * (size_t)j));
+        const double lz = __ldg(lml + 4 * (size_t)j + 2);
+        const double w0 = ab[1] * lz - ab[2] * l01.y - ab[3], w1 = ab[2] * l01.x - ab[0] * lz - ab[4], w2 = ab[0] * l01.y - ab[1] * l01.x - ab[5];
+        const double s0 = -(jl[0] * w0 + jl[1] * w1 + jl[2] * w2), s1 = -(jl[3] * w0 + jl[4] * w1 + jl[5] * w2);
         // v goes straight to its landmark-major slot (one full 32-byte sector), so pass B reads its segment contiguously
         double2* o = reinterpret_cast<double2*>(v4 + 4 * (size_t)__ldg(p_inv + k));
         o[0] = make_double2(jl[0] * s0 + jl[3] * s1, jl[1] * s0 + jl[4] * s1);
@@ -1431,7 +1504,7 @@ __global__ void __launch_bounds__(kCtaThreads)
 schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
                     const double2* __restrict__ J, const double* __restrict__ u4, const double* __restrict__ x, const double* __restrict__ Bpp,
                     const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part,
-                    const double* __restrict__ lambda_dev) {
+                    const double* __restrict__ lambda_dev, const double* __restrict__ chain, const double* __restrict__ lml) {
     if (done && *done) return;
     const double lambda = lambda_dev ? *lambda_dev : lambda_val;   // device-resident inside the captured PCG graph
     __shared__ double s_part[kWarpsPerCta][8];
@@ -1439,24 +1512,30 @@ schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int
     const int p = blockIdx.x * kWarpsPerCta + warp;
     if (lane < 8) s_part[warp][lane] = 0.0;
     if (p < P) {
-        double acc[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) acc[i] = 0.0;
+        double ut[6] = {0, 0, 0, 0, 0, 0};   // U = sum l x t | T = sum t over this lane's observations
         const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
         for (int k = k0 + lane; k < k1; k += 32) {
-            double f[2 * N + 6];
-            load_planes<N>(J, M, k, f);
+            double jl[6];
+            load_jl<N>(J, M, k, jl);
             const int j = __ldg(p_lm + k);
             const double2 u01 = ldg2(reinterpret_cast<const double2*>(u4 + 4 * (size_t)j));
             const double uz = __ldg(u4 + 4 * (size_t)j + 2);
-            const double* jl = f + 2 * N;
+            const double2 l01 = ldg2(reinterpret_cast<const double2*>(lml + 4 * (size_t)j));
+            const double lz = __ldg(lml + 4 * (size_t)j + 2);
             const double e0 = jl[0] * u01.x + jl[1] * u01.y + jl[2] * uz, e1 = jl[3] * u01.x + jl[4] * u01.y + jl[5] * uz;
-#pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] = fma(f[i], e0, fma(f[N + i], e1, acc[i]));
+            const double t0 = jl[0] * e0 + jl[3] * e1, t1 = jl[1] * e0 + jl[4] * e1, t2 = jl[2] * e0 + jl[5] * e1;
+            ut[0] += l01.y * t2 - lz * t1; ut[1] += lz * t0 - l01.x * t2; ut[2] += l01.x * t1 - l01.y * t0;
+            ut[3] += t0; ut[4] += t1; ut[5] += t2;
         }
-        double mine = 0.0;   // lane c keeps component c
 #pragma unroll
-        for (int i = 0; i < N; ++i) { const double t = warp_sum(acc[i]); if (lane == i) mine = -t; }
+        for (int i = 0; i < 6; ++i) ut[i] = warp_sum(ut[i]);
+        double mine = 0.0;   // lane c keeps component c
+        if (lane < N) {
+            const double* c = chain + (size_t)p * 6 * N + 6 * lane;
+            const double a0 = c[0], a1 = c[1], a2 = c[2], o0 = c[3], o1 = c[4], o2 = c[5];
+            const double m0 = a1 * o2 - a2 * o1, m1 = a2 * o0 - a0 * o2, m2 = a0 * o1 - a1 * o0;
+            mine = (a0 * ut[0] + a1 * ut[1] + a2 * ut[2]) - (m0 * ut[3] + m1 * ut[4] + m2 * ut[5]);
+        }
         double xm = lane < N ? x[(size_t)p * N + lane] : 0.0;
         if (add_diag) {
             double xp[N];
@@ -1649,7 +1728,7 @@ pcg_update_kernel(int P, const double* __restrict__ p, const double* __restrict_
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_end_kernel(int P, int N, const double* __restrict__ part, int nPart, double tol2, int max_iters, double* __restrict__ p,
                double* __restrict__ z, double* __restrict__ scal, int* __restrict__ done, const double* __restrict__ rc,
-               const double* __restrict__ zc, int nz) {
+               const double* __restrict__ zc, int nz, int nC, int nA, int S) {
     if (*done) return;
     __shared__ double scratch[kReduceThreads];
     __shared__ double so[1];
@@ -1659,7 +1738,7 @@ pcg_end_kernel(int P, int N, const double* __restrict__ part, int nPart, double 
     if (rc) {   // r . (Z zc) = (Z^T r) . zc ; and the K rows of z get their coarse part
         __shared__ double prod[kReduceThreads];
         double a = 0.0;
-        for (int i = threadIdx.x; i < nz; i += kReduceThreads) a += rc[i] * zc[i];
+        for (int i = threadIdx.x; i < nC * N + 6; i += kReduceThreads) a += rc[i] * zc[coarse_index_of(i, nC, nA, N, S)];
         prod[threadIdx.x] = a;
         __syncthreads();
         block_sum_cols<1>(prod, kReduceThreads, so, scratch);
@@ -1731,7 +1810,7 @@ pcg_init_kernel(int P, const double* __restrict__ rhs, const double* __restrict_
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __restrict__ kdot, double* __restrict__ scal,
                     int* __restrict__ done, const double* __restrict__ rc, const double* __restrict__ zc, int nz, double* __restrict__ zK,
-                    double* __restrict__ pK, double lambda, double rz_ref, double tol2) {
+                    double* __restrict__ pK, double lambda, double rz_ref, double tol2, int nC, int nA, int N, int S) {
     __shared__ double scratch[kReduceThreads];
     __shared__ double so[1];
     block_sum_cols<1>(part, nPart, so, scratch);
@@ -1739,7 +1818,7 @@ pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __
     if (rc) {
         __shared__ double prod[kReduceThreads];
         double a = 0.0;
-        for (int i = threadIdx.x; i < nz; i += kReduceThreads) a += rc[i] * zc[i];
+        for (int i = threadIdx.x; i < nC * N + 6; i += kReduceThreads) a += rc[i] * zc[coarse_index_of(i, nC, nA, N, S)];
         prod[threadIdx.x] = a;
         __syncthreads();
         block_sum_cols<1>(prod, kReduceThreads, so, scratch);

@@ -40,12 +40,12 @@ def algorithmic_bytes(kid, N, P, L, M):
         return M * (16 + 4 + planes) + L * 32 + P * 8 * (12 + 6 * N + 2 * N + N * N + 6 * N + N)
     if kid == 2:   # uv + pose index in; camera rows, landmarks, priors in; C, g, W_K out
         return M * (16 + 4) + P * 96 + L * (32 + 24) + L * 8 * (6 + 3 + 18)
-    if kid == 3:   # planes in, v (padded 32 B) out; p, z in, p out
-        return M * (planes + 32) + P * N * 8 * 3
+    if kid == 3:   # J_l planes + landmark index + slot index in, v (padded 32 B) out; landmark table, FK rows, p, z in, p out
+        return M * (48 + 4 + 4 + 32) + L * 32 + P * 8 * (6 * N + 3 * N)
     if kid == 4:   # v + permutation in; W_K, Cinv in, u out
         return M * (32 + 4) + L * 8 * (18 + 6) + L * 32
-    if kid == 5:   # planes + landmark index in; u table in; B_pp, B_pK, x in, y out
-        return M * (planes + 4) + L * 32 + P * 8 * (N * N + 6 * N + 2 * N)
+    if kid == 5:   # J_l planes + landmark index in; u table + landmark table in; FK rows, B_pp, B_pK, x in, y out
+        return M * (48 + 4) + L * 64 + P * 8 * (6 * N + N * N + 6 * N + 2 * N)
     if kid in (6, 7):   # uv + 2 indices in; camera rows + landmark table in
         return M * (16 + 8) + P * 96 + L * 32
     return 0
@@ -293,6 +293,8 @@ def main():
             for _ in range(8):
                 opt.graph_error()
         else:
+            opt.linearize()            # fresh linearisation: the solve below starts cold (no warm start, coarse operator rebuilt)
+            opt.profile_begin(kid, 64)
             opt.solve_damped(1e-5)
         n_s, mean_k, min_k = opt.profile_read()
         if n_s:

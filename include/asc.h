@@ -82,6 +82,8 @@ typedef struct asc_params {
                                         nClusters*N+6 is <= this (16384); 0 switches it off */
     int32_t pcg_coarse_fp32;         /* 1 (default): factorise/apply the coarse operator in fp32 (fp64 accumulation in the
                                         product; falls back to fp64 if the fp32 Cholesky fails); 0: fp64 throughout */
+    int32_t pcg_coarse_agg;          /* consecutive clusters per coarse aggregate: the coarse space has one joint-offset vector
+                                        per AGGREGATE, dimension ceil(nClusters/agg)*N+6 (the factorisation costs its cube) */
 } asc_params;
 
 /* One record per outer iterate() of the optimiser */

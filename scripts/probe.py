@@ -15,6 +15,10 @@ prm = configs.params_for(name, asc.default_params)
 prm.max_iterations = maxit
 if len(sys.argv) > 4:
     prm.pcg_rel_tol = float(sys.argv[4])
+if len(sys.argv) > 5:
+    prm.pcg_coarse_agg = int(sys.argv[5])
+if len(sys.argv) > 6:
+    prm.pcg_cluster_max = int(sys.argv[6])
 t = time.time()
 opt = asc.BatchOptimizer(pb, prm)
 print("setup %.2fs" % (time.time() - t), flush=True)
