@@ -54,6 +54,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -67,6 +68,7 @@ int load_nccl() {
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(lib, "ncclAllGather");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
@@ -140,6 +142,12 @@ struct asc_handle {
     // multi-GPU
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+    // peer-memory exchange of the PCG loop (kernels.cuh, PeerComm): one IPC-shared buffer per rank
+    PeerComm pcm{};
+    bool p2p_ok = false;
+    char* xbuf = nullptr;           // this rank's exchange buffer [flags 256 B | slot 0 | slot 1]
+    size_t xbuf_bytes = 0;
+    void* peer_map[kMaxPeers] = {nullptr};   // cudaIpcOpenMemHandle mappings of the peers' buffers
     // failure report
     char fail_kind = 0;
     int64_t fail_index = -1;
@@ -373,7 +381,7 @@ struct Engine {
     // damped landmark inverses, Schur-diagonal preconditioner, reduced right-hand side
     static int prepare(asc_handle* h, double lambda) {
         const int big = 0x7fffffff;
-        int init_flags[8] = {0, big, big, big, 0, 0, 0, 0};
+        int init_flags[16] = {0, big, big, big, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [8]: peer-exchange timeout
         h->launches += 5;
         CUDA_TRY(cudaMemcpyAsync(h->flags, init_flags, sizeof init_flags, cudaMemcpyHostToDevice, h->stream));
         landmark_invert_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->L, lambda, h->C, h->gl, h->WK, h->Cinv, h->cg4, h->partL, h->flags + 1);
@@ -497,7 +505,8 @@ struct Engine {
     }
 
     // one application y = S x written into ybuf; K rows handled by the caller's kernels
-    static int schur_apply_launch(asc_handle* h, double lambda, bool update_p, double* x, const int* done, const double* lambda_dev = nullptr) {
+    static int schur_apply_launch(asc_handle* h, double lambda, bool update_p, double* x, const int* done, const double* lambda_dev = nullptr,
+                                  bool to_slot = false) {
         h->launches += 3;
         prof_start(h, 3);
         if (update_p)
@@ -515,7 +524,8 @@ struct Engine {
         prof_stop(h, 4);
         prof_start(h, 5);
         schur_pass_c_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, h->rank == 0 ? 1 : 0, h->pose_ptr, h->p_lm, h->J, h->u4, x,
-                                                                         h->Bpp, h->BpK, done, h->ybuf, h->partC, lambda_dev, h->chain, h->lml);
+                                                                         h->Bpp, h->BpK, done, h->ybuf, h->partC, lambda_dev, h->chain, h->lml,
+                                                                         to_slot ? h->pcm.ctr : nullptr, to_slot ? h->pcm.x[h->rank] : nullptr, h->pcm.stride);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 5);
         return ASC_OK;
@@ -550,6 +560,8 @@ struct Engine {
         // A rejected LM step is re-solved with a 10x larger lambda on the same linearisation; while lambda is far below the
         // spectrum of S the solution hardly moves, so start from it (GTSAM refactorises from scratch each time).
         const bool warm = h->warm_ok && h->use_clusters && h->world == 1 && h->warm_rz_ref > 0.0;
+        PeerComm single{};   // world = 0: kernels take their single-GPU path
+        single.world = 1;
         if (warm) {
             int rcw = schur_apply_launch(h, lambda, false, h->vx, nullptr, nullptr);   // ybuf = S x0 (keyframe rows)
             if (rcw) return rcw;
@@ -560,7 +572,7 @@ struct Engine {
         if (h->use_clusters) {
             double* rc_ = h->use_coarse ? h->rc : nullptr;
             pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(warm ? 2 : 1, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp, h->scal,
-                                                                  h->flags, h->partA, rc_);
+                                                                  h->flags, h->partA, rc_, single);
             pcg_init_k_kernel<<<1, 32, 0, h->stream>>>((int64_t)PN, h->rhs, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->status + 40,
                                                       rc_ ? rc_ + (size_t)h->nC * N : nullptr, warm ? h->ybuf + PN : nullptr);
             CUDA_TRY(cudaGetLastError());
@@ -589,15 +601,21 @@ struct Engine {
         const int chunk = 8;
         int launched = 0;
         const double* lam_dev = h->scal + 8;
+        const bool p2p = h->world > 1 && h->p2p_ok && h->use_clusters;   // peer-memory exchange instead of ncclAllReduce
         auto one_iteration = [&]() -> int {
-            int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev);
+            int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev, p2p);
             if (rc) return rc;
             const double* pc_ = h->partC;
             const double* pb_ = h->partB;
             int nC = h->nCtaPose, nB = h->nBlkLm;
-            if (h->world > 1) {
-                double* rowC = h->ybuf + PN + 8;
-                double* rowB = rowC + kPartCols;
+            double* rowC = h->ybuf + PN + 8;
+            double* rowB = rowC + kPartCols;
+            if (p2p) {
+                pcg_signal_kernel<<<1, 1024, 0, h->stream>>>(h->pcm, h->partC, h->nCtaPose, h->partB, h->nBlkLm, h->flags);
+                CUDA_TRY(cudaGetLastError());
+                h->launches += 1;
+                pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
+            } else if (h->world > 1) {
                 reduce_rows_pair_kernel<<<2, 1024, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, rowC, h->partB, h->nBlkLm, 6, kPcgCols, rowB, h->flags);
                 CUDA_TRY(cudaGetLastError());
                 h->launches += 1;
@@ -606,11 +624,12 @@ struct Engine {
                 pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
             }
             pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, lam_dev, pc_, nC, pb_, nB, h->BKK, h->MinvK, h->vp, h->vx, h->vr, h->vz,
-                                                    h->ybuf + PN, h->scal, h->flags, h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr);
+                                                    h->ybuf + PN, h->scal, h->flags, h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr,
+                                                    p2p ? h->pcm : single, rowC);
             CUDA_TRY(cudaGetLastError());
             if (h->use_clusters) {
                 pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
-                                                                      h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr);
+                                                                      h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr, p2p ? h->pcm : single);
                 if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags); if (rc3) return rc3; }
             } else {
                 pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
@@ -625,11 +644,11 @@ struct Engine {
         // one chunk = `chunk` iterations; kernels return immediately once the device-side done flag is set
         static const bool no_graph = getenv("ASC_NO_GRAPH") != nullptr;
         const bool profiling = h->prof_id != 0 && 2 * h->prof_n + 1 < (int)h->prof_ev.size();   // event-bracketed launches cannot be captured
-        // multi-GPU: the per-iteration ncclAllReduce is captured with the kernels (NCCL supports stream capture; every rank
-        // captures and launches the same sequence); ASC_NO_GRAPH_MGPU=1 falls back to plain launches
+        // multi-GPU: with the peer-memory exchange the loop holds kernels only and is captured like the single-GPU one (a captured
+        // ncclAllReduce hung on this stack: NCCL 2.28.9, driver 580); ASC_NO_GRAPH_MGPU=1 falls back to plain launches
         static const bool no_graph_mgpu = getenv("ASC_NO_GRAPH_MGPU") != nullptr;
-        const bool can_graph = !no_graph && (h->world == 1 || !no_graph_mgpu) && !profiling && (!h->use_coarse || h->coarse_f32_active);
-        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0);
+        const bool can_graph = !no_graph && (h->world == 1 || (p2p && !no_graph_mgpu)) && !profiling && (!h->use_coarse || h->coarse_f32_active);
+        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0);
         for (;;) {
             if (can_graph) {
                 if (!h->pcg_graph || h->pcg_graph_key != graph_key) {
@@ -654,12 +673,13 @@ struct Engine {
                 for (int c = 0; c < chunk; ++c) { int rc = one_iteration(); if (rc) return rc; }
             }
             launched += chunk;
-            CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->flags, 16 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(cudaMemcpyAsync(h->h_status + 32, h->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(cudaStreamSynchronize(h->stream));
             if (h->h_flags[0] || launched >= h->prm.pcg_max_iters + chunk) break;
         }
         if (iters) *iters = (int)h->h_status[32 + 5];
+        if (p2p && h->h_flags[8] != 0) return fail(ASC_ERR_COMM, "peer-memory exchange timed out waiting for a peer rank");
         if (!warm) h->warm_rz_ref = h->h_status[32 + 3];
         return ASC_OK;
     }
@@ -749,7 +769,7 @@ int dispatch_schur_c(asc_handle* h, double lambda, double* x, double* u4_in) {
 #define X(n)                                                                                                                      \
     case n:                                                                                                                       \
         schur_pass_c_kernel<n><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, 0, h->pose_ptr, h->p_lm, h->J, u4_in, x, \
-                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr, h->chain, h->lml); \
+                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr, h->chain, h->lml, nullptr, nullptr, 0); \
         break;
     switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
 #undef X
@@ -998,6 +1018,64 @@ int dogleg_iterate(asc_handle* h, double* error, double* Delta, asc_iter_log* lg
     return ASC_OK;
 }
 
+// (Re)creates this rank's exchange buffer when it must grow, and maps every peer's buffer through CUDA IPC.  Collective:
+// every rank calls it from asc_set_problem with the same P and N.  Falls back to the NCCL path (p2p_ok = false) on any
+// failure, agreed between the ranks through one all-reduce.
+int setup_peer_exchange(asc_handle* h) {
+    h->p2p_ok = false;
+    if (h->world <= 1 || h->world > kMaxPeers || !g_nccl.AllGather || getenv("ASC_NO_P2P")) return ASC_OK;
+    const size_t PN = (size_t)h->P * h->N;
+    const size_t stride = (PN + 8 + 2 * kPartCols + 31) / 32 * 32;
+    const size_t need = 256 + 2 * stride * sizeof(double);
+    double bad = 0.0;
+    if (!h->xbuf || need > h->xbuf_bytes) {
+        int rc = allreduce(h, h->status, 1);   // barrier: no peer is still reading the buffer that is about to go away
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < h->world; ++r)
+            if (h->peer_map[r]) { cudaIpcCloseMemHandle(h->peer_map[r]); h->peer_map[r] = nullptr; }
+        if (h->xbuf) CUDA_TRY(cudaFree(h->xbuf));
+        h->xbuf = nullptr;
+        h->xbuf_bytes = need + need / 4;
+        CUDA_TRY(cudaMalloc((void**)&h->xbuf, h->xbuf_bytes));
+        CUDA_TRY(cudaMemsetAsync(h->xbuf, 0, h->xbuf_bytes, h->stream));
+        cudaIpcMemHandle_t mine;
+        if (cudaIpcGetMemHandle(&mine, h->xbuf) != cudaSuccess) { cudaGetLastError(); bad = 1.0; std::memset(&mine, 0, sizeof mine); }
+        char* d_handles = nullptr;
+        const size_t hs = sizeof(cudaIpcMemHandle_t);
+        CUDA_TRY(cudaMalloc((void**)&d_handles, hs * h->world));
+        CUDA_TRY(cudaMemcpyAsync(d_handles + hs * h->rank, &mine, hs, cudaMemcpyHostToDevice, h->stream));
+        if (g_nccl.AllGather(d_handles + hs * h->rank, d_handles, hs, ncclChar, h->comm, h->stream) != ncclSuccess) { cudaFree(d_handles); return fail(ASC_ERR_COMM, "ncclAllGather failed"); }
+        std::vector<cudaIpcMemHandle_t> all(h->world);
+        CUDA_TRY(cudaMemcpyAsync(all.data(), d_handles, hs * h->world, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(d_handles);
+        for (int r = 0; r < h->world && bad == 0.0; ++r) {
+            if (r == h->rank) continue;
+            if (cudaIpcOpenMemHandle(&h->peer_map[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); h->peer_map[r] = nullptr; bad = 1.0; }
+        }
+    }
+    // agree on the outcome
+    CUDA_TRY(cudaMemcpyAsync(h->status + 1, &bad, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, h->status + 1, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(&bad, h->status + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (bad != 0.0) return ASC_OK;   // NCCL path
+    for (int r = 0; r < h->world; ++r) {
+        char* base = r == h->rank ? h->xbuf : (char*)h->peer_map[r];
+        h->pcm.peer_flags[r] = (unsigned*)base;
+        h->pcm.x[r] = (double*)(base + 256);
+    }
+    h->pcm.ctr = (unsigned*)h->xbuf + 32;   // second half of the 256-byte header: local sequence counter (peers write entries 0..7 only)
+    h->pcm.fail = h->flags + 8;
+    h->pcm.stride = (long long)stride;
+    h->pcm.row_off = (long long)(PN + 8);
+    h->pcm.rank = h->rank; h->pcm.world = h->world;
+    h->p2p_ok = true;
+    return ASC_OK;
+}
+
 int check_ready(asc_handle* h, bool need_values) {
     if (!h) return fail(ASC_ERR_INVALID, "null handle");
     if (!h->chain_set || !h->cam_set || !h->problem_set) return fail(ASC_ERR_INVALID, "set chain, camera and problem first");
@@ -1062,7 +1140,7 @@ int asc_create(const asc_params* params, asc_handle** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& ev : h->ev) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMallocHost((void**)&h->h_status, 64 * sizeof(double)));
-    CUDA_TRY(cudaMallocHost((void**)&h->h_flags, 8 * sizeof(int)));
+    CUDA_TRY(cudaMallocHost((void**)&h->h_flags, 16 * sizeof(int)));
     h->t_base.resize(12);
     asc::xf_to12(asc::xf_identity(), h->t_base.data());
     *out = h;
@@ -1082,6 +1160,11 @@ int asc_destroy(asc_handle* h) {
     if (!h) return ASC_OK;
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->xbuf) {
+        if (h->world > 1 && h->comm && h->status) { allreduce(h, h->status, 1); cudaStreamSynchronize(h->stream); }   // peers are done with our buffer
+        for (int r = 0; r < kMaxPeers; ++r) if (h->peer_map[r]) cudaIpcCloseMemHandle(h->peer_map[r]);
+        cudaFree(h->xbuf);
+    }
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     if (h->solver) cusolverDnDestroy(h->solver);
@@ -1379,12 +1462,14 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
     h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
     ALLOC(errblk, h->nErrBlk); ALLOC(lmerr, h->nBlkLmK2);
-    ALLOC(scal, 16); ALLOC(status, 64); ALLOC(flags, 8); ALLOC(cheir, 1); ALLOC(SKK, 36); ALLOC(stage3, (size_t)L * 3);
+    ALLOC(scal, 16); ALLOC(status, 64); ALLOC(flags, 16); ALLOC(cheir, 1); ALLOC(SKK, 36); ALLOC(stage3, (size_t)L * 3);
 #undef ALLOC
     rc = commit_arena(h, reqs);
     if (rc) return rc;
     h->Bpp = h->poseblk; h->BpK = h->Bpp + PN * N; h->BKK = h->BpK + PN * 6; h->gr = h->BKK + 36; h->err_lin = h->gr + PN + 6;
     h->Dloc = h->precblk; h->rloc = h->Dloc + h->regionA; h->krow = h->rloc + PN;
+    rc = setup_peer_exchange(h);
+    if (rc) return rc;
     if (h->use_coarse) {   // cuSOLVER workspaces: separate grow-only allocations
         int lw1 = 0, lw2 = 0, lf1 = 0;
         if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw1) != CUSOLVER_STATUS_SUCCESS ||

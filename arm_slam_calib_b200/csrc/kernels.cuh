@@ -50,6 +50,45 @@ struct PriorConst {
     int chart;
 };
 
+// ------------------------------------------------------------------ peer-memory exchange (multi-GPU PCG)
+// One process per GPU; every rank owns one exchange buffer (cudaMalloc + CUDA IPC, mapped by all peers over NVLink):
+//   [ flags: one sequence number per peer (256 B) | slot 0 | slot 1 ],  slot = [ y partial (PN) | pad to PN+8 | rowC (32) | rowB (32) ]
+// Per PCG iteration a rank writes its shard's partial product into slot (seq & 1) of ITS OWN buffer (pass C), publishes
+// seq to every peer's flag array (pcg_signal_kernel) and the consumers (pcg_mid_kernel, pcg_cluster_update_kernel) sum the
+// slots of all ranks with peer loads in rank order -- the same order on every rank, so all ranks hold bitwise identical
+// vectors and stay in lock-step.  No collective library call and no host involvement inside the PCG loop, which is
+// what lets the multi-GPU loop run as one CUDA graph.  Two slots suffice: a rank can only overwrite slot s two
+// iterations later, after every peer has published the iteration in between, i.e. after it finished reading slot s.
+constexpr int kMaxPeers = 8;
+struct PeerComm {
+    double* x[kMaxPeers];            // exchange buffer of every rank (slot 0 base), peer-mapped
+    unsigned* peer_flags[kMaxPeers]; // flag array of every rank
+    unsigned* ctr;                   // local: last sequence number this rank published
+    int* fail;                       // local: set when a wait timed out
+    long long stride;                // doubles per slot
+    long long row_off;               // offset of rowC inside a slot (= PN + 8)
+    int rank, world;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ double ld_peer_f64(const double* p) {   // system-scope load: never served from a stale L1 line
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// sum over ranks (fixed order) of element i of the current slot
+__device__ __forceinline__ double peer_sum(const PeerComm& pc, unsigned seq, long long i) {
+    const long long off = (long long)(seq & 1u) * pc.stride + i;
+    double s = 0.0;
+    for (int r = 0; r < pc.world; ++r) s += ld_peer_f64(pc.x[r] + off);
+    return s;
+}
+
 // ------------------------------------------------------------------ tiny device helpers
 __device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
 
@@ -1138,7 +1177,7 @@ __global__ void __launch_bounds__(128)
 pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const long long* __restrict__ cl_off, const double* __restrict__ Mc,
                           const double* __restrict__ rhs, const double* __restrict__ y, double* __restrict__ x, double* __restrict__ r,
                           double* __restrict__ z, double* __restrict__ p, const double* __restrict__ scal, const int* __restrict__ done,
-                          double* __restrict__ part, double* __restrict__ rc) {
+                          double* __restrict__ part, double* __restrict__ rc, PeerComm pcm) {
     if (!init && *done) return;
     __shared__ double rs[128];
     __shared__ double red[4];
@@ -1150,7 +1189,11 @@ pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const
         const size_t i = base + t;
         if (init == 1) { rm = rhs[i]; x[i] = 0.0; }
         else if (init == 2) { rm = rhs[i] - y[i]; }   // warm start: x holds the previous solution, y = S x
-        else { const double alpha = scal[0]; x[i] += alpha * p[i]; rm = r[i] - alpha * y[i]; }
+        else {   // multi-GPU: y = sum over ranks of the partial products, read from the peers' exchange slots (published before pcg_mid ran)
+            const double alpha = scal[0];
+            const double yi = pcm.world > 1 ? peer_sum(pcm, *pcm.ctr, (long long)i) : y[i];
+            x[i] += alpha * p[i]; rm = r[i] - alpha * yi;
+        }
         r[i] = rm;
     }
     rs[t] = rm;
@@ -1504,8 +1547,10 @@ __global__ void __launch_bounds__(kCtaThreads)
 schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
                     const double2* __restrict__ J, const double* __restrict__ u4, const double* __restrict__ x, const double* __restrict__ Bpp,
                     const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part,
-                    const double* __restrict__ lambda_dev, const double* __restrict__ chain, const double* __restrict__ lml) {
+                    const double* __restrict__ lambda_dev, const double* __restrict__ chain, const double* __restrict__ lml,
+                    const unsigned* __restrict__ xctr, double* __restrict__ xbase, long long xstride) {
     if (done && *done) return;
+    if (xctr) y = xbase + (size_t)((*xctr + 1u) & 1u) * xstride;   // multi-GPU: the next exchange slot of this rank
     const double lambda = lambda_dev ? *lambda_dev : lambda_val;   // device-resident inside the captured PCG graph
     __shared__ double s_part[kWarpsPerCta][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1612,6 +1657,43 @@ __device__ inline double block_reduce_rows(const double* __restrict__ part, int 
     return t;
 }
 
+// Multi-GPU, after pass C: reduce this rank's CTA partials of pass C / pass B into the exchange slot's row area, then
+// publish the new sequence number to every peer (release at system scope: the slot is complete when a peer sees it).
+__global__ void __launch_bounds__(1024)
+pcg_signal_kernel(PeerComm pcm, const double* __restrict__ partC, int nC, const double* __restrict__ partB, int nB, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double s[32][kPartCols];
+    const unsigned seq = *pcm.ctr + 1u;
+    double* rows = pcm.x[pcm.rank] + (size_t)(seq & 1u) * pcm.stride + pcm.row_off;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int which = 0; which < 2; ++which) {
+        const double* in = which == 0 ? partC : partB;
+        const int R = which == 0 ? nC : nB, C = which == 0 ? 7 : 6;
+        double a0 = 0.0, a1 = 0.0;
+        if (lane < C) {
+            int r = warp;
+            for (; r + 32 < R; r += 64) { a0 += in[(size_t)r * kPcgCols + lane]; a1 += in[(size_t)(r + 32) * kPcgCols + lane]; }
+            if (r < R) a0 += in[(size_t)r * kPcgCols + lane];
+        }
+        __syncthreads();
+        s[warp][lane] = a0 + a1;
+        __syncthreads();
+        if (warp == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 32; ++w) t += s[w][lane];
+            rows[which * kPartCols + lane] = lane < C ? t : 0.0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *pcm.ctr = seq;
+        __threadfence_system();
+        for (int r = 0; r < pcm.world; ++r)
+            if (r != pcm.rank) st_release_sys_u32(pcm.peer_flags[r] + pcm.rank, seq);
+    }
+}
+
 // Device-side PCG scalars: scal[0]=alpha, [1]=beta, [2]=rz, [3]=rz0, [4]=pSp, [5]=iterations, [6]=breakdown flag
 // Finish y = S p: gathers the K rows, alpha, and updates the K part of x, r, z.  One block of 256 threads.
 //   partC: CTA partials of pass C [nC][32] (cols 0..5 = sum B_pK^T p_p, col 6 = sum p_p.y_p)
@@ -1622,10 +1704,25 @@ pcg_mid_kernel(int P, int N, double lambda_val, const double* __restrict__ lambd
                const double* __restrict__ partB, int nB,
                const double* __restrict__ BKK, const double* __restrict__ MinvK, double* __restrict__ p, double* __restrict__ x,
                double* __restrict__ r, double* __restrict__ z, double* __restrict__ yK_out, double* __restrict__ scal, int* __restrict__ done,
-               double* __restrict__ rcK) {
+               double* __restrict__ rcK, PeerComm pcm, double* __restrict__ rows_local) {
     if (*done) return;
     const double lambda = lambda_dev ? *lambda_dev : lambda_val;
     __shared__ double scratch[kReduceThreads];
+    if (pcm.world > 1) {
+        // wait until every peer has published this iteration's partial product, then sum the K-row partials of all ranks
+        const unsigned seq = *pcm.ctr;
+        if (threadIdx.x < pcm.world && threadIdx.x != pcm.rank) {
+            const unsigned* f = pcm.peer_flags[pcm.rank] + threadIdx.x;
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_sys_u32(f) - seq) < 0) {
+                if (clock64() - t0 > 8000000000ll) { *pcm.fail = 1; break; }   // ~4 s: a peer died; report instead of hanging
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * kPartCols) rows_local[threadIdx.x] = peer_sum(pcm, seq, pcm.row_off + threadIdx.x);
+        __syncthreads();
+    }
     __shared__ double sc[kPcgCols], sb[kPcgCols];
     __shared__ double sh[16];
     const int lane = threadIdx.x & 31;

@@ -33,6 +33,9 @@ q, l, x = opt.optimize(0)
 torch.cuda.synchronize()
 dt = time.time() - t
 log = [(g.iteration, g.inner_steps, g.pcg_iterations, g.error) for g in opt.log]
+if rank == 0:
+    for g in opt.log:
+        print("  [%d GPUs] it %2d pcg %4d lin %.2f ms solve %.2f ms (%.1f us/pcg-it)" % (world, g.iteration, g.pcg_iterations, g.linearize_ms, g.solve_ms, 1e3 * g.solve_ms / max(g.pcg_iterations, 1)), flush=True)
 print("rank %d: shard L=%d M=%d  e0 %.9g  %d iterations in %.3fs final %.9g" % (rank, sh.n_landmarks, sh.n_obs, e0, len(log), dt, opt.error()), flush=True)
 qs = [torch.zeros_like(torch.from_numpy(q)).cuda() for _ in range(world)]
 dist.all_gather(qs, torch.from_numpy(q).cuda())
@@ -43,6 +46,8 @@ if rank == 0:
     single = asc.BatchOptimizer(pb, p1)
     e1 = single.graph_error()
     t = time.time(); q1, l1, x1 = single.optimize(0); torch.cuda.synchronize(); dt1 = time.time() - t
+    for g in single.log:
+        print("  [1 GPU] it %2d pcg %4d lin %.2f ms solve %.2f ms (%.1f us/pcg-it)" % (g.iteration, g.pcg_iterations, g.linearize_ms, g.solve_ms, 1e3 * g.solve_ms / max(g.pcg_iterations, 1)))
     print("single GPU: e0 %.9g  %d iterations in %.3fs final %.9g" % (e1, single.iterations(), dt1, single.error()))
     assert abs(e0 - e1) <= 1e-12 * e1
     assert single.iterations() == len(log)
