@@ -43,6 +43,7 @@ SIGNATURES = {
     "asc_get_landmark_blocks": (C.c_int, [_vp, _vp, _vp, _vp]),
     "asc_get_pose_blocks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "asc_solve_damped": (C.c_int, [_vp, C.c_double, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
+    "asc_extrinsic_marginal": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32)]),
     "asc_save_values": (C.c_int, [_vp]),
     "asc_restore_values": (C.c_int, [_vp]),
     "asc_launch_count": (C.c_int64, [_vp]),
@@ -277,6 +278,13 @@ class BatchOptimizer:
         its = C.c_int32()
         self._check(self.L.asc_solve_damped(self.h, float(lam), _ptr(dq), _ptr(dl), _ptr(dx), C.byref(its)))
         return dq, dl, dx, its.value
+
+    def extrinsic_marginal(self):
+        """K0 block of (A^T A)^-1 at the current values (src/ArmSlamCalib.cpp:490-493); returns (cov 6x6, PCG iterations)."""
+        cov = np.empty((6, 6))
+        its = C.c_int32()
+        self._check(self.L.asc_extrinsic_marginal(self.h, _ptr(cov), C.byref(its)))
+        return cov, its.value
 
     def optimize(self, mode=D.ASC_BATCH_LM):
         cap = max(1, int(self.params.max_iterations))

@@ -715,6 +715,39 @@ struct Engine {
         return backsub(h);
     }
 
+    // (S^-1)_KK of the undamped reduced system: six PCG solves with unit right-hand sides on the K0 rows
+    static int marginal(asc_handle* h, double* cov36, int* iters_total) {
+        const size_t PN = (size_t)h->P * N;
+        h->coarse_valid = false;
+        int rc = prepare(h, 0.0);
+        if (rc) return rc;
+        int total = 0;
+        for (int i = 0; i < 6; ++i) {
+            CUDA_TRY(cudaMemsetAsync(h->rhs, 0, sizeof(double) * (PN + 8), h->stream));
+            set_scalar_kernel<<<1, 1, 0, h->stream>>>(h->rhs + PN + i, 1.0);
+            CUDA_TRY(cudaGetLastError());
+            h->warm_ok = false;
+            int its = 0;
+            rc = pcg(h, 0.0, &its);
+            total += its;
+            if (rc) return rc;
+            const int big = 0x7fffffff;
+            if (h->h_flags[1] != big || h->h_flags[2] != big || h->h_flags[3] != big || h->h_status[32 + 6] != 0.0) {
+                h->fail_kind = 'K'; h->fail_index = 0;
+                return fail(ASC_ERR_INDETERMINATE, "the undamped reduced system is not positive definite");
+            }
+            double col[6];
+            CUDA_TRY(cudaMemcpyAsync(col, h->vx + PN, sizeof col, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            for (int r = 0; r < 6; ++r) cov36[6 * r + i] = col[r];
+        }
+        for (int r = 0; r < 6; ++r)   // S^-1 is symmetric; average away the PCG tolerance
+            for (int c = r + 1; c < 6; ++c) { const double m = 0.5 * (cov36[6 * r + c] + cov36[6 * c + r]); cov36[6 * r + c] = m; cov36[6 * c + r] = m; }
+        if (iters_total) *iters_total = total;
+        h->warm_ok = false;   // rhs no longer belongs to the linearisation
+        return ASC_OK;
+    }
+
     // graph.error(values) at (q, lm4, X); synchronises and returns the value
     static int error(asc_handle* h, const double* q, const double* lm4, const double* X, double* out) {
         int rc = fk(h, q, X, false);
@@ -751,6 +784,11 @@ int dispatch_linearize(asc_handle* h, bool store_b, float* a, float* b) {
 }
 int dispatch_solve(asc_handle* h, double lambda, int* iters) {
 #define X(n) case n: return Engine<n>::solve(h, lambda, iters);
+    switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
+#undef X
+}
+int dispatch_marginal(asc_handle* h, double* cov36, int* iters) {
+#define X(n) case n: return Engine<n>::marginal(h, cov36, iters);
     switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
 #undef X
 }
@@ -1699,6 +1737,17 @@ int asc_solve_damped(asc_handle* h, double lambda, double* dq, double* dl, doubl
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return ASC_OK;
+}
+
+int asc_extrinsic_marginal(asc_handle* h, double* cov36, int32_t* pcg_iterations) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!cov36) return fail(ASC_ERR_INVALID, "null argument");
+    if (!h->linearized) { rc = dispatch_linearize(h, false, nullptr, nullptr); if (rc) return rc; }
+    int its = 0;
+    rc = dispatch_marginal(h, cov36, &its);
+    if (pcg_iterations) *pcg_iterations = its;
+    return rc;
 }
 
 // ---- measurement support

@@ -176,6 +176,15 @@ int asc_get_pose_blocks(asc_handle* h, double* bpp /*[P][N][N]*/, double* bpk /*
 int asc_solve_damped(asc_handle* h, double lambda, double* delta_q, double* delta_l,
                      double* delta_x, int32_t* pcg_iterations);
 
+/*
+ * Marginal covariance of the extrinsic K0 at the current values: the K0 block of (A^T A)^-1 of the linearised graph --
+ * what isam2.marginalCovariance(ExtrinsicSymbol()) hands to DrawState in the reference (src/ArmSlamCalib.cpp:490-493,
+ * :976-998) and what gtsam::Marginals(graph, values).marginalCovariance(K0) returns on the batch path.  Computed from
+ * the operators of the solve: (S^-1)_KK of the UNDAMPED reduced system, six PCG solves with unit right-hand sides.
+ * cov36: 6x6 row-major, tangent order [omega, v].  ASC_ERR_INDETERMINATE if the system is singular.
+ */
+int asc_extrinsic_marginal(asc_handle* h, double* cov36, int32_t* pcg_iterations);
+
 /* ---- measurement support (bench.py) ----------------------------------------------- */
 /* device-resident snapshot of the current values / restore it (keeps the timed region free of H2D copies) */
 int asc_save_values(asc_handle* h);

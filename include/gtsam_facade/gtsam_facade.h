@@ -63,6 +63,22 @@ private:
     std::vector<double> d_;
 };
 
+// dense row-major matrix; only what ArmSlamCalib.cpp does with a marginal covariance: rows(), operator()(i, j) (:976-985)
+class Matrix {
+public:
+    Matrix() : r_(0), c_(0) {}
+    Matrix(size_t r, size_t c, double v = 0.0) : r_(r), c_(c), d_(r * c, v) {}
+    double& operator()(size_t i, size_t j) { return d_[i * c_ + j]; }
+    double operator()(size_t i, size_t j) const { return d_[i * c_ + j]; }
+    size_t rows() const { return r_; }
+    size_t cols() const { return c_; }
+    const double* data() const { return d_.data(); }
+    double* data() { return d_.data(); }
+private:
+    size_t r_, c_;
+    std::vector<double> d_;
+};
+
 // Symbol(char, index), ArmSlamCalib.h:284-286: 'K' extrinsic, 'q' configuration, 'l' landmark
 class Symbol {
 public:
@@ -354,6 +370,13 @@ public:
     double error() const { return error_; }
     int iterations() const { return iterations_; }
     const Values& values() const { return values_; }
+    Key extrinsicKey() const { return extrinsic_key_; }
+    // K0 block of (A^T A)^-1 at the values the handle currently holds (the initial ones before optimize(), the result after)
+    Matrix extrinsicMarginal() {
+        Matrix m(6, 6);
+        check(asc_extrinsic_marginal(h_, m.data(), nullptr), h_);
+        return m;
+    }
 
 private:
     void pack(const NonlinearFactorGraph& graph, const Values& initial, const asc_params& prm_in) {
@@ -473,6 +496,20 @@ private:
         a.lambda_lower_bound = p.lambdaLowerBound; a.min_model_fidelity = p.minModelFidelity;
         return a;
     }
+    facade_detail::BatchOptimizer impl_;
+};
+
+// gtsam::Marginals, the batch counterpart of isam2.marginalCovariance(ExtrinsicSymbol()) (src/ArmSlamCalib.cpp:490-493).
+// Only the extrinsic K0 can be queried: that is the one marginal the reference computes and draws (:976-998).
+class Marginals {
+public:
+    Marginals(const NonlinearFactorGraph& graph, const Values& solution) : impl_(graph, solution, ASC_BATCH_LM, default_params()) {}
+    Matrix marginalCovariance(Key variable) {
+        if (variable != impl_.extrinsicKey()) throw std::invalid_argument("Marginals: only the extrinsic " + DefaultKeyFormatter(impl_.extrinsicKey()) + " is supported");
+        return impl_.extrinsicMarginal();
+    }
+private:
+    static asc_params default_params() { asc_params a; asc_default_params(&a); return a; }
     facade_detail::BatchOptimizer impl_;
 };
 

@@ -34,6 +34,8 @@ def _load():
         L.orc_error.argtypes = [_vp, _vp, _vp, _vp]
         L.orc_linearize.restype = C.c_double
         L.orc_linearize.argtypes = [_vp] + [_vp] * 16
+        L.orc_extrinsic_marginal.restype = C.c_int
+        L.orc_extrinsic_marginal.argtypes = [_vp, _vp, _vp, _vp, _vp]
         L.orc_solve_damped.restype = C.c_int
         L.orc_solve_damped.argtypes = [_vp, _vp, _vp, _vp, C.c_double, C.c_int, _vp, _vp, _vp, C.POINTER(C.c_int)]
         L.orc_optimize.restype = C.c_int
@@ -130,6 +132,13 @@ class Oracle:
         its = C.c_int()
         rc = self.L.orc_solve_damped(self.h, _p(q), _p(l), _p(x), float(lam), solver, _p(dq), _p(dl), _p(dx), C.byref(its))
         return rc, dq, dl, dx, its.value
+
+    def extrinsic_marginal(self, q, l, x):
+        """K0 block of (A^T A)^-1 at the given values (6x6, tangent order [w, v]); rc as in solve_damped."""
+        q, l, x = _f64(q), _f64(l), _f64(x)
+        cov = np.empty((6, 6))
+        rc = self.L.orc_extrinsic_marginal(self.h, _p(q), _p(l), _p(x), _p(cov))
+        return rc, cov
 
     def optimize(self, q, l, x, mode=0, solver=0):
         from arm_slam_calib_b200._ctypes_defs import AscIterLog

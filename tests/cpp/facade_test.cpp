@@ -110,5 +110,18 @@ int main(int argc, char** argv) {
     for (int j = 0; j < L; ++j)
         if (currentEstimate.find(LandmarkSymbol(lm_id[j])) != currentEstimate.end()) { (void)currentEstimate.at<gtsam::Point3>(LandmarkSymbol(lm_id[j])); ++found; }
     printf("RESULT %d %.12g %.12g %.12g %.12g %zu\n", iterations, total_error, X.translation().x(), X.translation().y(), X.translation().z(), found);
+    if (argc > 3 && std::string(argv[3]) == "marginal") {
+        // batch counterpart of  extrinsicMarginals = isam2.marginalCovariance(ExtrinsicSymbol());  (src/ArmSlamCalib.cpp:490-493)
+        try {
+            Marginals marginals(*graph, currentEstimate);
+            Matrix extrinsicMarginals = marginals.marginalCovariance(ExtrinsicSymbol());
+            if (extrinsicMarginals.rows() > 0)   // the guard of DrawState, :976
+                printf("MARGINAL %.12g %.12g %.12g %.12g %.12g %.12g\n", extrinsicMarginals(0, 0), extrinsicMarginals(1, 1), extrinsicMarginals(2, 2),
+                       extrinsicMarginals(3, 3), extrinsicMarginals(4, 4), extrinsicMarginals(5, 5));
+        } catch (std::exception& e) {
+            fprintf(stderr, "EXCEPTION %s\n", e.what());
+            return 3;
+        }
+    }
     return 0;
 }

@@ -39,3 +39,16 @@ def test_optimize_step_through_the_facade_matches_the_oracle(asc, oracle_cls, fa
     assert iters == ref["iterations"] and found == pb.n_landmarks
     assert abs(err - ref["error"]) <= 1e-6 * ref["error"]
     assert np.abs(np.array([kx, ky, kz]) - ref["x"].reshape(3, 4)[:, 3]).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_marginals_through_the_facade_match_the_oracle(asc, oracle_cls, facade_exe):
+    r = subprocess.run([facade_exe, "BatchLM", "40", "marginal"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    diag = np.array([float(t) for t in [l for l in r.stdout.splitlines() if l.startswith("MARGINAL")][0].split()[1:]])
+    pb = asc.make_sim_problem(trajectory_size=40, seed=3)
+    orc = oracle_cls(pb, asc.default_params())
+    ref = orc.optimize(pb.q0, pb.l0, pb.x0, mode=0, solver=0)
+    rc, cov = orc.extrinsic_marginal(ref["q"], ref["l"], ref["x"])
+    assert rc == 0
+    assert np.abs(diag - np.diag(cov)).max() < 1e-4 * np.abs(np.diag(cov)).max()

@@ -144,3 +144,24 @@ def test_repacking_on_a_reused_handle_is_bitwise_identical(asc, c1_offset_proble
         q, l, x = opt.optimize(0)
         assert np.array_equal(q, q0) and np.array_equal(l, l0) and np.array_equal(x, x0) and opt.error() == e0
     opt.close()
+
+
+@pytest.mark.parametrize("name", ["small", "c1off"])
+def test_extrinsic_marginal_matches_oracle(asc, oracle_cls, problems, name):
+    """asc_extrinsic_marginal (six PCG solves of the undamped reduced system) against the oracle's exact (S^-1)_KK."""
+    pb = problems[name]
+    prm = asc.default_params()
+    opt = asc.BatchOptimizer(pb, prm)
+    orc = oracle_cls(pb, prm)
+    vals = perturbed_values(pb)
+    opt.set_values(*vals)
+    cov, its = opt.extrinsic_marginal()
+    rc, ref = orc.extrinsic_marginal(*vals)
+    assert rc == 0 and its > 0
+    assert np.abs(cov - cov.T).max() == 0.0
+    assert np.abs(cov - ref).max() < 1e-7 * np.abs(ref).max(), (cov, ref)
+    # the marginal does not disturb a following optimize()
+    q, l, x = opt.optimize(asc.ASC_BATCH_LM)
+    r = orc.optimize(*vals, mode=0, solver=0)
+    assert opt.iterations() == r["iterations"] and abs(opt.error() - r["error"]) <= 1e-6 * r["error"]
+    opt.close()
