@@ -173,6 +173,9 @@ struct asc_handle {
     double *ybuf = nullptr;      // [y (PN) | yK(6) pad to 8 | rowC(32) | rowB(32)]
     double *partA = nullptr, *partB = nullptr, *partC = nullptr, *partL = nullptr, *partR = nullptr, *errblk = nullptr;
     int nCtaPose = 0, nBlkLm = 0, nErrBlk = 0;
+    int nBlkB = 0;               // CTAs of schur_pass_b_kernel (kPassBLmPerBlock landmarks each)
+    double *grpC = nullptr, *grpB = nullptr;     // group rows of pass C / pass B partials (kernels.cuh, grouped_rows_reduce)
+    unsigned *tickC = nullptr, *tickB = nullptr, *tickG = nullptr;   // their ticket counters; tickG: coarse GEMV
     int nBlkLmK2 = 0;            // CTAs of landmark_blocks_kernel (kLmPerBlock landmarks each)
     double* lmerr = nullptr;     // their landmark-prior error partials
     double *scal = nullptr, *status = nullptr;
@@ -504,9 +507,11 @@ struct Engine {
         return ASC_OK;
     }
 
-    // one application y = S x written into ybuf; K rows handled by the caller's kernels
+    // one application y = S x written into ybuf; K rows handled by the caller's kernels.
+    // grouped: passes B and C also leave group rows of their CTA partials in grpB / grpC (PCG loop); fuse_mid: the CTA of
+    // pass C that finishes last runs pcg_mid_body (single GPU, inside the loop)
     static int schur_apply_launch(asc_handle* h, double lambda, bool update_p, double* x, const int* done, const double* lambda_dev = nullptr,
-                                  bool to_slot = false) {
+                                  bool to_slot = false, bool grouped = false, const MidArgs* mid = nullptr) {
         h->launches += 3;
         prof_start(h, 3);
         if (update_p)
@@ -518,14 +523,16 @@ struct Engine {
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 3);
         prof_start(h, 4);
-        schur_pass_b_kernel<false><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, x + (size_t)h->P * N, done,
-                                                                    nullptr, h->u4, h->partB);
+        schur_pass_b_kernel<false><<<h->nBlkB, kPassBThreads, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, x + (size_t)h->P * N, done,
+                                                                             nullptr, h->u4, h->partB, grouped ? h->grpB : nullptr, grouped ? h->tickB : nullptr);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 4);
         prof_start(h, 5);
+        MidArgs none{};
         schur_pass_c_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, h->rank == 0 ? 1 : 0, h->pose_ptr, h->p_lm, h->J, h->u4, x,
                                                                          h->Bpp, h->BpK, done, h->ybuf, h->partC, lambda_dev, h->chain, h->lml,
-                                                                         to_slot ? h->pcm.ctr : nullptr, to_slot ? h->pcm.x[h->rank] : nullptr, h->pcm.stride);
+                                                                         to_slot ? h->pcm.ctr : nullptr, to_slot ? h->pcm.x[h->rank] : nullptr, h->pcm.stride,
+                                                                         grouped ? h->grpC : nullptr, grouped ? h->tickC : nullptr, mid ? 1 : 0, mid ? *mid : none);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 5);
         return ASC_OK;
@@ -533,7 +540,7 @@ struct Engine {
 
     // zc = E^-1 (A rc) (coarse correction of the preconditioner; A sums the per-cluster restriction over each aggregate)
     static const double* coarse_rhs(const asc_handle* h) { return h->aggS > 1 ? h->rca : h->rc; }
-    static int coarse_apply(asc_handle* h, const int* done) {
+    static int coarse_apply(asc_handle* h, const int* done, const EndArgs* end = nullptr) {
         h->launches += 1;
         if (h->aggS > 1) {
             coarse_aggregate_kernel<<<cdiv(h->nz, 256), 256, 0, h->stream>>>(h->rc, h->rca, h->nz, h->nA, h->nC, N, h->aggS, done);
@@ -541,7 +548,9 @@ struct Engine {
             h->launches += 1;
         }
         if (h->coarse_f32_active) {
-            coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9);
+            EndArgs none{};
+            coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9, end ? *end : none,
+                                                                         end ? h->tickG : nullptr);
             CUDA_TRY(cudaGetLastError());
         } else {
             const double one = 1.0, zero = 0.0;
@@ -565,7 +574,7 @@ struct Engine {
         if (warm) {
             int rcw = schur_apply_launch(h, lambda, false, h->vx, nullptr, nullptr);   // ybuf = S x0 (keyframe rows)
             if (rcw) return rcw;
-            schur_k_rows_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, h->partC, h->nCtaPose, h->partB, h->nBlkLm, h->BKK, h->vx, h->ybuf + PN);
+            schur_k_rows_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, h->partC, h->nCtaPose, h->partB, h->nBlkB, h->BKK, h->vx, h->ybuf + PN);
             CUDA_TRY(cudaGetLastError());
             h->launches += 1;
         }
@@ -602,53 +611,73 @@ struct Engine {
         int launched = 0;
         const double* lam_dev = h->scal + 8;
         const bool p2p = h->world > 1 && h->p2p_ok && h->use_clusters;   // peer-memory exchange instead of ncclAllReduce
+        const bool profiling = h->prof_id != 0 && 2 * h->prof_n + 1 < (int)h->prof_ev.size();   // event-bracketed launches cannot be captured
+        // "last CTA" fusion (kernels.cuh): pcg_mid inside pass C (single GPU), pcg_end inside the fp32 coarse GEMV, with the CTA
+        // partials of passes B / C pre-reduced in groups.  MEASURED SLOWER on C2 (166.6 vs 157.8 ms per step: the per-CTA
+        // __threadfence + ticket costs more than the two kernel boundaries it saves), so it is off unless ASC_FUSE=1.
+        static const bool fuse = getenv("ASC_FUSE") != nullptr;
+        const bool fuse_mid = fuse && !profiling && h->world == 1;
+        const bool fuse_end = fuse && !profiling && h->use_clusters && h->use_coarse && h->coarse_f32_active;
+        const int nGrpC = cdiv(h->nCtaPose, kRowGroup), nGrpB = cdiv(h->nBlkB, kRowGroup);
+        CUDA_TRY(cudaMemsetAsync(h->tickC, 0, sizeof(unsigned) * (nGrpC + 2), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->tickB, 0, sizeof(unsigned) * (nGrpB + 2), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->tickG, 0, sizeof(unsigned) * 4, h->stream));
         auto one_iteration = [&]() -> int {
-            int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev, p2p);
-            if (rc) return rc;
-            const double* pc_ = h->partC;
-            const double* pb_ = h->partB;
-            int nC = h->nCtaPose, nB = h->nBlkLm;
             double* rowC = h->ybuf + PN + 8;
             double* rowB = rowC + kPartCols;
+            MidArgs mid{};
+            mid.P = h->P; mid.N = N; mid.lambda_val = lambda; mid.lambda_dev = lam_dev;
+            mid.partC = fuse ? h->grpC : h->partC; mid.nC = fuse ? nGrpC : h->nCtaPose; mid.partB = fuse ? h->grpB : h->partB; mid.nB = fuse ? nGrpB : h->nBlkB;
+            mid.BKK = h->BKK; mid.MinvK = h->MinvK; mid.p = h->vp; mid.x = h->vx; mid.r = h->vr; mid.z = h->vz;
+            mid.yK_out = h->ybuf + PN; mid.scal = h->scal; mid.done = h->flags;
+            mid.rcK = h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr;
+            int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev, p2p, fuse, fuse_mid ? &mid : nullptr);
+            if (rc) return rc;
             if (p2p) {
-                pcg_signal_kernel<<<1, 1024, 0, h->stream>>>(h->pcm, h->partC, h->nCtaPose, h->partB, h->nBlkLm, h->flags);
+                pcg_signal_kernel<<<1, 1024, 0, h->stream>>>(h->pcm, mid.partC, mid.nC, mid.partB, mid.nB, h->flags);
                 CUDA_TRY(cudaGetLastError());
                 h->launches += 1;
-                pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
+                mid.partC = rowC; mid.partB = rowB; mid.nC = 1; mid.nB = 1;
             } else if (h->world > 1) {
-                reduce_rows_pair_kernel<<<2, 1024, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, rowC, h->partB, h->nBlkLm, 6, kPcgCols, rowB, h->flags);
+                reduce_rows_pair_kernel<<<2, 1024, 0, h->stream>>>(mid.partC, mid.nC, 7, kPcgCols, rowC, mid.partB, mid.nB, 6, kPcgCols, rowB, h->flags);
                 CUDA_TRY(cudaGetLastError());
                 h->launches += 1;
                 rc = allreduce(h, h->ybuf, PN + 8 + 2 * kPartCols);
                 if (rc) return rc;
-                pc_ = rowC; pb_ = rowB; nC = 1; nB = 1;
+                mid.partC = rowC; mid.partB = rowB; mid.nC = 1; mid.nB = 1;
             }
-            pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, lam_dev, pc_, nC, pb_, nB, h->BKK, h->MinvK, h->vp, h->vx, h->vr, h->vz,
-                                                    h->ybuf + PN, h->scal, h->flags, h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr,
-                                                    p2p ? h->pcm : single, rowC);
-            CUDA_TRY(cudaGetLastError());
+            if (!fuse_mid) {
+                pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(mid, p2p ? h->pcm : single, rowC);
+                CUDA_TRY(cudaGetLastError());
+                h->launches += 1;
+            }
+            EndArgs end{};
+            end.P = h->P; end.N = N; end.part = h->partA; end.nPart = nUpd; end.tol2 = tol2; end.max_iters = h->prm.pcg_max_iters;
+            end.p = h->vp; end.z = h->vz; end.scal = h->scal; end.done = h->flags; end.rc = h->use_coarse ? h->rc : nullptr; end.zc = h->zc;
+            end.nz = h->nz; end.nC = h->nC; end.nA = h->nA; end.S = h->aggS;
             if (h->use_clusters) {
                 pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
                                                                       h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr, p2p ? h->pcm : single);
-                if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags); if (rc3) return rc3; }
+                if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags, fuse_end ? &end : nullptr); if (rc3) return rc3; }
             } else {
                 pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
             }
             CUDA_TRY(cudaGetLastError());
-            h->launches += 3;
-            pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, h->partA, nUpd, tol2, h->prm.pcg_max_iters, h->vp, h->vz, h->scal, h->flags,
-                                                    h->use_coarse ? h->rc : nullptr, h->zc, h->nz, h->nC, h->nA, h->aggS);
-            CUDA_TRY(cudaGetLastError());
+            h->launches += 1;
+            if (!fuse_end) {
+                pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(end);
+                CUDA_TRY(cudaGetLastError());
+                h->launches += 1;
+            }
             return ASC_OK;
         };
         // one chunk = `chunk` iterations; kernels return immediately once the device-side done flag is set
         static const bool no_graph = getenv("ASC_NO_GRAPH") != nullptr;
-        const bool profiling = h->prof_id != 0 && 2 * h->prof_n + 1 < (int)h->prof_ev.size();   // event-bracketed launches cannot be captured
         // multi-GPU: with the peer-memory exchange the loop holds kernels only and is captured like the single-GPU one (a captured
         // ncclAllReduce hung on this stack: NCCL 2.28.9, driver 580); ASC_NO_GRAPH_MGPU=1 falls back to plain launches
         static const bool no_graph_mgpu = getenv("ASC_NO_GRAPH_MGPU") != nullptr;
         const bool can_graph = !no_graph && (h->world == 1 || (p2p && !no_graph_mgpu)) && !profiling && (!h->use_coarse || h->coarse_f32_active);
-        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0);
+        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0) | (fuse_mid ? 16 : 0) | (fuse_end ? 32 : 0);
         for (;;) {
             if (can_graph) {
                 if (!h->pcg_graph || h->pcg_graph_key != graph_key) {
@@ -690,8 +719,8 @@ struct Engine {
         schur_pass_a_kernel<N, false><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, h->pose_ptr, h->p_lm, h->J, h->vx, nullptr, nullptr, nullptr, h->v4, nullptr,
                                                                                 nullptr, h->p_inv, h->chain, h->lml);
         CUDA_TRY(cudaGetLastError());
-        schur_pass_b_kernel<true><<<h->nBlkLm, 128, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
-                                                                   h->cg4, h->dl4, nullptr);
+        schur_pass_b_kernel<true><<<h->nBlkB, kPassBThreads, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
+                                                                   h->cg4, h->dl4, nullptr, nullptr, nullptr);
         CUDA_TRY(cudaGetLastError());
         return ASC_OK;
     }
@@ -807,7 +836,8 @@ int dispatch_schur_c(asc_handle* h, double lambda, double* x, double* u4_in) {
 #define X(n)                                                                                                                      \
     case n:                                                                                                                       \
         schur_pass_c_kernel<n><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, 0, h->pose_ptr, h->p_lm, h->J, u4_in, x, \
-                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr, h->chain, h->lml, nullptr, nullptr, 0); \
+                                                                         h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr, h->chain, h->lml, nullptr, nullptr, 0, \
+                                                                         nullptr, nullptr, 0, MidArgs{}); \
         break;
     switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
 #undef X
@@ -1457,6 +1487,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     h->nCtaPose = cdiv(P, kWarpsPerCta);
     h->nBlkLm = std::max(1, cdiv(L, 128));
     h->nBlkLmK2 = std::max(1, cdiv(L, kLmPerBlock));
+    h->nBlkB = std::max(1, cdiv(L, kPassBLmPerBlock));
     int rc = ASC_OK;
     std::vector<ArenaReq> reqs;
 #define ALLOC(ptr, count) reqs.push_back(ArenaReq{(void**)&h->ptr, sizeof(*h->ptr) * std::max<size_t>((size_t)(count), 1)})
@@ -1497,7 +1528,9 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     ALLOC(ybuf, PN + 8 + 2 * kPartCols);
     const size_t nStep = (size_t)cdiv(std::max<int64_t>((int64_t)PN + 6, (int64_t)L * 4), 256);
     ALLOC(partA, std::max<size_t>(std::max<size_t>((size_t)P + 1024, nStep), (size_t)h->nC) * kPartCols); ALLOC(partC, (size_t)h->nCtaPose * kPartCols);
-    ALLOC(partB, (size_t)h->nBlkLm * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
+    ALLOC(grpC, (size_t)(cdiv(h->nCtaPose, kRowGroup) + 1) * kPcgCols); ALLOC(grpB, (size_t)(cdiv(h->nBlkB, kRowGroup) + 1) * kPcgCols);
+    ALLOC(tickC, cdiv(h->nCtaPose, kRowGroup) + 2); ALLOC(tickB, cdiv(h->nBlkB, kRowGroup) + 2); ALLOC(tickG, 4);
+    ALLOC(partB, (size_t)h->nBlkB * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
     h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
     ALLOC(errblk, h->nErrBlk); ALLOC(lmerr, h->nBlkLmK2);
     ALLOC(scal, 16); ALLOC(status, 64); ALLOC(flags, 16); ALLOC(cheir, 1); ALLOC(SKK, 36); ALLOC(stage3, (size_t)L * 3);

@@ -92,6 +92,18 @@ __device__ __forceinline__ double peer_sum(const PeerComm& pc, unsigned seq, lon
 // ------------------------------------------------------------------ tiny device helpers
 __device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
 
+// One 32-byte sector per instruction (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256).  The padded 3-vector tables (lm4, u4, v4,
+// lml) are gathered one sector per lane; a 128-bit + 64-bit pair costs two L1 tag passes per sector, this costs one.
+struct d4 { double x, y, z, w; };
+__device__ __forceinline__ d4 ldg256(const double* p) {   // read-only data, 32-byte aligned
+    d4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -467,17 +479,16 @@ __device__ __forceinline__ void linearize_role(const Camera& cm, const PriorCons
     const bool any = k1 > k0;
     int j_nxt = any ? __ldg(p_lm + min(k0 + lane, klast)) : 0;
     double2 z_nxt = any ? ldg2(p_uv + min(k0 + lane, klast)) : make_double2(0.0, 0.0);
-    double2 l01_nxt = any ? ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j_nxt)) : make_double2(0.0, 0.0);
-    double lz_nxt = any ? __ldg(lm4 + 4 * (size_t)j_nxt + 2) : 0.0;
+    d4 l_nxt = ldg256(lm4 + 4 * (size_t)j_nxt);
     int j_nxt2 = any ? __ldg(p_lm + min(k0 + 32 + lane, klast)) : 0;
     for (int base = k0; base < k1; base += 32) {
         const int k = base + lane;
-        const double2 z = z_nxt, l01 = l01_nxt;
-        const double lz = lz_nxt;
+        const double2 z = z_nxt;
+        const double2 l01 = make_double2(l_nxt.x, l_nxt.y);
+        const double lz = l_nxt.z;
         {   // prefetch tile t+1 (clamped indices keep the loads in range; values of inactive lanes are not used)
             z_nxt = ldg2(p_uv + min(k + 32, klast));
-            l01_nxt = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j_nxt2));
-            lz_nxt = __ldg(lm4 + 4 * (size_t)j_nxt2 + 2);
+            l_nxt = ldg256(lm4 + 4 * (size_t)j_nxt2);
             j_nxt2 = __ldg(p_lm + min(k + 64, klast));
         }
         double r0[D], r1[D];   // the two whitened rows [J_q (N) | J_K (6) | b] of this lane's factor (zero if none)
@@ -620,13 +631,11 @@ proj_kk_kernel(Camera cm, int64_t M, const int* __restrict__ p_pose, const int* 
         const int p = __ldg(p_pose + k), j = __ldg(p_lm + k);
         const double2 z = ldg2(p_uv + k);
         double R[12];
-        const double2* cp = reinterpret_cast<const double2*>(cam + (size_t)p * 12);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { const double2 t = ldg2(cp + i); R[2 * i] = t.x; R[2 * i + 1] = t.y; }
-        const double2 l01 = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j));
-        const double lz = __ldg(lm4 + 4 * (size_t)j + 2);
+        for (int i = 0; i < 3; ++i) { const d4 t = ldg256(cam + (size_t)p * 12 + 4 * i); R[4 * i] = t.x; R[4 * i + 1] = t.y; R[4 * i + 2] = t.z; R[4 * i + 3] = t.w; }
+        const d4 lq = ldg256(lm4 + 4 * (size_t)j);
         ProjOut o;
-        project_factor<true, true>(cm, R, R + 9, l01.x, l01.y, lz, z.x, z.y, o);
+        project_factor<true, true>(cm, R, R + 9, lq.x, lq.y, lq.z, z.x, z.y, o);
         double r0[7], r1[7];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { r0[i] = o.jk[i]; r1[i] = o.jk[6 + i]; }
@@ -748,9 +757,8 @@ landmark_blocks_kernel(Camera cm, int L, const int* __restrict__ lm_ptr, const i
             const int p = __ldg(l_pose + k);
             const double2 z = ldg2(l_uv + k);
             double R[12];
-            const double2* cp = reinterpret_cast<const double2*>(cam + (size_t)p * 12);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) { const double2 t = ldg2(cp + i); R[2 * i] = t.x; R[2 * i + 1] = t.y; }
+            for (int i = 0; i < 3; ++i) { const d4 t = ldg256(cam + (size_t)p * 12 + 4 * i); R[4 * i] = t.x; R[4 * i + 1] = t.y; R[4 * i + 2] = t.z; R[4 * i + 3] = t.w; }
             ProjOut o;
             project_factor<true, true>(cm, R, R + 9, lx, ly, lz, z.x, z.y, o);
             v[0] += o.jl[0] * o.jl[0] + o.jl[3] * o.jl[3]; v[1] += o.jl[0] * o.jl[1] + o.jl[3] * o.jl[4];
@@ -1349,32 +1357,6 @@ __device__ __forceinline__ int coarse_index_of(int i, int nC, int nA, int N, int
     return (c / S) * N + (i - c * N);
 }
 
-// zc = Einv(fp32, full symmetric, row-major) * x, one warp per row, fp64 accumulation.  x is the restriction itself
-// (one cluster per aggregate) or its aggregated copy written by coarse_aggregate_kernel.
-__global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
-                                                              int n, const int* __restrict__ done, const double* __restrict__ alpha) {
-    if (done && *done) return;
-    const double scale = alpha ? *alpha : 1.0;   // scalar re-fit of a reused (stale) coarse inverse, see coarse_refit_kernel
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 4 + warp;
-    if (row >= n) return;
-    const float* a = A + (size_t)row * n;
-    double acc0 = 0.0, acc1 = 0.0;
-    int i = lane * 2;
-    for (; i + 64 + 1 < n; i += 128) {
-        const float2 u = *reinterpret_cast<const float2*>(a + i);
-        const float2 v = *reinterpret_cast<const float2*>(a + i + 64);
-        acc0 = fma((double)u.x, x[i], fma((double)u.y, x[i + 1], acc0));
-        acc1 = fma((double)v.x, x[i + 64], fma((double)v.y, x[i + 65], acc1));
-    }
-    for (; i < n; i += 64) {
-        acc0 = fma((double)a[i], x[i], acc0);
-        if (i + 1 < n) acc0 = fma((double)a[i + 1], x[i + 1], acc0);
-    }
-    const double t = warp_sum(acc0 + acc1);
-    if (lane == 0) y[row] = scale * t;
-}
-
 // aggregated restriction A rc (only launched when an aggregate holds more than one cluster)
 __global__ void __launch_bounds__(256) coarse_aggregate_kernel(const double* __restrict__ rc, double* __restrict__ rca, int n, int nA, int nC, int N, int S,
                                                                 const int* __restrict__ done) {
@@ -1484,154 +1466,38 @@ schur_pass_a_kernel(int P, int64_t M, const int* __restrict__ pose_ptr, const in
 #pragma unroll
     for (int i = 0; i < 6; ++i) ab[i] = warp_sum(ab[i]);
     const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+    // (a one-tile-ahead software pipeline of the streamed loads was measured slower here: 64 instead of 48 registers)
     for (int k = k0 + lane; k < k1; k += 32) {
         double jl[6];
         load_jl<N>(J, M, k, jl);
         const int j = __ldg(p_lm + k);
-        const double2 l01 = ldg2(reinterpret_cast<const double2*>(lml + 4 * (size_t)j));
-        const double lz = __ldg(lml + 4 * (size_t)j + 2);
-        const double w0 = ab[1] * lz - ab[2] * l01.y - ab[3], w1 = ab[2] * l01.x - ab[0] * lz - ab[4], w2 = ab[0] * l01.y - ab[1] * l01.x - ab[5];
+        const int slot = __ldg(p_inv + k);
+        const d4 l = ldg256(lml + 4 * (size_t)j);
+        const double w0 = ab[1] * l.z - ab[2] * l.y - ab[3], w1 = ab[2] * l.x - ab[0] * l.z - ab[4], w2 = ab[0] * l.y - ab[1] * l.x - ab[5];
         const double s0 = -(jl[0] * w0 + jl[1] * w1 + jl[2] * w2), s1 = -(jl[3] * w0 + jl[4] * w1 + jl[5] * w2);
         // v goes straight to its landmark-major slot (one full 32-byte sector), so pass B reads its segment contiguously
-        double2* o = reinterpret_cast<double2*>(v4 + 4 * (size_t)__ldg(p_inv + k));
-        o[0] = make_double2(jl[0] * s0 + jl[3] * s1, jl[1] * s0 + jl[4] * s1);
-        o[1] = make_double2(jl[2] * s0 + jl[5] * s1, 0.0);
-    }
-}
-
-// pass B (landmark-major): u_j = Cinv_j (sum_k v + W_Kj^T x_K) [or cg_j - that, for back-substitution];
-// block partials of sum_j W_Kj u_j.   One thread per landmark.
-template <bool BACKSUB>
-__global__ void __launch_bounds__(128)
-schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const double* __restrict__ v4,
-                    const double* __restrict__ WK, const double* __restrict__ Cinv, const double* __restrict__ xK,
-                    const int* __restrict__ done, const double* __restrict__ cg4, double* __restrict__ u4, double* __restrict__ blk_part) {
-    if (done && *done) return;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    double wu[6] = {0, 0, 0, 0, 0, 0};
-    if (j < L) {
-        double tx = 0, ty = 0, tz = 0;
-        const int k0 = lm_ptr[j], k1 = lm_ptr[j + 1];
-        for (int k = k0; k < k1; ++k) {
-            const double2 a = ldg2(reinterpret_cast<const double2*>(v4 + 4 * (size_t)k));
-            const double c = __ldg(v4 + 4 * (size_t)k + 2);
-            tx += a.x; ty += a.y; tz += c;
-        }
-        double W[18], xk[6];
-#pragma unroll
-        for (int i = 0; i < 18; ++i) W[i] = WK[18 * (size_t)j + i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) xk[i] = xK[i];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) { tx += W[3 * r] * xk[r]; ty += W[3 * r + 1] * xk[r]; tz += W[3 * r + 2] * xk[r]; }
-        double ux, uy, uz;
-        sym3_mul(Cinv + 6 * (size_t)j, tx, ty, tz, ux, uy, uz);
-        if (BACKSUB) { ux = cg4[4 * (size_t)j] - ux; uy = cg4[4 * (size_t)j + 1] - uy; uz = cg4[4 * (size_t)j + 2] - uz; }
-        u4[4 * (size_t)j] = ux; u4[4 * (size_t)j + 1] = uy; u4[4 * (size_t)j + 2] = uz; u4[4 * (size_t)j + 3] = 0.0;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) wu[r] = W[3 * r] * ux + W[3 * r + 1] * uy + W[3 * r + 2] * uz;
-    }
-    if (BACKSUB) return;
-    __shared__ double s[4][8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { const double t = warp_sum(wu[i]); if (lane == 0) s[warp][i] = t; }
-    __syncthreads();
-    if (threadIdx.x < kPcgCols) blk_part[(size_t)blockIdx.x * kPcgCols + threadIdx.x] = threadIdx.x < 6 ? s[0][threadIdx.x] + s[1][threadIdx.x] + s[2][threadIdx.x] + s[3][threadIdx.x] : 0.0;
-}
-
-// pass C (pose-major): yloc_p = - sum_m J_q^T (J_l u_j); then (if add_diag) y_p = (B_pp + lambda) x_p + B_pK x_K + yloc_p.
-// CTA partial row: [ sum_p B_pK^T x_p (6) | sum_p x_p . y_p (1) ]
-template <int N>
-__global__ void __launch_bounds__(kCtaThreads)
-schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
-                    const double2* __restrict__ J, const double* __restrict__ u4, const double* __restrict__ x, const double* __restrict__ Bpp,
-                    const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part,
-                    const double* __restrict__ lambda_dev, const double* __restrict__ chain, const double* __restrict__ lml,
-                    const unsigned* __restrict__ xctr, double* __restrict__ xbase, long long xstride) {
-    if (done && *done) return;
-    if (xctr) y = xbase + (size_t)((*xctr + 1u) & 1u) * xstride;   // multi-GPU: the next exchange slot of this rank
-    const double lambda = lambda_dev ? *lambda_dev : lambda_val;   // device-resident inside the captured PCG graph
-    __shared__ double s_part[kWarpsPerCta][8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * kWarpsPerCta + warp;
-    if (lane < 8) s_part[warp][lane] = 0.0;
-    if (p < P) {
-        double ut[6] = {0, 0, 0, 0, 0, 0};   // U = sum l x t | T = sum t over this lane's observations
-        const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
-        for (int k = k0 + lane; k < k1; k += 32) {
-            double jl[6];
-            load_jl<N>(J, M, k, jl);
-            const int j = __ldg(p_lm + k);
-            const double2 u01 = ldg2(reinterpret_cast<const double2*>(u4 + 4 * (size_t)j));
-            const double uz = __ldg(u4 + 4 * (size_t)j + 2);
-            const double2 l01 = ldg2(reinterpret_cast<const double2*>(lml + 4 * (size_t)j));
-            const double lz = __ldg(lml + 4 * (size_t)j + 2);
-            const double e0 = jl[0] * u01.x + jl[1] * u01.y + jl[2] * uz, e1 = jl[3] * u01.x + jl[4] * u01.y + jl[5] * uz;
-            const double t0 = jl[0] * e0 + jl[3] * e1, t1 = jl[1] * e0 + jl[4] * e1, t2 = jl[2] * e0 + jl[5] * e1;
-            ut[0] += l01.y * t2 - lz * t1; ut[1] += lz * t0 - l01.x * t2; ut[2] += l01.x * t1 - l01.y * t0;
-            ut[3] += t0; ut[4] += t1; ut[5] += t2;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ut[i] = warp_sum(ut[i]);
-        double mine = 0.0;   // lane c keeps component c
-        if (lane < N) {
-            const double* c = chain + (size_t)p * 6 * N + 6 * lane;
-            const double a0 = c[0], a1 = c[1], a2 = c[2], o0 = c[3], o1 = c[4], o2 = c[5];
-            const double m0 = a1 * o2 - a2 * o1, m1 = a2 * o0 - a0 * o2, m2 = a0 * o1 - a1 * o0;
-            mine = (a0 * ut[0] + a1 * ut[1] + a2 * ut[2]) - (m0 * ut[3] + m1 * ut[4] + m2 * ut[5]);
-        }
-        double xm = lane < N ? x[(size_t)p * N + lane] : 0.0;
-        if (add_diag) {
-            double xp[N];
-#pragma unroll
-            for (int i = 0; i < N; ++i) xp[i] = __shfl_sync(kFull, xm, i);
-            if (lane < N) {
-                const double* B = Bpp + (size_t)p * N * N + lane * N;
-                const double* BK = BpK + (size_t)p * N * 6 + lane * 6;
-                const double* xK = x + (size_t)P * N;
-                double t = lambda * xm;
-#pragma unroll
-                for (int i = 0; i < N; ++i) t = fma(B[i], xp[i], t);
-#pragma unroll
-                for (int i = 0; i < 6; ++i) t = fma(BK[i], xK[i], t);
-                mine += t;
-            }
-            // B_pK^T x_p : lane c < 6 takes column c
-            double bk = 0.0;
-            if (lane < 6) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) bk = fma(BpK[(size_t)p * N * 6 + i * 6 + lane], xp[i], bk);
-                s_part[warp][lane] = bk;
-            }
-        }
-        if (lane < N) y[(size_t)p * N + lane] = mine;
-        const double dot = warp_sum(lane < N ? xm * mine : 0.0);
-        if (lane == 0) s_part[warp][6] = dot;
-    }
-    __syncthreads();
-    if (threadIdx.x < kPcgCols) {
-        double s = 0.0;
-        if (threadIdx.x < 7)
-#pragma unroll
-            for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w][threadIdx.x];
-        cta_part[(size_t)blockIdx.x * kPcgCols + threadIdx.x] = s;
+        stg256(v4 + 4 * (size_t)slot, jl[0] * s0 + jl[3] * s1, jl[1] * s0 + jl[4] * s1, jl[2] * s0 + jl[5] * s1, 0.0);
     }
 }
 
 // Sum the rows of part[R][W] (W = 1 or 8) with all 1024 threads of the block: each thread strides over rows with
 // four independent accumulators (memory-level parallelism), then a fixed shared-memory tree.  out[W] valid after return.
-template <int W>
-__device__ __forceinline__ void block_sum_cols(const double* __restrict__ part, int R, double* out, double* scratch) {
-    constexpr int RL = kReduceThreads / W;
+template <bool CG>
+__device__ __forceinline__ double ld_part(const double* p) { return CG ? __ldcg(p) : *p; }
+
+template <int W, int T = kReduceThreads, bool CG = true>   // CG = false: `part` is in shared memory
+__device__ __forceinline__ void block_sum_cols(const double* part, int R, double* out, double* scratch) {
+    // T threads.  Loads go to L2 (__ldcg): in the fused "last CTA" callers the partials were written by other SMs of the
+    // same launch.
+    constexpr int RL = T / W;
     const int t = threadIdx.x, col = t % W, rl = t / W;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int r = rl;
     for (; r + 3 * RL < R; r += 4 * RL) {
-        a0 += part[(size_t)r * W + col]; a1 += part[(size_t)(r + RL) * W + col];
-        a2 += part[(size_t)(r + 2 * RL) * W + col]; a3 += part[(size_t)(r + 3 * RL) * W + col];
+        a0 += ld_part<CG>(part + (size_t)r * W + col); a1 += ld_part<CG>(part + (size_t)(r + RL) * W + col);
+        a2 += ld_part<CG>(part + (size_t)(r + 2 * RL) * W + col); a3 += ld_part<CG>(part + (size_t)(r + 3 * RL) * W + col);
     }
-    for (; r < R; r += RL) a0 += part[(size_t)r * W + col];
+    for (; r < R; r += RL) a0 += ld_part<CG>(part + (size_t)r * W + col);
     scratch[t] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     for (int s = RL / 2; s > 0; s >>= 1) {
@@ -1699,15 +1565,124 @@ pcg_signal_kernel(PeerComm pcm, const double* __restrict__ partC, int nC, const 
 //   partC: CTA partials of pass C [nC][32] (cols 0..5 = sum B_pK^T p_p, col 6 = sum p_p.y_p)
 //   partB: block partials of pass B [nB][32] (cols 0..5 = sum W_Kj u_j)
 // Multi-GPU: the partial sums have been all-reduced already and arrive as a single row each (nC = nB = 1).
+struct MidArgs {
+    int P, N;
+    double lambda_val;
+    const double* lambda_dev;
+    const double *partC, *partB;
+    int nC, nB;
+    const double *BKK, *MinvK;
+    double *p, *x, *r, *z, *yK_out, *scal;
+    int* done;
+    double* rcK;
+};
+
+// T threads of one CTA.  In shared memory: scratch[T], sc/sb, sh.
+template <int T>
+__device__ __forceinline__ void pcg_mid_body(const MidArgs& a) {
+    const double lambda = a.lambda_dev ? *a.lambda_dev : a.lambda_val;
+    __shared__ double scratch[T];
+    __shared__ double sc[kPcgCols], sb[kPcgCols];
+    __shared__ double sh[16];
+    const int lane = threadIdx.x & 31, P = a.P, N = a.N;
+    block_sum_cols<kPcgCols, T>(a.partC, a.nC, sc, scratch);
+    block_sum_cols<kPcgCols, T>(a.partB, a.nB, sb, scratch);
+    const double c = lane < kPcgCols ? sc[lane] : 0.0;
+    const double b = lane < kPcgCols ? sb[lane] : 0.0;
+    double* pK = a.p + (size_t)P * N;
+    if (threadIdx.x < 32) {
+        double yk = 0.0;
+        if (lane < 6) {
+            yk = lambda * pK[lane] + c - b;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) yk += a.BKK[6 * lane + i] * pK[i];
+        }
+        double dot = lane < 6 ? yk * pK[lane] : 0.0;
+        dot = warp_sum(dot);
+        const double cdot = __shfl_sync(kFull, c, 6);
+        const double pSp = cdot + dot;
+        const double alpha = a.scal[2] / pSp;
+        if (lane == 0) { a.scal[0] = alpha; a.scal[4] = pSp; if (!(pSp > 0)) { a.scal[6] = 1.0; } }
+        double rk = 0.0;
+        if (lane < 6) {
+            a.yK_out[lane] = yk;
+            a.x[(size_t)P * N + lane] += alpha * pK[lane];
+            rk = a.r[(size_t)P * N + lane] - alpha * yk;
+            a.r[(size_t)P * N + lane] = rk;
+            if (a.rcK) a.rcK[lane] = rk;
+            sh[lane] = rk;
+        }
+        __syncwarp();
+        if (lane < 6) {
+            double zk = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) zk += a.MinvK[6 * lane + i] * sh[i];
+            a.z[(size_t)P * N + lane] = zk;
+            sh[8 + lane] = zk * rk;
+        }
+        __syncwarp();
+        if (lane == 0) a.scal[7] = sh[8] + sh[9] + sh[10] + sh[11] + sh[12] + sh[13];   // r_K . z_K
+    }
+}
+
+// "Last CTA" hand-over: every thread has made its global writes visible (__threadfence), the CTA takes a ticket, and the
+// CTA that draws the last one runs the single-CTA tail of the step inside the same launch (saves a kernel boundary of
+// ~8 us per fused pair in the PCG loop).  The partial sums are combined in a fixed order by that one CTA, so the result
+// does not depend on which CTA it is.
+__device__ __forceinline__ bool last_cta_arrives(unsigned* ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const bool last = atomicAdd(ticket, 1u) == total - 1;
+        if (last) *ticket = 0;   // ready for the next launch
+        s_last = last ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// Two-level variant for kernels with thousands of CTAs: CTAs are grouped by 32 (consecutive blockIdx); the CTA that
+// completes a group sums the group's partial rows [8 columns] in row order into grp_rows[g]; the CTA that completes the
+// last group gets `true`.  tickets: [nGroups + 1] counters that return to zero.  The consumer then reads nGroups rows
+// instead of gridDim.x rows -- short enough for a 128-thread tail.
+constexpr int kRowGroup = 32;
+__device__ __forceinline__ bool grouped_rows_reduce(const double* cta_part, double* grp_rows, unsigned* tickets) {
+    __shared__ int s_flag;
+    const int nCta = gridDim.x, nGroups = (nCta + kRowGroup - 1) / kRowGroup;
+    const int g = blockIdx.x / kRowGroup, g0 = g * kRowGroup, gsize = min(kRowGroup, nCta - g0);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool last = atomicAdd(tickets + g, 1u) == (unsigned)(gsize - 1);
+        if (last) tickets[g] = 0;
+        s_flag = last ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_flag) return false;
+    __threadfence();
+    if (threadIdx.x < kPcgCols) {
+        double t = 0.0;
+        for (int r = 0; r < gsize; ++r) t += __ldcg(cta_part + (size_t)(g0 + r) * kPcgCols + threadIdx.x);
+        grp_rows[(size_t)g * kPcgCols + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool last = atomicAdd(tickets + nGroups, 1u) == (unsigned)(nGroups - 1);
+        if (last) tickets[nGroups] = 0;
+        s_flag = last ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_flag) __threadfence();
+    return s_flag != 0;
+}
+
 __global__ void __launch_bounds__(kReduceThreads)
-pcg_mid_kernel(int P, int N, double lambda_val, const double* __restrict__ lambda_dev, const double* __restrict__ partC, int nC,
-               const double* __restrict__ partB, int nB,
-               const double* __restrict__ BKK, const double* __restrict__ MinvK, double* __restrict__ p, double* __restrict__ x,
-               double* __restrict__ r, double* __restrict__ z, double* __restrict__ yK_out, double* __restrict__ scal, int* __restrict__ done,
-               double* __restrict__ rcK, PeerComm pcm, double* __restrict__ rows_local) {
-    if (*done) return;
-    const double lambda = lambda_dev ? *lambda_dev : lambda_val;
-    __shared__ double scratch[kReduceThreads];
+pcg_mid_kernel(MidArgs a, PeerComm pcm, double* __restrict__ rows_local) {
+    if (*a.done) return;
     if (pcm.world > 1) {
         // wait until every peer has published this iteration's partial product, then sum the K-row partials of all ranks
         const unsigned seq = *pcm.ctr;
@@ -1723,46 +1698,145 @@ pcg_mid_kernel(int P, int N, double lambda_val, const double* __restrict__ lambd
         if (threadIdx.x < 2 * kPartCols) rows_local[threadIdx.x] = peer_sum(pcm, seq, pcm.row_off + threadIdx.x);
         __syncthreads();
     }
-    __shared__ double sc[kPcgCols], sb[kPcgCols];
-    __shared__ double sh[16];
-    const int lane = threadIdx.x & 31;
-    block_sum_cols<kPcgCols>(partC, nC, sc, scratch);
-    block_sum_cols<kPcgCols>(partB, nB, sb, scratch);
-    const double c = lane < kPcgCols ? sc[lane] : 0.0;
-    const double b = lane < kPcgCols ? sb[lane] : 0.0;
-    double* pK = p + (size_t)P * N;
-    if (threadIdx.x < 32) {
-        double yk = 0.0;
-        if (lane < 6) {
-            yk = lambda * pK[lane] + c - b;
+    pcg_mid_body<kReduceThreads>(a);
+}
+
+// pass B (landmark-major): u_j = Cinv_j (sum_k v + W_Kj^T x_K) [or cg_j - that, for back-substitution];
+// block partials of sum_j W_Kj u_j.   Eight lanes per landmark (as in K2a): lane s sums slots s, s+8, ... of the
+// landmark's contiguous v segment (one 32-byte sector per load, 256 B per group and step), lane r < 6 owns row r of
+// W_Kj; xor-folds over the group in a fixed order.
+constexpr int kPassBThreads = 256;
+constexpr int kPassBLmPerBlock = kPassBThreads / kLmLanes;
+template <bool BACKSUB>
+__global__ void __launch_bounds__(kPassBThreads)
+schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const double* __restrict__ v4,
+                    const double* __restrict__ WK, const double* __restrict__ Cinv, const double* __restrict__ xK,
+                    const int* __restrict__ done, const double* __restrict__ cg4, double* __restrict__ u4, double* __restrict__ blk_part,
+                    double* __restrict__ grp_rows, unsigned* __restrict__ grp_tickets) {
+    if (done && *done) return;
+    const int j = blockIdx.x * kPassBLmPerBlock + (threadIdx.x >> 3);
+    const int sub = threadIdx.x & 7;
+    double tx = 0, ty = 0, tz = 0, w0 = 0, w1 = 0, w2 = 0;
+    if (j < L) {
+        const int k0 = lm_ptr[j], k1 = lm_ptr[j + 1];
+        for (int k = k0 + sub; k < k1; k += kLmLanes) {
+            const d4 a = ldg256(v4 + 4 * (size_t)k);
+            tx += a.x; ty += a.y; tz += a.z;
+        }
+        if (sub < 6) {
+            w0 = WK[18 * (size_t)j + 3 * sub]; w1 = WK[18 * (size_t)j + 3 * sub + 1]; w2 = WK[18 * (size_t)j + 3 * sub + 2];
+            const double xk = xK[sub];
+            tx += w0 * xk; ty += w1 * xk; tz += w2 * xk;
+        }
+    }
 #pragma unroll
-            for (int i = 0; i < 6; ++i) yk += BKK[6 * lane + i] * pK[i];
-        }
-        double dot = lane < 6 ? yk * pK[lane] : 0.0;
-        dot = warp_sum(dot);
-        const double cdot = __shfl_sync(kFull, c, 6);
-        const double pSp = cdot + dot;
-        const double alpha = scal[2] / pSp;
-        if (lane == 0) { scal[0] = alpha; scal[4] = pSp; if (!(pSp > 0)) { scal[6] = 1.0; } }
-        double rk = 0.0;
-        if (lane < 6) {
-            yK_out[lane] = yk;
-            x[(size_t)P * N + lane] += alpha * pK[lane];
-            rk = r[(size_t)P * N + lane] - alpha * yk;
-            r[(size_t)P * N + lane] = rk;
-            if (rcK) rcK[lane] = rk;
-            sh[lane] = rk;
-        }
-        __syncwarp();
-        if (lane < 6) {
-            double zk = 0.0;
+    for (int o = 4; o > 0; o >>= 1) { tx += __shfl_xor_sync(kFull, tx, o); ty += __shfl_xor_sync(kFull, ty, o); tz += __shfl_xor_sync(kFull, tz, o); }
+    double wu = 0.0;
+    if (j < L) {
+        const double* ci = Cinv + 6 * (size_t)j;
+        double ux, uy, uz;
+        sym3_mul(ci, tx, ty, tz, ux, uy, uz);
+        if (BACKSUB) { const d4 c = ldg256(cg4 + 4 * (size_t)j); ux = c.x - ux; uy = c.y - uy; uz = c.z - uz; }
+        if (sub == 0) stg256(u4 + 4 * (size_t)j, ux, uy, uz, 0.0);
+        wu = w0 * ux + w1 * uy + w2 * uz;   // lane r < 6: (W_Kj u_j)_r ; lanes 6, 7: 0
+    }
+    if (BACKSUB) return;
+    // block partial of sum_j W_Kj u_j: same-row lanes of the warp's four landmarks, then the four warps
+    wu += __shfl_xor_sync(kFull, wu, 8);
+    wu += __shfl_xor_sync(kFull, wu, 16);
+    __shared__ double s[kPassBThreads / 32][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 8) s[warp][lane] = wu;
+    __syncthreads();
+    if (threadIdx.x < kPcgCols) {
+        double t = 0.0;
+        if (threadIdx.x < 6)
 #pragma unroll
-            for (int i = 0; i < 6; ++i) zk += MinvK[6 * lane + i] * sh[i];
-            z[(size_t)P * N + lane] = zk;
-            sh[8 + lane] = zk * rk;
+            for (int w = 0; w < kPassBThreads / 32; ++w) t += s[w][threadIdx.x];
+        blk_part[(size_t)blockIdx.x * kPcgCols + threadIdx.x] = t;
+    }
+    if (grp_tickets) grouped_rows_reduce(blk_part, grp_rows, grp_tickets);
+}
+
+// pass C (pose-major): yloc_p = - sum_m J_q^T (J_l u_j); then (if add_diag) y_p = (B_pp + lambda) x_p + B_pK x_K + yloc_p.
+// CTA partial row: [ sum_p B_pK^T x_p (6) | sum_p x_p . y_p (1) ]
+template <int N>
+__global__ void __launch_bounds__(kCtaThreads)
+schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int* __restrict__ pose_ptr, const int* __restrict__ p_lm,
+                    const double2* __restrict__ J, const double* __restrict__ u4, const double* __restrict__ x, const double* __restrict__ Bpp,
+                    const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part,
+                    const double* __restrict__ lambda_dev, const double* __restrict__ chain, const double* __restrict__ lml,
+                    const unsigned* __restrict__ xctr, double* __restrict__ xbase, long long xstride, double* __restrict__ grp_rows,
+                    unsigned* __restrict__ grp_tickets, int fuse_mid, MidArgs mid) {
+    if (done && *done) return;
+    if (xctr) y = xbase + (size_t)((*xctr + 1u) & 1u) * xstride;   // multi-GPU: the next exchange slot of this rank
+    const double lambda = lambda_dev ? *lambda_dev : lambda_val;   // device-resident inside the captured PCG graph
+    __shared__ double s_part[kWarpsPerCta][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWarpsPerCta + warp;
+    if (lane < 8) s_part[warp][lane] = 0.0;
+    if (p < P) {
+        double ut[6] = {0, 0, 0, 0, 0, 0};   // U = sum l x t | T = sum t over this lane's observations
+        const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
+        for (int k = k0 + lane; k < k1; k += 32) {
+            double jl[6];
+            load_jl<N>(J, M, k, jl);
+            const int j = __ldg(p_lm + k);
+            const d4 u = ldg256(u4 + 4 * (size_t)j);
+            const d4 l = ldg256(lml + 4 * (size_t)j);
+            const double e0 = jl[0] * u.x + jl[1] * u.y + jl[2] * u.z, e1 = jl[3] * u.x + jl[4] * u.y + jl[5] * u.z;
+            const double t0 = jl[0] * e0 + jl[3] * e1, t1 = jl[1] * e0 + jl[4] * e1, t2 = jl[2] * e0 + jl[5] * e1;
+            ut[0] += l.y * t2 - l.z * t1; ut[1] += l.z * t0 - l.x * t2; ut[2] += l.x * t1 - l.y * t0;
+            ut[3] += t0; ut[4] += t1; ut[5] += t2;
         }
-        __syncwarp();
-        if (lane == 0) scal[7] = sh[8] + sh[9] + sh[10] + sh[11] + sh[12] + sh[13];   // r_K . z_K
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ut[i] = warp_sum(ut[i]);
+        double mine = 0.0;   // lane c keeps component c
+        if (lane < N) {
+            const double* c = chain + (size_t)p * 6 * N + 6 * lane;
+            const double a0 = c[0], a1 = c[1], a2 = c[2], o0 = c[3], o1 = c[4], o2 = c[5];
+            const double m0 = a1 * o2 - a2 * o1, m1 = a2 * o0 - a0 * o2, m2 = a0 * o1 - a1 * o0;
+            mine = (a0 * ut[0] + a1 * ut[1] + a2 * ut[2]) - (m0 * ut[3] + m1 * ut[4] + m2 * ut[5]);
+        }
+        double xm = lane < N ? x[(size_t)p * N + lane] : 0.0;
+        if (add_diag) {
+            double xp[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) xp[i] = __shfl_sync(kFull, xm, i);
+            if (lane < N) {
+                const double* B = Bpp + (size_t)p * N * N + lane * N;
+                const double* BK = BpK + (size_t)p * N * 6 + lane * 6;
+                const double* xK = x + (size_t)P * N;
+                double t = lambda * xm;
+#pragma unroll
+                for (int i = 0; i < N; ++i) t = fma(B[i], xp[i], t);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) t = fma(BK[i], xK[i], t);
+                mine += t;
+            }
+            // B_pK^T x_p : lane c < 6 takes column c
+            double bk = 0.0;
+            if (lane < 6) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) bk = fma(BpK[(size_t)p * N * 6 + i * 6 + lane], xp[i], bk);
+                s_part[warp][lane] = bk;
+            }
+        }
+        if (lane < N) y[(size_t)p * N + lane] = mine;
+        const double dot = warp_sum(lane < N ? xm * mine : 0.0);
+        if (lane == 0) s_part[warp][6] = dot;
+    }
+    __syncthreads();
+    if (threadIdx.x < kPcgCols) {
+        double s = 0.0;
+        if (threadIdx.x < 7)
+#pragma unroll
+            for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w][threadIdx.x];
+        cta_part[(size_t)blockIdx.x * kPcgCols + threadIdx.x] = s;
+    }
+    if (grp_tickets) {
+        const bool fin = grouped_rows_reduce(cta_part, grp_rows, grp_tickets);
+        if (fin && fuse_mid) pcg_mid_body<kCtaThreads>(mid);   // single GPU: alpha and the K rows in the same launch
     }
 }
 
@@ -1821,39 +1895,83 @@ pcg_update_kernel(int P, const double* __restrict__ p, const double* __restrict_
     }
 }
 
-// rz_new, beta, convergence test, p_K <- z_K + beta p_K.  One block of 256 threads.
-__global__ void __launch_bounds__(kReduceThreads)
-pcg_end_kernel(int P, int N, const double* __restrict__ part, int nPart, double tol2, int max_iters, double* __restrict__ p,
-               double* __restrict__ z, double* __restrict__ scal, int* __restrict__ done, const double* __restrict__ rc,
-               const double* __restrict__ zc, int nz, int nC, int nA, int S) {
-    if (*done) return;
-    __shared__ double scratch[kReduceThreads];
+// rz_new, beta, convergence test, p_K <- z_K + beta p_K.  One CTA of T threads.
+struct EndArgs {
+    int P, N;
+    const double* part;
+    int nPart;
+    double tol2;
+    int max_iters;
+    double *p, *z, *scal;
+    int* done;
+    const double *rc, *zc;
+    int nz, nC, nA, S;
+};
+
+template <int T>
+__device__ __forceinline__ void pcg_end_body(const EndArgs& a) {
+    __shared__ double scratch[T];
     __shared__ double so[1];
-    const int lane = threadIdx.x & 31;
-    block_sum_cols<1>(part, nPart, so, scratch);
+    const int lane = threadIdx.x & 31, P = a.P, N = a.N;
+    block_sum_cols<1, T>(a.part, a.nPart, so, scratch);
     double t = so[0];
-    if (rc) {   // r . (Z zc) = (Z^T r) . zc ; and the K rows of z get their coarse part
-        __shared__ double prod[kReduceThreads];
-        double a = 0.0;
-        for (int i = threadIdx.x; i < nC * N + 6; i += kReduceThreads) a += rc[i] * zc[coarse_index_of(i, nC, nA, N, S)];
-        prod[threadIdx.x] = a;
+    if (a.rc) {   // r . (Z zc) = (Z^T r) . zc ; and the K rows of z get their coarse part
+        __shared__ double prod[T];
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < a.nC * N + 6; i += T) acc += __ldcg(a.rc + i) * __ldcg(a.zc + coarse_index_of(i, a.nC, a.nA, N, a.S));
+        prod[threadIdx.x] = acc;
         __syncthreads();
-        block_sum_cols<1>(prod, kReduceThreads, so, scratch);
+        block_sum_cols<1, T, false>(prod, T, so, scratch);
         t += so[0];
-        if (threadIdx.x < 6) z[(size_t)P * N + threadIdx.x] += zc[nz - 6 + threadIdx.x];
+        if (threadIdx.x < 6) a.z[(size_t)P * N + threadIdx.x] += __ldcg(a.zc + a.nz - 6 + threadIdx.x);
         __syncthreads();
     }
     if (threadIdx.x < 32) {
-        const double rz_new = t + scal[7];
-        const double beta = rz_new / scal[2];
-        const double it = scal[5] + 1.0;
-        if (lane < 6) p[(size_t)P * N + lane] = z[(size_t)P * N + lane] + beta * p[(size_t)P * N + lane];
+        const double rz_new = t + a.scal[7];
+        const double beta = rz_new / a.scal[2];
+        const double it = a.scal[5] + 1.0;
+        if (lane < 6) a.p[(size_t)P * N + lane] = a.z[(size_t)P * N + lane] + beta * a.p[(size_t)P * N + lane];
         __syncwarp();
         if (lane == 0) {
-            scal[1] = beta; scal[2] = rz_new; scal[5] = it;
-            if (!(rz_new > tol2 * scal[3]) || it >= max_iters || scal[6] != 0.0) *done = 1;
+            a.scal[1] = beta; a.scal[2] = rz_new; a.scal[5] = it;
+            if (!(rz_new > a.tol2 * a.scal[3]) || it >= a.max_iters || a.scal[6] != 0.0) *a.done = 1;
         }
     }
+}
+
+__global__ void __launch_bounds__(kReduceThreads) pcg_end_kernel(EndArgs a) {
+    if (*a.done) return;
+    pcg_end_body<kReduceThreads>(a);
+}
+
+// zc = Einv(fp32, full symmetric, row-major) * x, one warp per row, fp64 accumulation.  x is the restriction itself
+// (one cluster per aggregate) or its aggregated copy written by coarse_aggregate_kernel.  With a ticket, the CTA that
+// finishes last also runs the end-of-iteration step (pcg_end_body) in the same launch.
+__global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
+                                                              int n, const int* __restrict__ done, const double* __restrict__ alpha,
+                                                              EndArgs end, unsigned* ticket) {
+    if (done && *done) return;
+    const double scale = alpha ? *alpha : 1.0;   // scalar re-fit of a reused (stale) coarse inverse, see coarse_refit_kernel
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + warp;
+    if (row < n) {
+        const float* a = A + (size_t)row * n;
+        double acc0 = 0.0, acc1 = 0.0;
+        int i = lane * 2;
+        for (; i + 64 + 1 < n; i += 128) {
+            const float2 u = *reinterpret_cast<const float2*>(a + i);
+            const float2 v = *reinterpret_cast<const float2*>(a + i + 64);
+            acc0 = fma((double)u.x, x[i], fma((double)u.y, x[i + 1], acc0));
+            acc1 = fma((double)v.x, x[i + 64], fma((double)v.y, x[i + 65], acc1));
+        }
+        for (; i < n; i += 64) {
+            acc0 = fma((double)a[i], x[i], acc0);
+            if (i + 1 < n) acc0 = fma((double)a[i + 1], x[i + 1], acc0);
+        }
+        const double t = warp_sum(acc0 + acc1);
+        if (lane == 0) y[row] = scale * t;
+    }
+    if (ticket && last_cta_arrives(ticket)) pcg_end_body<128>(end);
 }
 
 // PCG start: x = 0, r = rhs, z = Minv r, p = z, CTA partials of r.z  (one warp per keyframe); K part by block 0 / warp 0 extra.
@@ -1918,7 +2036,7 @@ pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __
         for (int i = threadIdx.x; i < nC * N + 6; i += kReduceThreads) a += rc[i] * zc[coarse_index_of(i, nC, nA, N, S)];
         prod[threadIdx.x] = a;
         __syncthreads();
-        block_sum_cols<1>(prod, kReduceThreads, so, scratch);
+        block_sum_cols<1, kReduceThreads, false>(prod, kReduceThreads, so, scratch);
         t += so[0];
         if (threadIdx.x < 6) { const double v = zK[threadIdx.x] + zc[nz - 6 + threadIdx.x]; zK[threadIdx.x] = v; pK[threadIdx.x] = v; }
         __syncthreads();
@@ -2025,13 +2143,11 @@ error_proj_kernel(Camera cm, int64_t M, const int* __restrict__ p_pose, const in
         const int p = __ldg(p_pose + k), j = __ldg(p_lm + k);
         const double2 z = ldg2(p_uv + k);
         double R[12];
-        const double2* cp = reinterpret_cast<const double2*>(cam + (size_t)p * 12);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { const double2 t = ldg2(cp + i); R[2 * i] = t.x; R[2 * i + 1] = t.y; }
-        const double2 l01 = ldg2(reinterpret_cast<const double2*>(lm4 + 4 * (size_t)j));
-        const double lz = __ldg(lm4 + 4 * (size_t)j + 2);
+        for (int i = 0; i < 3; ++i) { const d4 t = ldg256(cam + (size_t)p * 12 + 4 * i); R[4 * i] = t.x; R[4 * i + 1] = t.y; R[4 * i + 2] = t.z; R[4 * i + 3] = t.w; }
+        const d4 lq = ldg256(lm4 + 4 * (size_t)j);
         ProjOut o;
-        project_factor<false, false>(cm, R, R + 9, l01.x, l01.y, lz, z.x, z.y, o);
+        project_factor<false, false>(cm, R, R + 9, lq.x, lq.y, lq.z, z.x, z.y, o);
         e = o.err;
     }
     __shared__ double s[8];

@@ -42,8 +42,8 @@ def algorithmic_bytes(kid, N, P, L, M):
         return M * (16 + 4) + P * 96 + L * (32 + 24) + L * 8 * (6 + 3 + 18)
     if kid == 3:   # J_l planes + landmark index + slot index in, v (padded 32 B) out; landmark table, FK rows, p, z in, p out
         return M * (48 + 4 + 4 + 32) + L * 32 + P * 8 * (6 * N + 3 * N)
-    if kid == 4:   # v + permutation in; W_K, Cinv in, u out
-        return M * (32 + 4) + L * 8 * (18 + 6) + L * 32
+    if kid == 4:   # v segments (one 32-byte slot per observation) + segment pointers in; W_K, Cinv in, u out
+        return M * 32 + L * (4 + 8 * (18 + 6) + 32)
     if kid == 5:   # J_l planes + landmark index in; u table + landmark table in; FK rows, B_pp, B_pK, x in, y out
         return M * (48 + 4) + L * 64 + P * 8 * (6 * N + N * N + 6 * N + 2 * N)
     if kid in (6, 7):   # uv + 2 indices in; camera rows + landmark table in
