@@ -129,6 +129,8 @@ struct asc_handle {
     asc_params prm;
     int dev = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;              // side stream: cluster blocks run beside the coarse factorisation (single GPU)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int N = 0, P = 0, L = 0;
     int64_t M = 0;
@@ -390,14 +392,24 @@ struct Engine {
         landmark_invert_kernel<<<h->nBlkLm, 128, 0, h->stream>>>(h->L, lambda, h->C, h->gl, h->WK, h->Cinv, h->cg4, h->partL, h->flags + 1);
         CUDA_TRY(cudaGetLastError());
         DBG_SYNC(h, "landmark_invert");
+        // Single GPU: the cluster blocks (cluster_schur + cluster_invert, ~3 ms on C2) depend only on the landmark inverses, and
+        // so does the coarse operator (assembly + cuSOLVER factorisation, ~25 ms): the former run on a side stream beside the
+        // latter and are joined at the end of prepare().  Multi-GPU keeps one stream (the blocks go through an all-reduce).
+        static const bool no_side = getenv("ASC_NO_SIDE_STREAM") != nullptr;
+        const bool side = h->world == 1 && h->use_clusters && !no_side;
+        cudaStream_t cs = side ? h->stream2 : h->stream;
+        if (side) {
+            CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));
+            CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+        }
         if (h->use_clusters && !h->dup_obs) {
             const size_t sm = sizeof(double) * ((size_t)h->nmax * (h->nmax | 1) + h->nmax + 2 * (size_t)h->gmax * 3 * N) + sizeof(int) * (h->gmax + 2);
-            cluster_schur_cta_kernel<N><<<h->nC, 256, sm, h->stream>>>(lambda, h->rank == 0 ? 1 : 0, h->gmax, h->cl_ptr, h->cl_off, h->cl_inc_ptr, h->cl_inc,
+            cluster_schur_cta_kernel<N><<<h->nC, 256, sm, cs>>>(lambda, h->rank == 0 ? 1 : 0, h->gmax, h->cl_ptr, h->cl_off, h->cl_inc_ptr, h->cl_inc,
                                                                       h->inc_lo, h->inc_hi, h->inc_lm, h->l_pose, h->l_perm, h->Wm, h->Cinv, h->cg4, h->Bpp,
                                                                       h->Dloc, h->rloc);
         } else if (h->use_clusters) {
             const size_t sm = sizeof(double) * kWarpsPerCta * ((size_t)N * h->nmax + 3 * N);
-            cluster_schur_kernel<N><<<h->nCtaPose, kCtaThreads, sm, h->stream>>>(h->P, lambda, h->rank == 0 ? 1 : 0, h->nmax, h->pose_ptr, h->p_lm,
+            cluster_schur_kernel<N><<<h->nCtaPose, kCtaThreads, sm, cs>>>(h->P, lambda, h->rank == 0 ? 1 : 0, h->nmax, h->pose_ptr, h->p_lm,
                                                                                h->p_run_lo, h->p_run_hi, h->l_pose, h->l_perm, h->Wm, h->Cinv, h->cg4,
                                                                                h->Bpp, h->pose_cluster, h->cl_ptr, h->cl_off, h->Dloc, h->rloc);
         } else {
@@ -405,6 +417,12 @@ struct Engine {
                                                                                                   h->Dloc, h->rloc);
         }
         CUDA_TRY(cudaGetLastError());
+        if (side) {   // the inverse of the blocks follows directly; the main stream waits for ev_join before it returns
+            const size_t smi = sizeof(double) * (size_t)h->nmax * (h->nmax | 1);
+            cluster_invert_kernel<<<h->nC, 256, smi, cs>>>(N, h->cl_ptr, h->cl_off, h->Dloc, h->gr, h->rloc, h->Mc, h->rhs, h->flags + 2);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(h->ev_join, h->stream2));
+        }
         DBG_SYNC(h, "cluster_schur / pose_schur_diag");
         const int nR1 = std::min(64, h->nBlkLm), rpb = cdiv(h->nBlkLm, nR1);
         reduce_rows_kernel<<<cdiv(h->nBlkLm, rpb), 256, 0, h->stream>>>(h->partL, h->nBlkLm, 27, kPartCols, rpb, h->partR);
@@ -424,7 +442,7 @@ struct Engine {
         DBG_SYNC(h, "k_rows");
         if (h->use_clusters) {
             const size_t sm = sizeof(double) * (size_t)h->nmax * (h->nmax | 1);
-            cluster_invert_kernel<<<h->nC, 256, sm, h->stream>>>(N, h->cl_ptr, h->cl_off, h->Dloc, h->gr, h->rloc, h->Mc, h->rhs, h->flags + 2);
+            if (!side) cluster_invert_kernel<<<h->nC, 256, sm, h->stream>>>(N, h->cl_ptr, h->cl_off, h->Dloc, h->gr, h->rloc, h->Mc, h->rhs, h->flags + 2);
             DBG_SYNC(h, "cluster_invert");
             // The coarse operator is only a preconditioner: any SPD E^-1 keeps PCG exact, so a factorisation from an
             // earlier lambda / linearisation is reused until it visibly costs iterations (deterministic policy).
@@ -503,6 +521,7 @@ struct Engine {
             pose_invert_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, lambda, h->Bpp, h->gr, h->Dloc, h->rloc, h->Minv, h->rhs, h->flags + 2);
         }
         CUDA_TRY(cudaGetLastError());
+        if (side) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         h->lin_lambda = lambda;
         return ASC_OK;
     }
@@ -1206,6 +1225,9 @@ int asc_create(const asc_params* params, asc_handle** out) {
     h->prm = *params;
     h->dev = dev;
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     for (auto& ev : h->ev) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMallocHost((void**)&h->h_status, 64 * sizeof(double)));
     CUDA_TRY(cudaMallocHost((void**)&h->h_flags, 16 * sizeof(int)));
@@ -1245,6 +1267,9 @@ int asc_destroy(asc_handle* h) {
     for (auto& ev : h->prof_ev) cudaEventDestroy(ev);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return ASC_OK;
