@@ -147,6 +147,8 @@ struct asc_handle {
     // peer-memory exchange of the PCG loop (kernels.cuh, PeerComm): one IPC-shared buffer per rank
     PeerComm pcm{};
     bool p2p_ok = false;
+    bool coarse_sharded = false;    // E^-1 rows are split over the ranks (valid while coarse_f32_active)
+    int crow0 = 0, crows = 0, crows_per_rank = 0;
     char* xbuf = nullptr;           // this rank's exchange buffer [flags 256 B | slot 0 | slot 1]
     size_t xbuf_bytes = 0;
     void* peer_map[kMaxPeers] = {nullptr};   // cudaIpcOpenMemHandle mappings of the peers' buffers
@@ -492,9 +494,18 @@ struct Engine {
                             return fail(ASC_ERR_CUDA, "cusolverDnSpotrf failed: status %d, lwork %d, cuda: %s", (int)st, h->lworkf, cudaGetErrorString(cudaGetLastError()));
                     }
                     if (timing) cudaEventRecord(e1, h->stream);
-                    // E^-1 = solve(U^T U, I): two TRSMs run much closer to peak than cuSOLVER's potri
-                    identity_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->Einvf, nz);
-                    if (cusolverDnSpotrs(h->solver, CUBLAS_FILL_MODE_UPPER, nz, nz, h->Ef, nz, h->Einvf, nz, h->flags + 7) != CUSOLVER_STATUS_SUCCESS)
+                    // E^-1 = solve(U^T U, I): two TRSMs run much closer to peak than cuSOLVER's potri.
+                    // Multi-GPU with the peer exchange: every rank solves only for ITS columns of the identity = its rows of
+                    // the (symmetric) inverse, which is all its share of the per-iteration product needs.
+                    h->coarse_sharded = h->world > 1 && h->p2p_ok && getenv("ASC_NO_COARSE_SHARD") == nullptr;
+                    h->crows_per_rank = h->coarse_sharded ? (cdiv(nz, h->world) + 3) / 4 * 4 : nz;
+                    h->crow0 = h->coarse_sharded ? std::min(nz, h->rank * h->crows_per_rank) : 0;
+                    h->crows = h->coarse_sharded ? std::max(0, std::min(nz, h->crow0 + h->crows_per_rank) - h->crow0) : nz;
+                    if (h->coarse_sharded && h->rank == h->world - 1) h->crows = nz - h->crow0;
+                    if (h->coarse_sharded) identity_slice_f32_kernel<<<cdiv((int64_t)nz * std::max(h->crows, 1), 256), 256, 0, h->stream>>>(h->Einvf, nz, h->crow0, h->crows);
+                    else identity_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->Einvf, nz);
+                    if (h->crows > 0 &&
+                        cusolverDnSpotrs(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->crows, h->Ef, nz, h->Einvf, nz, h->flags + 7) != CUSOLVER_STATUS_SUCCESS)
                         return fail(ASC_ERR_CUDA, "cusolverDnSpotrs failed");
                     CUDA_TRY(cudaGetLastError());
                     int info[2] = {0, 0};
@@ -503,6 +514,7 @@ struct Engine {
                     f32_ok = info[0] == 0 && info[1] == 0;   // not positive definite in fp32: redo in fp64 below
                 }
                 h->coarse_f32_active = f32_ok;
+                if (!f32_ok) h->coarse_sharded = false;   // the fp64 fallback keeps the full inverse on every rank
                 if (!f32_ok) {
                     if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 4) != CUSOLVER_STATUS_SUCCESS)
                         return fail(ASC_ERR_CUDA, "cusolverDnDpotrf failed");
@@ -568,8 +580,17 @@ struct Engine {
         }
         if (h->coarse_f32_active) {
             EndArgs none{};
-            coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9, end ? *end : none,
-                                                                         end ? h->tickG : nullptr);
+            if (h->coarse_sharded) {   // own rows -> exchange slot; publish, wait, gather (kernels.cuh, coarse_exchange_kernel)
+                if (h->crows > 0)
+                    coarse_gemv_f32_kernel<<<cdiv(h->crows, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9, none, nullptr,
+                                                                                   h->crow0, h->crows, h->pcm.ctr + 1, h->pcm.x[h->rank] + h->pcm.zoff,
+                                                                                   h->pcm.zstride);
+                coarse_exchange_kernel<<<1, 1024, 0, h->stream>>>(h->pcm, h->nz, h->crows_per_rank, h->zc, done);
+                h->launches += 1;
+            } else {
+                coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9, end ? *end : none,
+                                                                             end ? h->tickG : nullptr, 0, h->nz, nullptr, nullptr, 0);
+            }
             CUDA_TRY(cudaGetLastError());
         } else {
             const double one = 1.0, zero = 0.0;
@@ -587,13 +608,24 @@ struct Engine {
         const double tol2_ = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
         // A rejected LM step is re-solved with a 10x larger lambda on the same linearisation; while lambda is far below the
         // spectrum of S the solution hardly moves, so start from it (GTSAM refactorises from scratch each time).
-        const bool warm = h->warm_ok && h->use_clusters && h->world == 1 && h->warm_rz_ref > 0.0;
+        const bool warm = h->warm_ok && h->use_clusters && h->warm_rz_ref > 0.0;
         PeerComm single{};   // world = 0: kernels take their single-GPU path
         single.world = 1;
         if (warm) {
             int rcw = schur_apply_launch(h, lambda, false, h->vx, nullptr, nullptr);   // ybuf = S x0 (keyframe rows)
             if (rcw) return rcw;
-            schur_k_rows_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, h->partC, h->nCtaPose, h->partB, h->nBlkB, h->BKK, h->vx, h->ybuf + PN);
+            if (h->world > 1) {   // one collective outside the loop: sum the shard products and the K-row partials
+                double* rowC = h->ybuf + PN + 8;
+                double* rowB = rowC + kPartCols;
+                reduce_rows_pair_kernel<<<2, 1024, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, rowC, h->partB, h->nBlkB, 6, kPcgCols, rowB, nullptr);
+                CUDA_TRY(cudaGetLastError());
+                rcw = allreduce(h, h->ybuf, PN + 8 + 2 * kPartCols);
+                if (rcw) return rcw;
+                schur_k_rows_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, rowC, 1, rowB, 1, h->BKK, h->vx, h->ybuf + PN);
+                h->launches += 1;
+            } else {
+                schur_k_rows_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->P, N, lambda, h->partC, h->nCtaPose, h->partB, h->nBlkB, h->BKK, h->vx, h->ybuf + PN);
+            }
             CUDA_TRY(cudaGetLastError());
             h->launches += 1;
         }
@@ -636,7 +668,7 @@ struct Engine {
         // __threadfence + ticket costs more than the two kernel boundaries it saves), so it is off unless ASC_FUSE=1.
         static const bool fuse = getenv("ASC_FUSE") != nullptr;
         const bool fuse_mid = fuse && !profiling && h->world == 1;
-        const bool fuse_end = fuse && !profiling && h->use_clusters && h->use_coarse && h->coarse_f32_active;
+        const bool fuse_end = fuse && !profiling && h->use_clusters && h->use_coarse && h->coarse_f32_active && !h->coarse_sharded;
         const int nGrpC = cdiv(h->nCtaPose, kRowGroup), nGrpB = cdiv(h->nBlkB, kRowGroup);
         CUDA_TRY(cudaMemsetAsync(h->tickC, 0, sizeof(unsigned) * (nGrpC + 2), h->stream));
         CUDA_TRY(cudaMemsetAsync(h->tickB, 0, sizeof(unsigned) * (nGrpB + 2), h->stream));
@@ -696,7 +728,7 @@ struct Engine {
         // ncclAllReduce hung on this stack: NCCL 2.28.9, driver 580); ASC_NO_GRAPH_MGPU=1 falls back to plain launches
         static const bool no_graph_mgpu = getenv("ASC_NO_GRAPH_MGPU") != nullptr;
         const bool can_graph = !no_graph && (h->world == 1 || (p2p && !no_graph_mgpu)) && !profiling && (!h->use_coarse || h->coarse_f32_active);
-        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0) | (fuse_mid ? 16 : 0) | (fuse_end ? 32 : 0);
+        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0) | (fuse_mid ? 16 : 0) | (fuse_end ? 32 : 0) | (h->coarse_sharded ? 64 : 0);
         for (;;) {
             if (can_graph) {
                 if (!h->pcg_graph || h->pcg_graph_key != graph_key) {
@@ -1113,7 +1145,8 @@ int setup_peer_exchange(asc_handle* h) {
     if (h->world <= 1 || h->world > kMaxPeers || !g_nccl.AllGather || getenv("ASC_NO_P2P")) return ASC_OK;
     const size_t PN = (size_t)h->P * h->N;
     const size_t stride = (PN + 8 + 2 * kPartCols + 31) / 32 * 32;
-    const size_t need = 256 + 2 * stride * sizeof(double);
+    const size_t zstride = ((size_t)std::max(h->nz, 8) + 31) / 32 * 32;
+    const size_t need = 256 + 2 * (stride + zstride) * sizeof(double);
     double bad = 0.0;
     if (!h->xbuf || need > h->xbuf_bytes) {
         int rc = allreduce(h, h->status, 1);   // barrier: no peer is still reading the buffer that is about to go away
@@ -1158,6 +1191,8 @@ int setup_peer_exchange(asc_handle* h) {
     h->pcm.fail = h->flags + 8;
     h->pcm.stride = (long long)stride;
     h->pcm.row_off = (long long)(PN + 8);
+    h->pcm.zoff = (long long)(2 * stride);
+    h->pcm.zstride = (long long)zstride;
     h->pcm.rank = h->rank; h->pcm.world = h->world;
     h->p2p_ok = true;
     return ASC_OK;
