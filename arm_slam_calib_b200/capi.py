@@ -47,6 +47,7 @@ SIGNATURES = {
     "asc_save_values": (C.c_int, [_vp]),
     "asc_restore_values": (C.c_int, [_vp]),
     "asc_launch_count": (C.c_int64, [_vp]),
+    "asc_solver_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "asc_timer_start": (C.c_int, [_vp]),
     "asc_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "asc_profile_begin": (C.c_int, [_vp, C.c_int32, C.c_int32]),
@@ -278,6 +279,12 @@ class BatchOptimizer:
         its = C.c_int32()
         self._check(self.L.asc_solve_damped(self.h, float(lam), _ptr(dq), _ptr(dl), _ptr(dx), C.byref(its)))
         return dq, dl, dx, its.value
+
+    def solver_info(self):
+        """(clusters, coarse dimension, doubles in the cluster blocks) of the packed problem."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int64()
+        self._check(self.L.asc_solver_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def extrinsic_marginal(self):
         """K0 block of (A^T A)^-1 at the current values (src/ArmSlamCalib.cpp:490-493); returns (cov 6x6, PCG iterations)."""

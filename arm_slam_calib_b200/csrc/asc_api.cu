@@ -147,7 +147,7 @@ struct asc_handle {
     // peer-memory exchange of the PCG loop (kernels.cuh, PeerComm): one IPC-shared buffer per rank
     PeerComm pcm{};
     bool p2p_ok = false;
-    bool coarse_sharded = false;    // E^-1 rows are split over the ranks (valid while coarse_f32_active)
+    bool coarse_sharded = false;    // the rows of E^-1 are computed 1/G per rank and all-gathered
     int crow0 = 0, crows = 0, crows_per_rank = 0;
     char* xbuf = nullptr;           // this rank's exchange buffer [flags 256 B | slot 0 | slot 1]
     size_t xbuf_bytes = 0;
@@ -495,18 +495,24 @@ struct Engine {
                     }
                     if (timing) cudaEventRecord(e1, h->stream);
                     // E^-1 = solve(U^T U, I): two TRSMs run much closer to peak than cuSOLVER's potri.
-                    // Multi-GPU with the peer exchange: every rank solves only for ITS columns of the identity = its rows of
-                    // the (symmetric) inverse, which is all its share of the per-iteration product needs.
-                    h->coarse_sharded = h->world > 1 && h->p2p_ok && getenv("ASC_NO_COARSE_SHARD") == nullptr;
+                    // Multi-GPU: every rank solves only for ITS columns of the identity = its rows of the (symmetric) inverse,
+                    // written in place at their row offset, and one in-place ncclAllGather completes the matrix on every rank
+                    // (1/G of the triangular-solve work each; the per-iteration product stays local).
+                    h->coarse_sharded = h->world > 1 && g_nccl.AllGather && getenv("ASC_NO_COARSE_SHARD") == nullptr;
                     h->crows_per_rank = h->coarse_sharded ? (cdiv(nz, h->world) + 3) / 4 * 4 : nz;
                     h->crow0 = h->coarse_sharded ? std::min(nz, h->rank * h->crows_per_rank) : 0;
                     h->crows = h->coarse_sharded ? std::max(0, std::min(nz, h->crow0 + h->crows_per_rank) - h->crow0) : nz;
-                    if (h->coarse_sharded && h->rank == h->world - 1) h->crows = nz - h->crow0;
-                    if (h->coarse_sharded) identity_slice_f32_kernel<<<cdiv((int64_t)nz * std::max(h->crows, 1), 256), 256, 0, h->stream>>>(h->Einvf, nz, h->crow0, h->crows);
+                    float* slice = h->Einvf + (size_t)h->crow0 * nz;
+                    if (h->coarse_sharded) identity_slice_f32_kernel<<<cdiv((int64_t)nz * std::max(h->crows, 1), 256), 256, 0, h->stream>>>(slice, nz, h->crow0, h->crows);
                     else identity_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->Einvf, nz);
                     if (h->crows > 0 &&
-                        cusolverDnSpotrs(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->crows, h->Ef, nz, h->Einvf, nz, h->flags + 7) != CUSOLVER_STATUS_SUCCESS)
+                        cusolverDnSpotrs(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->crows, h->Ef, nz, slice, nz, h->flags + 7) != CUSOLVER_STATUS_SUCCESS)
                         return fail(ASC_ERR_CUDA, "cusolverDnSpotrs failed");
+                    if (h->coarse_sharded) {
+                        const size_t cnt = (size_t)h->crows_per_rank * nz;   // Einvf holds world * cnt floats (padding rows after the last)
+                        if (g_nccl.AllGather(h->Einvf + (size_t)h->rank * cnt, h->Einvf, cnt, ncclFloat, h->comm, h->stream) != ncclSuccess)
+                            return fail(ASC_ERR_COMM, "ncclAllGather of the coarse inverse failed");
+                    }
                     CUDA_TRY(cudaGetLastError());
                     int info[2] = {0, 0};
                     CUDA_TRY(cudaMemcpyAsync(info, h->flags + 6, sizeof info, cudaMemcpyDeviceToHost, h->stream));
@@ -514,7 +520,7 @@ struct Engine {
                     f32_ok = info[0] == 0 && info[1] == 0;   // not positive definite in fp32: redo in fp64 below
                 }
                 h->coarse_f32_active = f32_ok;
-                if (!f32_ok) h->coarse_sharded = false;   // the fp64 fallback keeps the full inverse on every rank
+                if (!f32_ok) h->coarse_sharded = false;   // the fp64 fallback factorises and inverts on every rank
                 if (!f32_ok) {
                     if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 4) != CUSOLVER_STATUS_SUCCESS)
                         return fail(ASC_ERR_CUDA, "cusolverDnDpotrf failed");
@@ -580,18 +586,13 @@ struct Engine {
         }
         if (h->coarse_f32_active) {
             EndArgs none{};
-            if (h->coarse_sharded) {   // own rows -> exchange slot; publish, wait, gather (kernels.cuh, coarse_exchange_kernel)
-                if (h->crows > 0)
-                    coarse_gemv_f32_kernel<<<cdiv(h->crows, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9, none, nullptr,
-                                                                                   h->crow0, h->crows, h->pcm.ctr + 1, h->pcm.x[h->rank] + h->pcm.zoff,
-                                                                                   h->pcm.zstride);
-                coarse_exchange_kernel<<<1, 1024, 0, h->stream>>>(h->pcm, h->nz, h->crows_per_rank, h->zc, done);
-                h->launches += 1;
-            } else {
+            prof_start(h, 8);
+            {
                 coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9, end ? *end : none,
-                                                                             end ? h->tickG : nullptr, 0, h->nz, nullptr, nullptr, 0);
+                                                                             end ? h->tickG : nullptr);
             }
             CUDA_TRY(cudaGetLastError());
+            prof_stop(h, 8);
         } else {
             const double one = 1.0, zero = 0.0;
             if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, coarse_rhs(h), 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
@@ -668,7 +669,7 @@ struct Engine {
         // __threadfence + ticket costs more than the two kernel boundaries it saves), so it is off unless ASC_FUSE=1.
         static const bool fuse = getenv("ASC_FUSE") != nullptr;
         const bool fuse_mid = fuse && !profiling && h->world == 1;
-        const bool fuse_end = fuse && !profiling && h->use_clusters && h->use_coarse && h->coarse_f32_active && !h->coarse_sharded;
+        const bool fuse_end = fuse && !profiling && h->use_clusters && h->use_coarse && h->coarse_f32_active;
         const int nGrpC = cdiv(h->nCtaPose, kRowGroup), nGrpB = cdiv(h->nBlkB, kRowGroup);
         CUDA_TRY(cudaMemsetAsync(h->tickC, 0, sizeof(unsigned) * (nGrpC + 2), h->stream));
         CUDA_TRY(cudaMemsetAsync(h->tickB, 0, sizeof(unsigned) * (nGrpB + 2), h->stream));
@@ -707,8 +708,10 @@ struct Engine {
             end.p = h->vp; end.z = h->vz; end.scal = h->scal; end.done = h->flags; end.rc = h->use_coarse ? h->rc : nullptr; end.zc = h->zc;
             end.nz = h->nz; end.nC = h->nC; end.nA = h->nA; end.S = h->aggS;
             if (h->use_clusters) {
+                prof_start(h, 9);
                 pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
                                                                       h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr, p2p ? h->pcm : single);
+                prof_stop(h, 9);
                 if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags, fuse_end ? &end : nullptr); if (rc3) return rc3; }
             } else {
                 pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
@@ -728,7 +731,7 @@ struct Engine {
         // ncclAllReduce hung on this stack: NCCL 2.28.9, driver 580); ASC_NO_GRAPH_MGPU=1 falls back to plain launches
         static const bool no_graph_mgpu = getenv("ASC_NO_GRAPH_MGPU") != nullptr;
         const bool can_graph = !no_graph && (h->world == 1 || (p2p && !no_graph_mgpu)) && !profiling && (!h->use_coarse || h->coarse_f32_active);
-        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0) | (fuse_mid ? 16 : 0) | (fuse_end ? 32 : 0) | (h->coarse_sharded ? 64 : 0);
+        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0) | (fuse_mid ? 16 : 0) | (fuse_end ? 32 : 0);
         for (;;) {
             if (can_graph) {
                 if (!h->pcg_graph || h->pcg_graph_key != graph_key) {
@@ -1145,8 +1148,7 @@ int setup_peer_exchange(asc_handle* h) {
     if (h->world <= 1 || h->world > kMaxPeers || !g_nccl.AllGather || getenv("ASC_NO_P2P")) return ASC_OK;
     const size_t PN = (size_t)h->P * h->N;
     const size_t stride = (PN + 8 + 2 * kPartCols + 31) / 32 * 32;
-    const size_t zstride = ((size_t)std::max(h->nz, 8) + 31) / 32 * 32;
-    const size_t need = 256 + 2 * (stride + zstride) * sizeof(double);
+    const size_t need = 256 + 2 * stride * sizeof(double);
     double bad = 0.0;
     if (!h->xbuf || need > h->xbuf_bytes) {
         int rc = allreduce(h, h->status, 1);   // barrier: no peer is still reading the buffer that is about to go away
@@ -1191,8 +1193,6 @@ int setup_peer_exchange(asc_handle* h) {
     h->pcm.fail = h->flags + 8;
     h->pcm.stride = (long long)stride;
     h->pcm.row_off = (long long)(PN + 8);
-    h->pcm.zoff = (long long)(2 * stride);
-    h->pcm.zstride = (long long)zstride;
     h->pcm.rank = h->rank; h->pcm.world = h->world;
     h->p2p_ok = true;
     return ASC_OK;
@@ -1575,7 +1575,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         ALLOC(pair_a, np); ALLOC(pair_b, np);
         ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, (size_t)h->nC * N + 6); ALLOC(zc, nz); ALLOC(yc, nz); ALLOC(rca, nz);
         ALLOC(agg_pose_ptr, h->nA + 1); ALLOC(agg_inc_ptr, h->nA + 1); ALLOC(pose_agg, P);
-        if (pr.pcg_coarse_fp32) { ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * nz); } else { h->Ef = nullptr; h->Einvf = nullptr; }
+        if (pr.pcg_coarse_fp32) { ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * (nz + 4 * (size_t)std::max(h->world, 1))); } else { h->Ef = nullptr; h->Einvf = nullptr; }
         if (!h->solver) {
             if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cusolverDnCreate failed");
             if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cublasCreate failed");
@@ -1867,6 +1867,14 @@ int asc_restore_values(asc_handle* h) {
 
 int64_t asc_launch_count(asc_handle* h) { return h ? h->launches : 0; }
 
+int asc_solver_info(asc_handle* h, int32_t* n_clusters, int32_t* coarse_dim, int64_t* cluster_block_doubles) {
+    if (!h || !h->problem_set) return fail(ASC_ERR_INVALID, "set the problem first");
+    if (n_clusters) *n_clusters = h->nC;
+    if (coarse_dim) *coarse_dim = h->use_coarse ? h->nz : 0;
+    if (cluster_block_doubles) *cluster_block_doubles = (int64_t)h->scTotal;
+    return ASC_OK;
+}
+
 // CUDA-event stopwatch on the stream every kernel of this handle is launched on
 int asc_timer_start(asc_handle* h) {
     if (!h) return fail(ASC_ERR_INVALID, "null handle");
@@ -1889,7 +1897,7 @@ int asc_timer_stop(asc_handle* h, double* elapsed_ms) {
 }
 
 int asc_profile_begin(asc_handle* h, int32_t kernel_id, int32_t max_samples) {
-    if (!h || kernel_id < 0 || kernel_id > 7 || max_samples < 0) return fail(ASC_ERR_INVALID, "bad profile request");
+    if (!h || kernel_id < 0 || kernel_id > 9 || max_samples < 0) return fail(ASC_ERR_INVALID, "bad profile request");
     CUDA_TRY(cudaSetDevice(h->dev));
     while ((int)h->prof_ev.size() < 2 * max_samples) {
         cudaEvent_t e;

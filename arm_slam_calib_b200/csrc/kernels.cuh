@@ -52,8 +52,8 @@ struct PriorConst {
 
 // ------------------------------------------------------------------ peer-memory exchange (multi-GPU PCG)
 // One process per GPU; every rank owns one exchange buffer (cudaMalloc + CUDA IPC, mapped by all peers over NVLink):
-//   [ header 256 B: flags[8] of exchange 1, flags[8] of exchange 2, ..., the two local sequence counters at words 32, 33 |
-//     y slot 0 | y slot 1 | zc slot 0 | zc slot 1 ],       y slot = [ y partial (PN) | pad to PN+8 | rowC (32) | rowB (32) ]
+//   [ header 256 B: one sequence number per peer (words 0..7), the local sequence counter (word 32) | slot 0 | slot 1 ],
+//   slot = [ y partial (PN) | pad to PN+8 | rowC (32) | rowB (32) ]
 // Per PCG iteration a rank writes its shard's partial product into slot (seq & 1) of ITS OWN buffer (pass C), publishes
 // seq to every peer's flag array (pcg_signal_kernel) and the consumers (pcg_mid_kernel, pcg_cluster_update_kernel) sum the
 // slots of all ranks with peer loads in rank order -- the same order on every rank, so all ranks hold bitwise identical
@@ -68,8 +68,6 @@ struct PeerComm {
     int* fail;                       // local: set when a wait timed out
     long long stride;                // doubles per slot
     long long row_off;               // offset of rowC inside a slot (= PN + 8)
-    long long zoff, zstride;         // second exchange (coarse correction zc): slot s at x[r] + zoff + s * zstride; its flags are
-                                     // peer_flags[r][8..15], its sequence counter ctr[1]
     int rank, world;
 };
 
@@ -1377,43 +1375,11 @@ __global__ void __launch_bounds__(256) coarse_aggregate_kernel(const double* __r
     rca[i] = v;
 }
 
-// Multi-GPU coarse level: rank r owns rows [r0, r0 + m) of E^-1 (it solves U^T U X = I[:, r0 : r0 + m] after the replicated
-// factorisation, 1/G of the triangular-solve work), applies them to the restriction and writes its slice of zc into its
-// exchange slot; this kernel then publishes the slice, waits for every peer's and gathers the full vector with peer loads.
+// Multi-GPU coarse level: rank r solves U^T U X = I[:, r0 : r0 + m] after the replicated factorisation (1/G of the
+// triangular-solve work); X is rows r0 .. r0+m-1 of the symmetric inverse.  B is column-major n x m.
 __global__ void __launch_bounds__(256) identity_slice_f32_kernel(float* __restrict__ B, int n, int r0, int m) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (size_t)n * m) B[i] = ((int)(i % n) == r0 + (int)(i / n)) ? 1.0f : 0.0f;   // column-major n x m
-}
-
-__global__ void __launch_bounds__(1024)
-coarse_exchange_kernel(PeerComm pcm, int nz, int rows_per_rank, double* __restrict__ zc, const int* __restrict__ done) {
-    if (done && *done) return;
-    __shared__ unsigned s_seq;
-    unsigned* ctr2 = pcm.ctr + 1;
-    if (threadIdx.x == 0) {
-        const unsigned seq = *ctr2 + 1u;
-        *ctr2 = seq;
-        s_seq = seq;
-        __threadfence_system();   // the slice was written by the previous kernel of this stream
-        for (int r = 0; r < pcm.world; ++r)
-            if (r != pcm.rank) st_release_sys_u32(pcm.peer_flags[r] + 8 + pcm.rank, seq);
-    }
-    __syncthreads();
-    const unsigned seq = s_seq;
-    if (threadIdx.x < pcm.world && threadIdx.x != pcm.rank) {
-        const unsigned* f = pcm.peer_flags[pcm.rank] + 8 + threadIdx.x;
-        const long long t0 = clock64();
-        while ((int)(ld_acquire_sys_u32(f) - seq) < 0) {
-            if (clock64() - t0 > 8000000000ll) { *pcm.fail = 1; break; }
-            __nanosleep(64);
-        }
-    }
-    __syncthreads();
-    const long long off = pcm.zoff + (long long)(seq & 1u) * pcm.zstride;
-    for (int i = threadIdx.x; i < nz; i += 1024) {
-        const int owner = min(i / rows_per_rank, pcm.world - 1);
-        zc[i] = ld_peer_f64(pcm.x[owner] + off + i);
-    }
+    if (i < (size_t)n * m) B[i] = ((int)(i % n) == r0 + (int)(i / n)) ? 1.0f : 0.0f;
 }
 
 // A coarse inverse kept from an earlier linearisation is mostly off by a scalar (the robust weights move together while the
@@ -1991,17 +1957,13 @@ __global__ void __launch_bounds__(kReduceThreads) pcg_end_kernel(EndArgs a) {
 // finishes last also runs the end-of-iteration step (pcg_end_body) in the same launch.
 __global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
                                                               int n, const int* __restrict__ done, const double* __restrict__ alpha,
-                                                              EndArgs end, unsigned* ticket, int row0, int nrows, const unsigned* __restrict__ zctr,
-                                                              double* __restrict__ zbase, long long zstride) {
-    // rows [row0, row0 + nrows) of the inverse, stored as the rows 0 .. nrows-1 of A (single GPU: row0 = 0, nrows = n).
-    // zctr != null (multi-GPU): the output goes to this rank's next exchange slot instead of y.
+                                                              EndArgs end, unsigned* ticket) {
     if (done && *done) return;
-    if (zctr) y = zbase + (size_t)((*zctr + 1u) & 1u) * zstride;
     const double scale = alpha ? *alpha : 1.0;   // scalar re-fit of a reused (stale) coarse inverse, see coarse_refit_kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lrow = blockIdx.x * 4 + warp, row = row0 + lrow;
-    if (lrow < nrows) {
-        const float* a = A + (size_t)lrow * n;
+    const int row = blockIdx.x * 4 + warp;
+    if (row < n) {
+        const float* a = A + (size_t)row * n;
         double acc0 = 0.0, acc1 = 0.0;
         int i = lane * 2;
         for (; i + 64 + 1 < n; i += 128) {

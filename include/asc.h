@@ -191,6 +191,9 @@ int asc_save_values(asc_handle* h);
 int asc_restore_values(asc_handle* h);
 /* number of kernels this handle has launched so far */
 int64_t asc_launch_count(asc_handle* h);
+/* Sizes of the preconditioner of the packed problem (for byte accounting): clusters, coarse dimension (0 = no coarse level),
+ * total doubles in the cluster blocks. */
+int asc_solver_info(asc_handle* h, int32_t* n_clusters, int32_t* coarse_dim, int64_t* cluster_block_doubles);
 /* CUDA-event stopwatch recorded on the stream this handle launches its kernels on */
 int asc_timer_start(asc_handle* h);
 int asc_timer_stop(asc_handle* h, double* elapsed_ms);
