@@ -205,6 +205,8 @@ struct asc_handle {
     int nA = 0, aggS = 1;           // coarse aggregates: aggS consecutive clusters each
     int *agg_pose_ptr = nullptr, *agg_inc_ptr = nullptr, *pose_agg = nullptr;
     double* rca = nullptr;          // aggregated restriction (length nz)
+    double *ryc = nullptr, *qc = nullptr;   // side-branch GEMV: Z^T y and Einv Z^T y
+    cudaEvent_t ev_c = nullptr, ev_q = nullptr;
     int *inc_lo = nullptr, *inc_hi = nullptr, *inc_lm = nullptr, *dest_ptr = nullptr, *dest_ca = nullptr, *dest_cb = nullptr;
     int *pair_a = nullptr, *pair_b = nullptr, *cl_inc_ptr = nullptr, *cl_inc = nullptr;
     double *Vinc = nullptr, *Tinc = nullptr, *E = nullptr, *rc = nullptr, *zc = nullptr, *yc = nullptr, *SKK = nullptr, *work = nullptr;
@@ -670,10 +672,14 @@ struct Engine {
         static const bool fuse = getenv("ASC_FUSE") != nullptr;
         const bool fuse_mid = fuse && !profiling && h->world == 1;
         const bool fuse_end = fuse && !profiling && h->use_clusters && h->use_coarse && h->coarse_f32_active;
+        // coarse GEMV off the critical path (single GPU, fp32 inverse, one cluster per aggregate): see EndArgs in kernels.cuh
+        static const bool no_side_gemv = getenv("ASC_NO_SIDE_GEMV") != nullptr;
+        const bool side_gemv = !no_side_gemv && h->world == 1 && h->use_clusters && h->use_coarse && h->coarse_f32_active && h->aggS == 1 && !fuse_end;
         const int nGrpC = cdiv(h->nCtaPose, kRowGroup), nGrpB = cdiv(h->nBlkB, kRowGroup);
         CUDA_TRY(cudaMemsetAsync(h->tickC, 0, sizeof(unsigned) * (nGrpC + 2), h->stream));
         CUDA_TRY(cudaMemsetAsync(h->tickB, 0, sizeof(unsigned) * (nGrpB + 2), h->stream));
         CUDA_TRY(cudaMemsetAsync(h->tickG, 0, sizeof(unsigned) * 4, h->stream));
+        if (side_gemv) CUDA_TRY(cudaMemsetAsync(h->ryc + (size_t)h->nC * N, 0, sizeof(double) * 6, h->stream));   // K entries of Z^T y are added in pcg_end
         auto one_iteration = [&]() -> int {
             double* rowC = h->ybuf + PN + 8;
             double* rowB = rowC + kPartCols;
@@ -685,6 +691,16 @@ struct Engine {
             mid.rcK = h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr;
             int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev, p2p, fuse, fuse_mid ? &mid : nullptr);
             if (rc) return rc;
+            if (side_gemv) {   // fork: qc = Einv Z^T y on the side stream, beside pcg_mid + the cluster update
+                CUDA_TRY(cudaEventRecord(h->ev_c, h->stream));
+                CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_c, 0));
+                coarse_restrict_y_kernel<<<cdiv(h->nC, 4), 128, 0, h->stream2>>>(h->nC, N, h->cl_ptr, h->ybuf, h->ryc, h->flags);
+                EndArgs none{};
+                coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream2>>>(h->Einvf, h->ryc, h->qc, h->nz, h->flags, h->scal + 9, none, nullptr);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaEventRecord(h->ev_q, h->stream2));
+                h->launches += 2;
+            }
             if (p2p) {
                 pcg_signal_kernel<<<1, 1024, 0, h->stream>>>(h->pcm, mid.partC, mid.nC, mid.partB, mid.nB, h->flags);
                 CUDA_TRY(cudaGetLastError());
@@ -712,7 +728,10 @@ struct Engine {
                 pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
                                                                       h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr, p2p ? h->pcm : single);
                 prof_stop(h, 9);
-                if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags, fuse_end ? &end : nullptr); if (rc3) return rc3; }
+                if (side_gemv) {   // join; pcg_end advances zc by linearity
+                    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_q, 0));
+                    end.zc_rw = h->zc; end.qc = h->qc; end.EinvK = h->Einvf + (size_t)h->nC * N; end.yK = h->ybuf + PN; end.gemv_scale = h->scal + 9;
+                } else if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags, fuse_end ? &end : nullptr); if (rc3) return rc3; }
             } else {
                 pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
             }
@@ -731,7 +750,7 @@ struct Engine {
         // ncclAllReduce hung on this stack: NCCL 2.28.9, driver 580); ASC_NO_GRAPH_MGPU=1 falls back to plain launches
         static const bool no_graph_mgpu = getenv("ASC_NO_GRAPH_MGPU") != nullptr;
         const bool can_graph = !no_graph && (h->world == 1 || (p2p && !no_graph_mgpu)) && !profiling && (!h->use_coarse || h->coarse_f32_active);
-        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0) | (fuse_mid ? 16 : 0) | (fuse_end ? 32 : 0);
+        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0) | (fuse_mid ? 16 : 0) | (fuse_end ? 32 : 0) | (side_gemv ? 64 : 0);
         for (;;) {
             if (can_graph) {
                 if (!h->pcg_graph || h->pcg_graph_key != graph_key) {
@@ -1028,7 +1047,9 @@ int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
             // (C2: a stale operator costs ~1000 extra PCG iterations after a 30 % drop, ~15 after a 20 % drop; a rebuild costs ~110)
             // and the first steps from an initial estimate re-weight almost every factor even when the error barely moves
             // (a reused inverse is additionally re-fitted by a scalar, which narrows but does not close that gap)
-            if ((*error - new_error) > 0.25 * *error || h->outer_iteration < 2) h->coarse_valid = false;
+            static const int force_iters = getenv("ASC_COARSE_FORCE_ITERS") ? atoi(getenv("ASC_COARSE_FORCE_ITERS")) : 2;
+            static const double drop_frac = getenv("ASC_COARSE_DROP") ? atof(getenv("ASC_COARSE_DROP")) : 0.25;
+            if ((*error - new_error) > drop_frac * *error || h->outer_iteration < force_iters) h->coarse_valid = false;
             *error = new_error;
             *lambda = std::max(*lambda / p.lambda_factor, p.lambda_lower_bound);
             lg->accepted = 1;
@@ -1263,6 +1284,8 @@ int asc_create(const asc_params* params, asc_handle** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_c, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming));
     for (auto& ev : h->ev) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMallocHost((void**)&h->h_status, 64 * sizeof(double)));
     CUDA_TRY(cudaMallocHost((void**)&h->h_flags, 16 * sizeof(int)));
@@ -1305,6 +1328,8 @@ int asc_destroy(asc_handle* h) {
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_c) cudaEventDestroy(h->ev_c);
+    if (h->ev_q) cudaEventDestroy(h->ev_q);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return ASC_OK;
@@ -1573,7 +1598,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         const size_t ni = h->nInc, nd = h->nDest, np = pair_a.size(), nz = h->nz;
         ALLOC(dest_ptr, nd + 1); ALLOC(dest_ca, nd); ALLOC(dest_cb, nd);
         ALLOC(pair_a, np); ALLOC(pair_b, np);
-        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, (size_t)h->nC * N + 6); ALLOC(zc, nz); ALLOC(yc, nz); ALLOC(rca, nz);
+        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, (size_t)h->nC * N + 6); ALLOC(zc, nz); ALLOC(yc, nz); ALLOC(rca, nz); ALLOC(ryc, nz); ALLOC(qc, nz);
         ALLOC(agg_pose_ptr, h->nA + 1); ALLOC(agg_inc_ptr, h->nA + 1); ALLOC(pose_agg, P);
         if (pr.pcg_coarse_fp32) { ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * (nz + 4 * (size_t)std::max(h->world, 1))); } else { h->Ef = nullptr; h->Einvf = nullptr; }
         if (!h->solver) {

@@ -1903,6 +1903,18 @@ pcg_update_kernel(int P, const double* __restrict__ p, const double* __restrict_
     }
 }
 
+// Z^T y over the keyframe rows: ry[c N + t] = sum of y[p N + t] over the keyframes p of cluster c (K entries of ry stay 0).
+// One warp per cluster; feeds the side-stream GEMV qc = Einv ry while pcg_mid / the cluster update run on the main stream.
+__global__ void __launch_bounds__(128) coarse_restrict_y_kernel(int nC, int N, const int* __restrict__ cl_ptr, const double* __restrict__ y,
+                                                                 double* __restrict__ ry, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= nC || lane >= N) return;
+    double a = 0.0;
+    for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) a += y[(size_t)p * N + lane];
+    ry[(size_t)c * N + lane] = a;
+}
+
 // rz_new, beta, convergence test, p_K <- z_K + beta p_K.  One CTA of T threads.
 struct EndArgs {
     int P, N;
@@ -1914,6 +1926,16 @@ struct EndArgs {
     int* done;
     const double *rc, *zc;
     int nz, nC, nA, S;
+    // side-branch mode (single GPU): the coarse correction is advanced by linearity instead of recomputed,
+    //   zc <- zc - alpha * scale * (qc + EinvK^T yK),   qc = Einv [Z^T y (clusters) ; 0]  from the side stream,
+    // EinvK = Einv + (offset of the 6 extrinsic COLUMNS): exactly the entries Einv[i][K] the direct product would use -- the
+    // fp32 inverse is symmetric only to ~1e-7, and using the extrinsic rows instead stalls CG at a 1e-7 relative residual,
+    // because the recursion accumulates that mismatch in absolute terms.  yK = K rows of y (pcg_mid), alpha = scal[0]
+    double* zc_rw;           // null: zc was recomputed by the GEMV
+    const double* qc;
+    const float* EinvK;
+    const double* yK;
+    const double* gemv_scale;
 };
 
 template <int T>
@@ -1921,6 +1943,19 @@ __device__ __forceinline__ void pcg_end_body(const EndArgs& a) {
     __shared__ double scratch[T];
     __shared__ double so[1];
     const int lane = threadIdx.x & 31, P = a.P, N = a.N;
+    if (a.zc_rw) {
+        const double alpha = a.scal[0], sc = a.gemv_scale ? *a.gemv_scale : 1.0;
+        double yk[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) yk[r] = a.yK[r];
+        for (int i = threadIdx.x; i < a.nz; i += T) {
+            double kq = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) kq = fma((double)a.EinvK[(size_t)i * a.nz + r], yk[r], kq);   // row i, extrinsic columns
+            a.zc_rw[i] -= alpha * (a.qc[i] + sc * kq);   // qc already carries the GEMV's scale
+        }
+        __syncthreads();
+    }
     block_sum_cols<1, T>(a.part, a.nPart, so, scratch);
     double t = so[0];
     if (a.rc) {   // r . (Z zc) = (Z^T r) . zc ; and the K rows of z get their coarse part
