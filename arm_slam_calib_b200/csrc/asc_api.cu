@@ -212,6 +212,7 @@ struct asc_handle {
     double *Vinc = nullptr, *Tinc = nullptr, *E = nullptr, *rc = nullptr, *zc = nullptr, *yc = nullptr, *SKK = nullptr, *work = nullptr;
     int lwork = 0, lworkf = 0;
     float *Ef = nullptr, *workf = nullptr, *Einvf = nullptr;
+    float *Xf = nullptr, *Tf = nullptr;   // U^-1 and a GEMM scratch of the single-GPU inverse (invert_from_cholesky_f32)
     bool coarse_f32_active = false;   // E^-1 currently lives in Ef (fp32) rather than in E (fp64)
     bool coarse_refit = false;      // this solve reuses an older inverse: fit its scalar against the freshly assembled E
     bool coarse_valid = false;      // E holds a factorised inverse (possibly from an earlier lambda / linearisation)
@@ -293,6 +294,63 @@ ChainConst<N> make_chain_const(const asc_handle* h) {
         for (int k = 0; k < 3; ++k) cc.axis[i][k] = h->axis[3 * i + k];
     }
     return cc;
+}
+
+// ---- E^-1 from its Cholesky factor, single GPU (all column-major, leading dimension ld).
+// cuSOLVER's potrs with an identity right-hand side runs two n x n TRSMs (2 n^3 flop, 14.2 ms at n = 6006 on a B200, 30 TFLOP/s).
+// Here U^-1 comes from a block recursion ( [U11 U12; 0 U22]^-1 = [X11 -X11 U12 X22; 0 X22], TRSM leaves, SGEMM for the
+// off-diagonal block: 4.7 ms ) and E^-1 = U^-1 U^-T from a 2 x 2 blocked SYRK that skips the zero block (2.9 ms).
+__global__ void ident_block_f32_kernel(float* A, int m, int ld) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)m * m) { const int c = (int)(i / m), r = (int)(i % m); A[(size_t)c * ld + r] = (r == c) ? 1.0f : 0.0f; }
+}
+
+int inv_upper_f32(asc_handle* h, const float* U, float* X, int m, int ld, float* T) {
+    const float one = 1.f, zero = 0.f, mone = -1.f;
+    if (m <= 1024) {
+        ident_block_f32_kernel<<<cdiv((int64_t)m * m, 256), 256, 0, h->stream>>>(X, m, ld);
+        if (cublasStrsm(h->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, m, m, &one, U, ld, X, ld) != CUBLAS_STATUS_SUCCESS)
+            return fail(ASC_ERR_CUDA, "cublasStrsm failed");
+        return ASC_OK;
+    }
+    const int m1 = (m / 2 + 31) / 32 * 32, m2 = m - m1;
+    int rc = inv_upper_f32(h, U, X, m1, ld, T);
+    if (rc) return rc;
+    rc = inv_upper_f32(h, U + (size_t)m1 * ld + m1, X + (size_t)m1 * ld + m1, m2, ld, T);
+    if (rc) return rc;
+    if (cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, m1, m2, m2, &one, U + (size_t)m1 * ld, ld, X + (size_t)m1 * ld + m1, ld, &zero, T, m1) != CUBLAS_STATUS_SUCCESS ||
+        cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, m1, m2, m1, &mone, X, ld, T, m1, &zero, X + (size_t)m1 * ld, ld) != CUBLAS_STATUS_SUCCESS)
+        return fail(ASC_ERR_CUDA, "cublasSgemm failed");
+    return ASC_OK;
+}
+
+// Ef holds U (potrf, UPPER); on return Einvf holds the full symmetric inverse (row-major == column-major)
+int invert_from_cholesky_f32(asc_handle* h, int n) {
+    const float one = 1.f, zero = 0.f;
+    CUDA_TRY(cudaMemsetAsync(h->Xf, 0, sizeof(float) * (size_t)n * n, h->stream));
+    int rc = inv_upper_f32(h, h->Ef, h->Xf, n, n, h->Tf);
+    if (rc) return rc;
+    if (n < 128) {   // tiny coarse spaces: one SYRK
+        if (cublasSsyrk(h->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, n, n, &one, h->Xf, n, &zero, h->Einvf, n) != CUBLAS_STATUS_SUCCESS)
+            return fail(ASC_ERR_CUDA, "cublasSsyrk failed");
+        const int nbs = cdiv(n, 32);
+        mirror_lower_f32_kernel<<<dim3(nbs, nbs), 256, 0, h->stream>>>(h->Einvf, n);
+        CUDA_TRY(cudaGetLastError());
+        return ASC_OK;
+    }
+    const int m1 = (n / 2 + 31) / 32 * 32, m2 = n - m1;
+    const float *X11 = h->Xf, *X12 = h->Xf + (size_t)m1 * n, *X22 = h->Xf + (size_t)m1 * n + m1;
+    float *C11 = h->Einvf, *C12 = h->Einvf + (size_t)m1 * n, *C22 = h->Einvf + (size_t)m1 * n + m1;
+    if (cublasSsyrk(h->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, m1, m1, &one, X11, n, &zero, C11, n) != CUBLAS_STATUS_SUCCESS ||
+        cublasSsyrk(h->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, m1, m2, &one, X12, n, &one, C11, n) != CUBLAS_STATUS_SUCCESS ||
+        cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, m1, m2, m2, &one, X12, n, X22, n, &zero, C12, n) != CUBLAS_STATUS_SUCCESS ||
+        cublasSsyrk(h->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, m2, m2, &one, X22, n, &zero, C22, n) != CUBLAS_STATUS_SUCCESS)
+        return fail(ASC_ERR_CUDA, "cuBLAS syrk/gemm failed in the coarse inverse");
+    // column-major UPPER == row-major lower: complete the rows
+    const int nb = cdiv(n, 32);
+    mirror_lower_f32_kernel<<<dim3(nb, nb), 256, 0, h->stream>>>(h->Einvf, n);
+    CUDA_TRY(cudaGetLastError());
+    return ASC_OK;
 }
 
 // ------------------------------------------------------------------ launch sequences (templated on DOF)
@@ -505,9 +563,13 @@ struct Engine {
                     h->crow0 = h->coarse_sharded ? std::min(nz, h->rank * h->crows_per_rank) : 0;
                     h->crows = h->coarse_sharded ? std::max(0, std::min(nz, h->crow0 + h->crows_per_rank) - h->crow0) : nz;
                     float* slice = h->Einvf + (size_t)h->crow0 * nz;
-                    if (h->coarse_sharded) identity_slice_f32_kernel<<<cdiv((int64_t)nz * std::max(h->crows, 1), 256), 256, 0, h->stream>>>(slice, nz, h->crow0, h->crows);
+                    static const bool use_potrs = getenv("ASC_POTRS") != nullptr;
+                    if (h->world == 1 && h->Xf && !use_potrs) {   // single GPU: own inverse from the factor (see invert_from_cholesky_f32)
+                        int rci = invert_from_cholesky_f32(h, nz);
+                        if (rci) return rci;
+                    } else if (h->coarse_sharded) identity_slice_f32_kernel<<<cdiv((int64_t)nz * std::max(h->crows, 1), 256), 256, 0, h->stream>>>(slice, nz, h->crow0, h->crows);
                     else identity_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->Einvf, nz);
-                    if (h->crows > 0 &&
+                    if (!(h->world == 1 && h->Xf && !use_potrs) && h->crows > 0 &&
                         cusolverDnSpotrs(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->crows, h->Ef, nz, slice, nz, h->flags + 7) != CUSOLVER_STATUS_SUCCESS)
                         return fail(ASC_ERR_CUDA, "cusolverDnSpotrs failed");
                     if (h->coarse_sharded) {
@@ -1600,7 +1662,10 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         ALLOC(pair_a, np); ALLOC(pair_b, np);
         ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, (size_t)h->nC * N + 6); ALLOC(zc, nz); ALLOC(yc, nz); ALLOC(rca, nz); ALLOC(ryc, nz); ALLOC(qc, nz);
         ALLOC(agg_pose_ptr, h->nA + 1); ALLOC(agg_inc_ptr, h->nA + 1); ALLOC(pose_agg, P);
-        if (pr.pcg_coarse_fp32) { ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * (nz + 4 * (size_t)std::max(h->world, 1))); } else { h->Ef = nullptr; h->Einvf = nullptr; }
+        if (pr.pcg_coarse_fp32) {
+            ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * (nz + 4 * (size_t)std::max(h->world, 1)));
+            if (h->world == 1) { ALLOC(Xf, nz * nz); ALLOC(Tf, (nz / 2 + 64) * (nz / 2 + 64)); } else { h->Xf = nullptr; h->Tf = nullptr; }
+        } else { h->Ef = nullptr; h->Einvf = nullptr; h->Xf = nullptr; h->Tf = nullptr; }
         if (!h->solver) {
             if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cusolverDnCreate failed");
             if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cublasCreate failed");
