@@ -145,6 +145,11 @@ class Problem:
     continuous: np.ndarray = None
     has_enc: np.ndarray = None
     t_base: np.ndarray = None
+    # DriftFactor(q_{p-1}, q_p) links (DriftFactor.h:44-61; use_drift_noise in the drivers): has_drift[p] != 0, measurement
+    # drift_meas[p] = encoders[p] - encoders[p-1] (ArmSlamCalib.cpp:1668), per-joint sigma (drift_noise_level, default 0.05)
+    has_drift: np.ndarray = None
+    drift_meas: np.ndarray = None
+    sigma_drift: np.ndarray = None
     # initial estimate (Values)
     q0: np.ndarray = None
     l0: np.ndarray = None

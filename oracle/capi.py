@@ -34,6 +34,8 @@ def _load():
         L.orc_error.argtypes = [_vp, _vp, _vp, _vp]
         L.orc_linearize.restype = C.c_double
         L.orc_linearize.argtypes = [_vp] + [_vp] * 16
+        L.orc_set_drift.restype = None
+        L.orc_set_drift.argtypes = [_vp, _vp, _vp, _vp]
         L.orc_extrinsic_marginal.restype = C.c_int
         L.orc_extrinsic_marginal.argtypes = [_vp, _vp, _vp, _vp, _vp]
         L.orc_solve_damped.restype = C.c_int
@@ -75,6 +77,16 @@ class Oracle:
         self.h = self.L.orc_create(C.byref(params), self.N, _p(k["t_p2j"]), _p(k["axis"]), _p(k["t_c2j"]), _p(k["cont"]), _p(k["t_base"]),
                                    pb.fx, pb.fy, pb.cx, pb.cy, self.P, self.Lm, self.M, _p(k["pi"]), _p(k["li"]), _p(k["uv"]),
                                    _p(k["enc"]), _p(k["he"]), _p(k["lp"]), _p(k["xp"]))
+        if getattr(pb, "has_drift", None) is not None:
+            self.set_drift(pb.has_drift, pb.drift_meas, pb.sigma_drift)
+
+    def set_drift(self, has_drift, meas, sigma):
+        """DriftFactor(q_{p-1}, q_p) where has_drift[p] != 0 (DriftFactor.h:44-61); meas [P][N] = q1Encoders - q0Encoders."""
+        if has_drift is None:
+            self.L.orc_set_drift(self.h, None, None, None)
+            return
+        hd = np.ascontiguousarray(has_drift, dtype=np.uint8); m = _f64(meas); sg = _f64(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (self.N,)))
+        self.L.orc_set_drift(self.h, _p(hd), _p(m), _p(sg))
 
     def close(self):
         if self.h:

@@ -83,7 +83,19 @@ def whitened_residuals(pb, prm, q, l, x12):
         r = (l[j] - pb.lm_prior[j]) / prm.sigma_landmark
         out.append(np.sqrt(k2 / (k2 + r @ r)) * r)
     out.append(local_pose(pb.x_prior, x12) / np.array(prm.sigma_extrinsic[:6]))
+    out.extend(drift_residuals(pb, q))
     return np.concatenate(out)
+
+
+def drift_residuals(pb, q):
+    """DriftFactor (DriftFactor.h:44-61): (q1 - q0) - (q1Encoders - q0Encoders), Diagonal sigma; linear, no robust weight."""
+    out = []
+    if getattr(pb, "has_drift", None) is not None:
+        sg = np.broadcast_to(np.asarray(pb.sigma_drift, dtype=np.float64), (pb.n_dof,))
+        for p in range(1, pb.n_poses):
+            if pb.has_drift[p]:
+                out.append(((q[p] - q[p - 1]) - pb.drift_meas[p]) / sg)
+    return out
 
 
 def error(pb, prm, q, l, x12):
@@ -108,6 +120,7 @@ def frozen_weight_residuals(pb, prm, q, l, x12, q0, l0, x0):
         r0 = (l0[j] - pb.lm_prior[j]) / prm.sigma_landmark
         out.append(np.sqrt(k2 / (k2 + r0 @ r0)) * (l[j] - pb.lm_prior[j]) / prm.sigma_landmark)
     out.append(local_pose(pb.x_prior, x12) / np.array(prm.sigma_extrinsic[:6]))
+    out.extend(drift_residuals(pb, q))
     return np.concatenate(out)
 
 
@@ -131,8 +144,10 @@ def dense_jacobian(pb, prm, q, l, x12, h=1e-6):
     A = np.stack(cols, axis=1)
     # [DEP] gtsam::PriorFactor<Pose3>::evaluateError returns H = eye(6) (not the derivative of localCoordinates):
     # the one place where the linearisation is knowingly not the true Jacobian
-    A[-6:, :] = 0.0
-    A[-6:, n - 6:] = np.diag(1.0 / np.array(prm.sigma_extrinsic[:6]))
+    nd = sum(len(r) for r in drift_residuals(pb, q))   # drift rows come after the K0 prior rows
+    k0 = A.shape[0] - nd - 6
+    A[k0:k0 + 6, :] = 0.0
+    A[k0:k0 + 6, n - 6:] = np.diag(1.0 / np.array(prm.sigma_extrinsic[:6]))
     return A
 
 
