@@ -42,6 +42,7 @@ SIGNATURES = {
     "asc_get_projection_blocks": (C.c_int, [_vp, _vp, _vp, _vp]),
     "asc_get_landmark_blocks": (C.c_int, [_vp, _vp, _vp, _vp]),
     "asc_get_pose_blocks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "asc_set_drift": (C.c_int, [_vp, _vp, _vp, _vp]),
     "asc_solve_damped": (C.c_int, [_vp, C.c_double, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
     "asc_extrinsic_marginal": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32)]),
     "asc_save_values": (C.c_int, [_vp]),
@@ -241,6 +242,18 @@ class BatchOptimizer:
         xp = np.ascontiguousarray(pb.x_prior, dtype=np.float64)
         self._check(self.L.asc_set_problem(self.h, enc.shape[0], lp.shape[0], pi.shape[0], _ptr(pi), _ptr(li), _ptr(uv), _ptr(enc), _ptr(he), _ptr(lp), _ptr(xp)))
         self.P, self.Lm, self.M, self.N = enc.shape[0], lp.shape[0], pi.shape[0], pb.n_dof
+        if getattr(pb, "has_drift", None) is not None:
+            self.set_drift(pb.has_drift, pb.drift_meas, pb.sigma_drift)
+
+    def set_drift(self, has_drift, drift_meas, sigma_drift):
+        """DriftFactor(q_{p-1}, q_p) links (asc_set_drift); has_drift None removes them."""
+        if has_drift is None:
+            self._check(self.L.asc_set_drift(self.h, None, None, None))
+            return
+        hd = np.ascontiguousarray(has_drift, dtype=np.uint8)
+        dm = np.ascontiguousarray(drift_meas, dtype=np.float64)
+        sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma_drift, dtype=np.float64), (self.N,)))
+        self._check(self.L.asc_set_drift(self.h, _ptr(hd), _ptr(dm), _ptr(sg)))
 
     def set_values(self, q, l, x):
         q = np.ascontiguousarray(q, dtype=np.float64)

@@ -164,6 +164,11 @@ struct asc_handle {
     double2 *p_uv = nullptr, *l_uv = nullptr, *J = nullptr, *b_dbg = nullptr;
     double *enc = nullptr, *lm_prior = nullptr;
     uint8_t* has_enc = nullptr;
+    // DriftFactor links (asc_set_drift): device tables live outside the arena (set after asc_set_problem)
+    uint8_t* d_has_drift = nullptr;   // [P + 1]
+    double *d_drift_meas = nullptr, *d_drift_w = nullptr;
+    bool drift_set = false;
+    DriftTab drift() const { DriftTab t; t.has = drift_set ? d_has_drift : nullptr; t.meas = d_drift_meas; t.w = d_drift_w; return t; }
     double *q = nullptr, *lm4 = nullptr, *X = nullptr, *q_try = nullptr, *lm4_try = nullptr, *X_try = nullptr;
     double *cam = nullptr, *chain = nullptr;
     double *lml = nullptr;       // landmark positions at the linearisation point (stable pointer: lm4 / lm4_try swap on accept)
@@ -390,11 +395,11 @@ struct Engine {
         if (store_b)
             linearize_pose_kernel<N, true><<<nCtaLin, LinCfg<N>::kThreads, LinCfg<N>::kBytes, h->stream>>>(
                 h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
-                h->J, h->Bpp, h->BpK, h->gr, h->partA, h->b_dbg, h->cheir);
+                h->J, h->Bpp, h->BpK, h->gr, h->partA, h->b_dbg, h->cheir, h->drift());
         else
             linearize_pose_kernel<N, false><<<nCtaLin, LinCfg<N>::kThreads, LinCfg<N>::kBytes, h->stream>>>(
                 h->cm, h->pc, h->P, h->M, h->pose_ptr, h->p_lm, h->p_uv, h->cam, h->chain, h->lm4, h->q, h->enc, h->has_enc, add_priors,
-                h->J, h->Bpp, h->BpK, h->gr, h->partA, nullptr, h->cheir);
+                h->J, h->Bpp, h->BpK, h->gr, h->partA, nullptr, h->cheir, h->drift());
         CUDA_TRY(cudaGetLastError());
         DBG_SYNC(h, "fk + linearize_pose");
         prof_stop(h, 1);
@@ -633,7 +638,8 @@ struct Engine {
         schur_pass_c_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, h->rank == 0 ? 1 : 0, h->pose_ptr, h->p_lm, h->J, h->u4, x,
                                                                          h->Bpp, h->BpK, done, h->ybuf, h->partC, lambda_dev, h->chain, h->lml,
                                                                          to_slot ? h->pcm.ctr : nullptr, to_slot ? h->pcm.x[h->rank] : nullptr, h->pcm.stride,
-                                                                         grouped ? h->grpC : nullptr, grouped ? h->tickC : nullptr, mid ? 1 : 0, mid ? *mid : none);
+                                                                         grouped ? h->grpC : nullptr, grouped ? h->tickC : nullptr, mid ? 1 : 0, mid ? *mid : none,
+                                                                         h->drift());
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 5);
         return ASC_OK;
@@ -922,7 +928,7 @@ struct Engine {
         if (nb1) error_proj_kernel<<<nb1, 256, 0, h->stream>>>(h->cm, h->M, h->p_pose, h->p_lm, h->p_uv, h->cam, lm4, h->errblk);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 6);
-        error_prior_kernel<<<nb2, 256, 0, h->stream>>>(h->cm, h->pc, N, h->P, h->L, h->rank == 0 ? 1 : 0, q, h->enc, h->has_enc, lm4, h->lm_prior, h->errblk + nb1);
+        error_prior_kernel<<<nb2, 256, 0, h->stream>>>(h->cm, h->pc, N, h->P, h->L, h->rank == 0 ? 1 : 0, q, h->enc, h->has_enc, lm4, h->lm_prior, h->errblk + nb1, h->drift());
         CUDA_TRY(cudaGetLastError());
         error_finish_kernel<<<1, 256, 0, h->stream>>>(h->pc, h->rank == 0 ? 1 : 0, X, h->errblk, nb1 + nb2, h->status + 4);
         CUDA_TRY(cudaGetLastError());
@@ -972,7 +978,7 @@ int dispatch_schur_c(asc_handle* h, double lambda, double* x, double* u4_in) {
     case n:                                                                                                                       \
         schur_pass_c_kernel<n><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, 0, h->pose_ptr, h->p_lm, h->J, u4_in, x, \
                                                                          h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr, h->chain, h->lml, nullptr, nullptr, 0, \
-                                                                         nullptr, nullptr, 0, MidArgs{}); \
+                                                                         nullptr, nullptr, 0, MidArgs{}, DriftTab{nullptr, nullptr, nullptr}); \
         break;
     switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
 #undef X
@@ -1010,7 +1016,8 @@ step_dots_kernel(int64_t nr, const double* __restrict__ x, const double* __restr
 
 // per keyframe g_p^T B_pp g_p + 2 g_p^T B_pK g_K   (Dogleg, |A g|^2)
 __global__ void __launch_bounds__(256)
-dogleg_pose_quad_kernel(int P, int N, const double* __restrict__ Bpp, const double* __restrict__ BpK, const double* __restrict__ g, double* __restrict__ blk) {
+dogleg_pose_quad_kernel(int P, int N, const double* __restrict__ Bpp, const double* __restrict__ BpK, const double* __restrict__ g, double* __restrict__ blk,
+                        DriftTab dt) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     double v = 0.0;
     if (p < P) {
@@ -1022,6 +1029,7 @@ dogleg_pose_quad_kernel(int P, int N, const double* __restrict__ Bpp, const doub
             double k = 0.0;
             for (int c = 0; c < 6; ++c) k += BpK[(size_t)p * N * 6 + r * 6 + c] * gK[c];
             v += gp[r] * (t + 2.0 * k);
+            if (dt.has && dt.has[p]) v -= 2.0 * dt.w[r] * gp[r] * g[(size_t)(p - 1) * N + r];   // 2 g_{p-1}^T B_{p-1,p} g_p
         }
     }
     __shared__ double s[8];
@@ -1138,7 +1146,7 @@ int dogleg_gHg(asc_handle* h, double* out) {
     if (rc) return rc;
     reduce_rows_kernel<<<1, 256, 0, h->stream>>>(h->partC, h->nCtaPose, 7, kPcgCols, h->nCtaPose, h->status + 16);   // [16+6] = T1
     const int nbp = cdiv(h->P, 256), nbl = cdiv(h->L, 256);
-    dogleg_pose_quad_kernel<<<nbp, 256, 0, h->stream>>>(h->P, N, h->Bpp, h->BpK, h->gr, h->errblk);
+    dogleg_pose_quad_kernel<<<nbp, 256, 0, h->stream>>>(h->P, N, h->Bpp, h->BpK, h->gr, h->errblk, h->drift());
     dogleg_landmark_quad_kernel<<<std::max(nbl, 1), 256, 0, h->stream>>>(h->L, h->C, h->gl, h->WK, h->gr + PN, h->errblk + nbp);
     CUDA_TRY(cudaGetLastError());
     sum_kernel<<<1, 256, 0, h->stream>>>(h->errblk, h->rank == 0 ? nbp : 0, h->status + 12);
@@ -1381,6 +1389,7 @@ int asc_destroy(asc_handle* h) {
     if (h->blas) cublasDestroy(h->blas);
     free_device(h);
     if (h->arena) cudaFree(h->arena);
+    if (h->d_has_drift) { cudaFree(h->d_has_drift); cudaFree(h->d_drift_meas); cudaFree(h->d_drift_w); }
     if (h->work) cudaFree(h->work);
     if (h->workf) cudaFree(h->workf);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -1443,6 +1452,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     const int N = h->N;
     h->P = P; h->L = L; h->M = M;
     h->values_set = false; h->linearized = false; h->lin_lambda = -1.0;
+    h->drift_set = false;   // drift links belong to the packed graph: set them again after asc_set_problem
     h->coarse_valid = false; h->coarse_ref_iters = 0; h->coarse_last_iters = 0;
     if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }
     // constants
@@ -1749,6 +1759,33 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     CUDA_TRY(cudaStreamSynchronize(h->stream));   // host staging vectors go out of scope
     lap("uploads");
     h->problem_set = true;
+    return ASC_OK;
+}
+
+int asc_set_drift(asc_handle* h, const uint8_t* has_drift, const double* drift_meas, const double* sigma_drift) {
+    if (!h || !h->problem_set) return fail(ASC_ERR_INVALID, "set the problem first");
+    CUDA_TRY(cudaSetDevice(h->dev));
+    h->drift_set = false;
+    h->linearized = false;
+    if (!has_drift) return ASC_OK;
+    if (!drift_meas || !sigma_drift) return fail(ASC_ERR_INVALID, "null argument");
+    const int P = h->P, N = h->N;
+    for (int i = 0; i < N; ++i) if (!(sigma_drift[i] > 0)) return fail(ASC_ERR_INVALID, "drift sigma must be positive");
+    std::vector<uint8_t> hd((size_t)P + 1, 0);
+    for (int p = 1; p < P; ++p) hd[p] = has_drift[p] ? 1 : 0;   // a link needs a predecessor; [P] stays 0 (kernels read p + 1)
+    std::vector<double> w(N);
+    for (int i = 0; i < N; ++i) { h->pc.inv_sigma_drift[i] = 1.0 / sigma_drift[i]; w[i] = h->pc.inv_sigma_drift[i] * h->pc.inv_sigma_drift[i]; }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->d_has_drift) { cudaFree(h->d_has_drift); cudaFree(h->d_drift_meas); cudaFree(h->d_drift_w); h->d_has_drift = nullptr; }
+    CUDA_TRY(cudaMalloc((void**)&h->d_has_drift, (size_t)P + 1));
+    CUDA_TRY(cudaMalloc((void**)&h->d_drift_meas, sizeof(double) * (size_t)P * N));
+    CUDA_TRY(cudaMalloc((void**)&h->d_drift_w, sizeof(double) * N));
+    CUDA_TRY(cudaMemcpyAsync(h->d_has_drift, hd.data(), (size_t)P + 1, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_drift_meas, drift_meas, sizeof(double) * (size_t)P * N, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_drift_w, w.data(), sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->drift_set = true;
+    if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }   // the drift table is a kernel argument of the captured loop
     return ASC_OK;
 }
 

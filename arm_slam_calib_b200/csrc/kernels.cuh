@@ -44,6 +44,7 @@ struct PriorConst {
     double x_prior[12];
     double inv_sigma_x[6];
     double inv_sigma_enc[20];
+    double inv_sigma_drift[20];   // DriftFactor sigmas (only read when a drift table is passed)
     int continuous_mask;          // bit i set: joint i is continuous (RobotConfig.h:72-77)
     int use_dead_band;
     double dead_band;
@@ -450,6 +451,18 @@ struct LinCfg {
     static constexpr size_t kBytes = sizeof(double) * (kPerWarpDoubles * kWarps + KF);
 };
 
+// DriftFactor(q_{p-1}, q_p) links (DriftFactor.h:44-61): has[p] != 0 (has[0] = has[P] = 0), meas[p][N] = q1Encoders - q0Encoders.
+// residual (q_p - q_{p-1}) - meas[p], J0 = -I, J1 = +I, Diagonal noise: B_{p-1,p-1} += W, B_pp += W, B_{p-1,p} = -W, W = diag(1/sigma^2).
+struct DriftTab {
+    const uint8_t* has;    // null: no drift factors
+    const double* meas;
+    const double* w;       // [N] 1 / sigma^2
+};
+// whitened residual of the link (p-1, p), joint i
+__device__ __forceinline__ double drift_residual(const PriorConst& pc, const DriftTab& dt, const double* __restrict__ q, int N, int p, int i) {
+    return ((q[(size_t)p * N + i] - q[(size_t)(p - 1) * N + i]) - dt.meas[(size_t)p * N + i]) * pc.inv_sigma_drift[i];
+}
+
 // whitened EncoderFactor residual of joint i (EncoderFactor.h:60-99): (q - enc) / sigma, SO(2)-wrapped if continuous
 __device__ __forceinline__ double encoder_residual(const PriorConst& pc, double qq, double ee, int i) {
     double d = qq - ee;
@@ -461,7 +474,7 @@ __device__ __forceinline__ double encoder_residual(const PriorConst& pc, double 
 template <int N, int ROLE, bool STORE_B>
 __device__ __forceinline__ void linearize_role(const Camera& cm, const PriorConst& pc, int p, int64_t M, const int* __restrict__ pose_ptr,
                                                const int* __restrict__ p_lm, const double2* __restrict__ p_uv, const double* __restrict__ lm4,
-                                               const double* __restrict__ q, const double* __restrict__ enc, bool with_enc,
+                                               const double* __restrict__ q, const double* __restrict__ enc, bool with_enc, DriftTab dt,
                                                double2* __restrict__ J, double* __restrict__ Bpp, double* __restrict__ BpK, double* __restrict__ gp,
                                                double2* __restrict__ b_out, unsigned long long* __restrict__ cheir_count,
                                                const double* s_cam, const double* s_chain, int lane) {
@@ -547,10 +560,15 @@ __device__ __forceinline__ void linearize_role(const Camera& cm, const PriorCons
         double v = tot[t];
         if (hi < N) {
             if (lo == hi && with_enc) v += pc.inv_sigma_enc[lo] * pc.inv_sigma_enc[lo];
+            if (lo == hi && dt.has) v += pc.inv_sigma_drift[lo] * pc.inv_sigma_drift[lo] * (double)((dt.has[p] ? 1 : 0) + (dt.has[p + 1] ? 1 : 0));
             B[lo * N + hi] = v; B[hi * N + lo] = v;
         } else if (hi < N + 6) BK[lo * 6 + (hi - N)] = v;
         else {                                               // hi == N+6: J_q^T b, plus the encoder factor's -J^T r (J = I)
             if (with_enc) v -= encoder_residual(pc, q[(size_t)p * N + lo], enc[(size_t)p * N + lo], lo) * pc.inv_sigma_enc[lo];
+            if (dt.has) {                                    // drift links: -J1^T r (this keyframe is q1) and -J0^T r (it is q0 of the next link)
+                if (dt.has[p]) v -= drift_residual(pc, dt, q, N, p, lo) * pc.inv_sigma_drift[lo];
+                if (dt.has[p + 1]) v += drift_residual(pc, dt, q, N, p + 1, lo) * pc.inv_sigma_drift[lo];
+            }
             g[lo] = v;
         }
     }
@@ -578,8 +596,9 @@ linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __r
                       const double* __restrict__ lm4, const double* __restrict__ q, const double* __restrict__ enc,
                       const uint8_t* __restrict__ has_enc, int add_priors, double2* __restrict__ J, double* __restrict__ Bpp,
                       double* __restrict__ BpK, double* __restrict__ gp, double* __restrict__ cta_part, double2* __restrict__ b_out,
-                      unsigned long long* __restrict__ cheir_count) {
+                      unsigned long long* __restrict__ cheir_count, DriftTab dt) {
     typedef LinCfg<N> Cf;
+    if (!add_priors) dt.has = nullptr;   // like the encoder factors, drift factors are added by rank 0 only
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kf = warp / Cf::W, role = warp % Cf::W;
@@ -593,11 +612,14 @@ linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __r
         for (int i = lane; i < 6 * N; i += 32) s_chain[i] = chain[(size_t)p * 6 * N + i];
         __syncwarp();
         const bool with_enc = add_priors && (has_enc == nullptr || has_enc[p]);
-        LinRoleDispatch<N, 0, STORE_B>::run(role, cm, pc, p, M, pose_ptr, p_lm, p_uv, lm4, q, enc, with_enc, J, Bpp, BpK, gp, b_out, cheir_count,
+        LinRoleDispatch<N, 0, STORE_B>::run(role, cm, pc, p, M, pose_ptr, p_lm, p_uv, lm4, q, enc, with_enc, dt, J, Bpp, BpK, gp, b_out, cheir_count,
                                              s_cam, s_chain, lane);
-        if (role == 0 && with_enc) {   // EncoderFactor error 0.5 |r / sigma|^2
+        if (role == 0 && (with_enc || dt.has)) {   // EncoderFactor / DriftFactor error 0.5 |r / sigma|^2 (a link is counted at its q1)
             double e2 = 0.0;
-            if (lane < N) { const double wr = encoder_residual(pc, q[(size_t)p * N + lane], enc[(size_t)p * N + lane], lane); e2 = 0.5 * wr * wr; }
+            if (lane < N) {
+                if (with_enc) { const double wr = encoder_residual(pc, q[(size_t)p * N + lane], enc[(size_t)p * N + lane], lane); e2 = 0.5 * wr * wr; }
+                if (dt.has && dt.has[p]) { const double wd = drift_residual(pc, dt, q, N, p, lane); e2 += 0.5 * wd * wd; }
+            }
             e2 = warp_sum(e2);
             if (lane == 0) s_enc[kf] = e2;
         }
@@ -1775,7 +1797,7 @@ schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int
                     const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part,
                     const double* __restrict__ lambda_dev, const double* __restrict__ chain, const double* __restrict__ lml,
                     const unsigned* __restrict__ xctr, double* __restrict__ xbase, long long xstride, double* __restrict__ grp_rows,
-                    unsigned* __restrict__ grp_tickets, int fuse_mid, MidArgs mid) {
+                    unsigned* __restrict__ grp_tickets, int fuse_mid, MidArgs mid, DriftTab dt) {
     if (done && *done) return;
     if (xctr) y = xbase + (size_t)((*xctr + 1u) & 1u) * xstride;   // multi-GPU: the next exchange slot of this rank
     const double lambda = lambda_dev ? *lambda_dev : lambda_val;   // device-resident inside the captured PCG graph
@@ -1820,6 +1842,11 @@ schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int
                 for (int i = 0; i < N; ++i) t = fma(B[i], xp[i], t);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) t = fma(BK[i], xK[i], t);
+                if (dt.has) {   // B_{p,p-1} x_{p-1} + B_{p,p+1} x_{p+1} = -W (x_{p-1} [link p] + x_{p+1} [link p+1])
+                    const double w = dt.w[lane];
+                    if (dt.has[p]) t -= w * x[(size_t)(p - 1) * N + lane];
+                    if (dt.has[p + 1]) t -= w * x[(size_t)(p + 1) * N + lane];
+                }
                 mine += t;
             }
             // B_pK^T x_p : lane c < 6 takes column c
@@ -2204,7 +2231,7 @@ error_proj_kernel(Camera cm, int64_t M, const int* __restrict__ p_pose, const in
 __global__ void __launch_bounds__(256)
 error_prior_kernel(Camera cm, PriorConst pc, int N, int P, int L, int with_enc, const double* __restrict__ q, const double* __restrict__ enc,
                    const uint8_t* __restrict__ has_enc, const double* __restrict__ lm4, const double* __restrict__ lm_prior,
-                   double* __restrict__ blk_err) {
+                   double* __restrict__ blk_err, DriftTab dt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0;
     if (i < P) {
@@ -2218,6 +2245,8 @@ error_prior_kernel(Camera cm, PriorConst pc, int N, int P, int L, int with_enc, 
                 e += 0.5 * w * w;
             }
         }
+        if (with_enc && dt.has && dt.has[i])   // DriftFactor(q_{i-1}, q_i), rank 0 only like the encoders
+            for (int c = 0; c < N; ++c) { const double w = drift_residual(pc, dt, q, N, i, c); e += 0.5 * w * w; }
     } else if (i < P + L) {
         const int j = i - P;
         const double r0 = (lm4[4 * (size_t)j] - lm_prior[3 * (size_t)j]) * cm.inv_sigma_lm, r1 = (lm4[4 * (size_t)j + 1] - lm_prior[3 * (size_t)j + 1]) * cm.inv_sigma_lm,

@@ -85,3 +85,15 @@ def make_sim_problem(chain=None, trajectory_size=250, nx=25, ny=25, size_x=10.0,
                    uv=uv, enc=enc, lm_prior=lm_truth.copy(), x_prior=guess.copy(), q0=enc.copy(), l0=lm_truth.copy(), x0=guess.copy(),
                    meta=dict(q_truth=q_truth, lm_truth=lm_truth, lm_id=lm_id, factor_order=order, n_sim_landmarks=Ls.value,
                              sim_extrinsic=np.array(list(cfg.sim_extrinsic))))
+
+
+def with_drift(pb, sigma=0.05):
+    """The same problem with DriftFactor(q_{p-1}, q_p) between every pair of consecutive configurations, as SimulationStep adds them
+    when use_drift_noise is set (src/ArmSlamCalib.cpp:317-320, :1653-1668): measurement = encoders[p] - encoders[p-1],
+    Diagonal sigma = drift_noise_level (0.05, ArmSlamCalib.h:84)."""
+    import dataclasses
+    import numpy as np
+    P, N = pb.enc.shape
+    hd = np.ones(P, dtype=np.uint8); hd[0] = 0
+    meas = np.zeros((P, N)); meas[1:] = pb.enc[1:] - pb.enc[:-1]
+    return dataclasses.replace(pb, has_drift=hd, drift_meas=meas, sigma_drift=np.full(N, float(sigma)))

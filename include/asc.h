@@ -142,6 +142,14 @@ int asc_set_problem(asc_handle* h, int32_t n_poses, int32_t n_landmarks, int64_t
                     const double* lm_prior /*[L][3]*/, const double* x_prior /*[12]*/);
 
 /* Values: q_i (RobotConfig), l_j (Point3), K0 (Pose3) */
+/*
+ * Optional DriftFactor links (include/arm_slam_calib/DriftFactor.h:44-61; added by AddDriftFactor when use_drift_noise is
+ * set, src/ArmSlamCalib.cpp:317-320, :1653-1668): has_drift[p] != 0 <=> DriftFactor(q_{p-1}, q_p) with measurement
+ * drift_meas[p][N] = q1Encoders - q0Encoders and Diagonal noise sigma_drift[N] (drift_noise_level, default 0.05).
+ * residual (q_p - q_{p-1}) - drift_meas[p], J0 = -I, J1 = +I: a block-tridiagonal term in the keyframe part of the normal
+ * equations.  Call after asc_set_problem (which drops earlier links); has_drift == NULL removes them.
+ */
+int asc_set_drift(asc_handle* h, const uint8_t* has_drift /*[P]*/, const double* drift_meas /*[P][N]*/, const double* sigma_drift /*[N]*/);
 int asc_set_values(asc_handle* h, const double* q /*[P][N]*/, const double* l /*[L][3]*/,
                    const double* x /*[12]*/);
 int asc_get_values(asc_handle* h, double* q, double* l, double* x);

@@ -272,6 +272,16 @@ private:
     bool hasDeadBand_;
 };
 
+class DriftFactor : public NonlinearFactor {   // include/arm_slam_calib/DriftFactor.h:18-61
+public:
+    DriftFactor(Key q0, Key q1, const Vector& q0Encoders_, const Vector& q1Encoders_, const SharedNoiseModel& model)
+        : q0Encoders(q0Encoders_), q1Encoders(q1Encoders_) { keys_.push_back(q0); keys_.push_back(q1); noise_ = model; }
+    const Vector& q0Measurement() const { return q0Encoders; }
+    const Vector& q1Measurement() const { return q1Encoders; }
+private:
+    Vector q0Encoders, q1Encoders;
+};
+
 template <class CameraCalibration> class RobotProjectionFactor : public NonlinearFactor {   // RobotProjectionFactor.h:52-70
 public:
     RobotProjectionFactor(const Point2& measured, const SharedNoiseModel& model, Key robotKey, Key landmarkKey, Key extrinsicKey,
@@ -399,7 +409,9 @@ private:
         // ---- factors
         std::vector<int32_t> pose_idx, lm_idx;
         std::vector<double> uv, enc(P * N_, 0.0), lm_prior(L * 3, 0.0), x_prior(12, 0.0);
-        std::vector<uint8_t> has_enc(P, 0), has_lm_prior(L, 0);
+        std::vector<uint8_t> has_enc(P, 0), has_lm_prior(L, 0), has_drift(P, 0);
+        std::vector<double> drift_meas(P * N_, 0.0), sigma_drift(N_, 0.05);
+        bool have_drift = false;
         bool have_x_prior = false, have_cam = false;
         double fx = 0, fy = 0, cx = 0, cy = 0;
         for (NonlinearFactorGraph::const_iterator it = graph.begin(); it != graph.end(); ++it) {
@@ -436,8 +448,18 @@ private:
                 if (!d) throw std::invalid_argument("the extrinsic prior needs Diagonal noise (ArmSlamCalib.cpp:684)");
                 for (int i = 0; i < 6; ++i) prm_.sigma_extrinsic[i] = d->sigmas()(i);   // tangent order, quirk of :684 preserved
                 have_x_prior = true;
+            } else if (const DriftFactor* df = dynamic_cast<const DriftFactor*>(f)) {
+                // AddDriftFactor (ArmSlamCalib.cpp:1653-1668) links consecutive configurations q_{i-1}, q_i
+                const int p0 = pose_of.at(df->keys()[0]), p1 = pose_of.at(df->keys()[1]);
+                if (p1 != p0 + 1) throw std::invalid_argument("DriftFactor must link consecutive configurations (ArmSlamCalib.cpp:1668)");
+                if (has_drift[p1]) throw std::invalid_argument("duplicate DriftFactor on " + DefaultKeyFormatter(df->keys()[1]));
+                has_drift[p1] = 1; have_drift = true;
+                for (int i = 0; i < N_; ++i) drift_meas[(size_t)p1 * N_ + i] = df->q1Measurement()(i) - df->q0Measurement()(i);
+                const noiseModel::Diagonal* d = dynamic_cast<const noiseModel::Diagonal*>(df->noiseModel().get());
+                if (!d) throw std::invalid_argument("drift factors need Diagonal noise (ArmSlamCalib.cpp:678)");
+                for (int i = 0; i < N_; ++i) sigma_drift[i] = d->sigmas()(i);
             } else {
-                throw std::invalid_argument("factor type outside the batch path (Drift/Velocity factors are not packed yet)");
+                throw std::invalid_argument("factor type outside the batch path (VelocityFactor is not packed)");
             }
         }
         if (!have_x_prior) throw std::invalid_argument("the graph has no PriorFactor<Pose3> on K0 (ArmSlamCalib.cpp:685)");
@@ -456,6 +478,7 @@ private:
         check(asc_set_camera(h_, fx, fy, cx, cy), h_);
         check(asc_set_problem(h_, (int32_t)P, (int32_t)L, (int64_t)pose_idx.size(), pose_idx.data(), lm_idx.data(), uv.data(), enc.data(),
                               has_enc.data(), lm_prior.data(), x_prior.data()), h_);
+        if (have_drift) check(asc_set_drift(h_, has_drift.data(), drift_meas.data(), sigma_drift.data()), h_);
         check(asc_set_values(h_, q.data(), l.data(), x.data()), h_);
     }
 

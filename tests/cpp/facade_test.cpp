@@ -50,6 +50,8 @@ int main(int argc, char** argv) {
     std::shared_ptr<Cal3_S2> calib = std::make_shared<Cal3_S2>(640, 640, 0.0, 320, 240);                        // :670
     noiseModel::mEstimator::Cauchy::shared_ptr cauchyEstimator = std::make_shared<noiseModel::mEstimator::Cauchy>(3.0);   // :197-199
     SharedNoiseModel encoderNoise = noiseModel::Diagonal::Sigmas(Vector::Constant(6, 0.1));                     // :672-677
+    SharedNoiseModel driftNoise = noiseModel::Diagonal::Sigmas(Vector::Constant(6, 0.05));                       // :678, drift_noise_level
+    const bool addDriftNoise = argc > 3 && std::string(argv[3]) == "drift";                                     // use_drift_noise, :373
     SharedNoiseModel calibrationPrior = noiseModel::Diagonal::Sigmas(Vector::Constant(6, 0.1));                 // :684
     SharedNoiseModel measurementNoise = noiseModel::Robust::Create(cauchyEstimator, noiseModel::Diagonal::Sigmas(Vector::Constant(2, 1.0)));   // :704
     SharedNoiseModel landmarkPrior = noiseModel::Robust::Create(cauchyEstimator, noiseModel::Diagonal::Sigmas(Vector::Constant(3, 50.0)));     // :705
@@ -60,6 +62,11 @@ int main(int argc, char** argv) {
         for (int k = 0; k < 6; ++k) e(k) = enc[6 * i + k];
         currentEstimate.insert(ConfigSymbol(i), RobotConfig(e, arm));
         graph->add(std::make_shared<EncoderFactor>(ConfigSymbol(i), e, encoderNoise, false, 0.05));
+        if (addDriftNoise && i > 0) {                                                                            // :317-320 -> AddDriftFactor :1653-1668
+            Vector e0(6);
+            for (int k = 0; k < 6; ++k) e0(k) = enc[6 * (i - 1) + k];
+            graph->add(std::make_shared<DriftFactor>(ConfigSymbol(i - 1), ConfigSymbol(i), e0, e, driftNoise));
+        }
     }
     for (int j = 0; j < L; ++j) {                                                                                // :1869-1870
         const Point3 pos(lt[3 * j], lt[3 * j + 1], lt[3 * j + 2]);

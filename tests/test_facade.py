@@ -52,3 +52,16 @@ def test_marginals_through_the_facade_match_the_oracle(asc, oracle_cls, facade_e
     rc, cov = orc.extrinsic_marginal(ref["q"], ref["l"], ref["x"])
     assert rc == 0
     assert np.abs(diag - np.diag(cov)).max() < 1e-4 * np.abs(np.diag(cov)).max()
+
+
+@pytest.mark.gpu
+def test_drift_factors_through_the_facade_match_the_oracle(asc, oracle_cls, facade_exe):
+    """use_drift_noise: DriftFactor between consecutive configurations (src/ArmSlamCalib.cpp:317-320, :1653-1668)."""
+    r = subprocess.run([facade_exe, "BatchLM", "40", "drift"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    tok = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    iters, err = int(tok[1]), float(tok[2])
+    pb = asc.with_drift(asc.make_sim_problem(trajectory_size=40, seed=3))
+    ref = oracle_cls(pb, asc.default_params()).optimize(pb.q0, pb.l0, pb.x0, mode=0, solver=0)
+    assert iters == ref["iterations"]
+    assert abs(err - ref["error"]) <= 1e-6 * ref["error"]

@@ -165,3 +165,37 @@ def test_extrinsic_marginal_matches_oracle(asc, oracle_cls, problems, name):
     r = orc.optimize(*vals, mode=0, solver=0)
     assert opt.iterations() == r["iterations"] and abs(opt.error() - r["error"]) <= 1e-6 * r["error"]
     opt.close()
+
+
+@pytest.mark.parametrize("name", ["small", "c1off"])
+def test_drift_factors_match_oracle(asc, oracle_cls, problems, name):
+    """DriftFactor(q_{p-1}, q_p) links (DriftFactor.h:44-61): error, keyframe blocks, exact damped step, both optimisers."""
+    pb = asc.with_drift(problems[name])
+    prm = asc.default_params()
+    opt = asc.BatchOptimizer(pb, prm)
+    orc = oracle_cls(pb, prm)
+    base = oracle_cls(problems[name], prm)
+    vals = perturbed_values(pb)
+    opt.set_values(*vals)
+    e_gpu, e_cpu = opt.graph_error(), orc.error(*vals)
+    assert abs(e_gpu - e_cpu) <= 1e-11 * e_cpu
+    assert e_cpu > base.error(*vals)           # the links do contribute
+    o = orc.linearize(*vals)
+    st = opt.linearize()
+    assert abs(st.error - o["error"]) <= 1e-11 * o["error"]
+    bpp, bpk, gp, bkk, gk = opt.pose_blocks()
+    assert rel(bpp, o["bpp"]) < 1e-9 and rel(gp, o["gp"]) < 1e-9
+    for lam in (1e-5, 1e-1):
+        rc, dq, dl, dx, _ = orc.solve_damped(*vals, lam, solver=0)
+        gq, gl_, gx, its = opt.solve_damped(lam)
+        s = np.abs(dq).max()
+        assert rc == 0 and np.abs(gq - dq).max() < 1e-7 * s and np.abs(gx - dx).max() < 1e-7 * s
+    for mode in (asc.ASC_BATCH_LM, asc.ASC_BATCH_DOGLEG):
+        opt.set_values(pb.q0, pb.l0, pb.x0)
+        q, l, x = opt.optimize(mode)
+        r = orc.optimize(pb.q0, pb.l0, pb.x0, mode=mode, solver=0)
+        assert opt.iterations() == r["iterations"]
+        for a, b in zip(opt.log, r["log"]):
+            assert abs(a.error - b.error) <= 1e-6 * b.error
+        assert np.abs(q - r["q"]).max() < 1e-5 and np.abs(x - r["x"]).max() < 1e-5
+    opt.close()
