@@ -7,6 +7,6 @@ from ._ctypes_defs import (ASC_BATCH_DOGLEG, ASC_BATCH_LM, ASC_ERR_CUDA, ASC_ERR
                            AscIterLog, AscLinearStats, AscParams, AscSimConfig)
 from .capi import (AscError, BatchOptimizer, IndeterminantLinearSystemException, Problem, default_params, lib,
                    optimization_mode_from_string, shard_by_landmark)
-from .sim import chain_generate, chain_mico, make_sim_problem, with_drift
+from .sim import chain_generate, chain_mico, make_sim_problem, with_drift, with_velocity
 
 __all__ = [n for n in dir() if not n.startswith("_")]

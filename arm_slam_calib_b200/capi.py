@@ -43,6 +43,7 @@ SIGNATURES = {
     "asc_get_landmark_blocks": (C.c_int, [_vp, _vp, _vp, _vp]),
     "asc_get_pose_blocks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "asc_set_drift": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "asc_set_velocity": (C.c_int, [_vp, _vp, _vp, _vp]),
     "asc_solve_damped": (C.c_int, [_vp, C.c_double, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
     "asc_extrinsic_marginal": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32)]),
     "asc_save_values": (C.c_int, [_vp]),
@@ -151,6 +152,11 @@ class Problem:
     has_drift: np.ndarray = None
     drift_meas: np.ndarray = None
     sigma_drift: np.ndarray = None
+    # VelocityFactor(q_{p-1}, q_p, velocities[p-1]) links (VelocityFactor.h:40-62; use_velocity_noise): residual (q_p - q_{p-1}) - vel_meas[p],
+    # per-joint sigma (velocity_noise_level, default 0.01)
+    has_vel: np.ndarray = None
+    vel_meas: np.ndarray = None
+    sigma_vel: np.ndarray = None
     # initial estimate (Values)
     q0: np.ndarray = None
     l0: np.ndarray = None
@@ -244,16 +250,25 @@ class BatchOptimizer:
         self.P, self.Lm, self.M, self.N = enc.shape[0], lp.shape[0], pi.shape[0], pb.n_dof
         if getattr(pb, "has_drift", None) is not None:
             self.set_drift(pb.has_drift, pb.drift_meas, pb.sigma_drift)
+        if getattr(pb, "has_vel", None) is not None:
+            self.set_velocity(pb.has_vel, pb.vel_meas, pb.sigma_vel)
+
+    def _set_links(self, fn, has, meas, sigma):
+        if has is None:
+            self._check(fn(self.h, None, None, None))
+            return
+        hd = np.ascontiguousarray(has, dtype=np.uint8)
+        dm = np.ascontiguousarray(meas, dtype=np.float64)
+        sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (self.N,)))
+        self._check(fn(self.h, _ptr(hd), _ptr(dm), _ptr(sg)))
 
     def set_drift(self, has_drift, drift_meas, sigma_drift):
         """DriftFactor(q_{p-1}, q_p) links (asc_set_drift); has_drift None removes them."""
-        if has_drift is None:
-            self._check(self.L.asc_set_drift(self.h, None, None, None))
-            return
-        hd = np.ascontiguousarray(has_drift, dtype=np.uint8)
-        dm = np.ascontiguousarray(drift_meas, dtype=np.float64)
-        sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma_drift, dtype=np.float64), (self.N,)))
-        self._check(self.L.asc_set_drift(self.h, _ptr(hd), _ptr(dm), _ptr(sg)))
+        self._set_links(self.L.asc_set_drift, has_drift, drift_meas, sigma_drift)
+
+    def set_velocity(self, has_vel, vel_meas, sigma_vel):
+        """VelocityFactor(q_{p-1}, q_p, qDot) links (asc_set_velocity); has_vel None removes them."""
+        self._set_links(self.L.asc_set_velocity, has_vel, vel_meas, sigma_vel)
 
     def set_values(self, q, l, x):
         q = np.ascontiguousarray(q, dtype=np.float64)

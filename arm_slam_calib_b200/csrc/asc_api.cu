@@ -165,10 +165,14 @@ struct asc_handle {
     double *enc = nullptr, *lm_prior = nullptr;
     uint8_t* has_enc = nullptr;
     // DriftFactor links (asc_set_drift): device tables live outside the arena (set after asc_set_problem)
-    uint8_t* d_has_drift = nullptr;   // [P + 1]
-    double *d_drift_meas = nullptr, *d_drift_w = nullptr;
-    bool drift_set = false;
-    DriftTab drift() const { DriftTab t; t.has = drift_set ? d_has_drift : nullptr; t.meas = d_drift_meas; t.w = d_drift_w; return t; }
+    uint8_t* d_has_link[2] = {nullptr, nullptr};   // [P + 1] per kind (0 drift, 1 velocity)
+    double *d_link_meas[2] = {nullptr, nullptr}, *d_link_w[2] = {nullptr, nullptr};
+    bool link_set[2] = {false, false};
+    DriftTab drift() const {
+        DriftTab t;
+        for (int k = 0; k < 2; ++k) { t.has[k] = link_set[k] ? d_has_link[k] : nullptr; t.meas[k] = d_link_meas[k]; t.w[k] = d_link_w[k]; }
+        return t;
+    }
     double *q = nullptr, *lm4 = nullptr, *X = nullptr, *q_try = nullptr, *lm4_try = nullptr, *X_try = nullptr;
     double *cam = nullptr, *chain = nullptr;
     double *lml = nullptr;       // landmark positions at the linearisation point (stable pointer: lm4 / lm4_try swap on accept)
@@ -978,7 +982,7 @@ int dispatch_schur_c(asc_handle* h, double lambda, double* x, double* u4_in) {
     case n:                                                                                                                       \
         schur_pass_c_kernel<n><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, 0, h->pose_ptr, h->p_lm, h->J, u4_in, x, \
                                                                          h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr, h->chain, h->lml, nullptr, nullptr, 0, \
-                                                                         nullptr, nullptr, 0, MidArgs{}, DriftTab{nullptr, nullptr, nullptr}); \
+                                                                         nullptr, nullptr, 0, MidArgs{}, DriftTab{{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}}); \
         break;
     switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
 #undef X
@@ -1029,7 +1033,8 @@ dogleg_pose_quad_kernel(int P, int N, const double* __restrict__ Bpp, const doub
             double k = 0.0;
             for (int c = 0; c < 6; ++c) k += BpK[(size_t)p * N * 6 + r * 6 + c] * gK[c];
             v += gp[r] * (t + 2.0 * k);
-            if (dt.has && dt.has[p]) v -= 2.0 * dt.w[r] * gp[r] * g[(size_t)(p - 1) * N + r];   // 2 g_{p-1}^T B_{p-1,p} g_p
+            for (int k = 0; k < 2; ++k)
+                if (dt.has[k] && dt.has[k][p]) v -= 2.0 * dt.w[k][r] * gp[r] * g[(size_t)(p - 1) * N + r];   // 2 g_{p-1}^T B_{p-1,p} g_p
         }
     }
     __shared__ double s[8];
@@ -1389,7 +1394,7 @@ int asc_destroy(asc_handle* h) {
     if (h->blas) cublasDestroy(h->blas);
     free_device(h);
     if (h->arena) cudaFree(h->arena);
-    if (h->d_has_drift) { cudaFree(h->d_has_drift); cudaFree(h->d_drift_meas); cudaFree(h->d_drift_w); }
+    for (int k = 0; k < 2; ++k) if (h->d_has_link[k]) { cudaFree(h->d_has_link[k]); cudaFree(h->d_link_meas[k]); cudaFree(h->d_link_w[k]); }
     if (h->work) cudaFree(h->work);
     if (h->workf) cudaFree(h->workf);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -1452,7 +1457,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     const int N = h->N;
     h->P = P; h->L = L; h->M = M;
     h->values_set = false; h->linearized = false; h->lin_lambda = -1.0;
-    h->drift_set = false;   // drift links belong to the packed graph: set them again after asc_set_problem
+    h->link_set[0] = h->link_set[1] = false;   // link factors belong to the packed graph: set them again after asc_set_problem
     h->coarse_valid = false; h->coarse_ref_iters = 0; h->coarse_last_iters = 0;
     if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }
     // constants
@@ -1762,31 +1767,39 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     return ASC_OK;
 }
 
-int asc_set_drift(asc_handle* h, const uint8_t* has_drift, const double* drift_meas, const double* sigma_drift) {
+static int set_links(asc_handle* h, int kind, const uint8_t* has, const double* meas, const double* sigma) {
     if (!h || !h->problem_set) return fail(ASC_ERR_INVALID, "set the problem first");
     CUDA_TRY(cudaSetDevice(h->dev));
-    h->drift_set = false;
+    h->link_set[kind] = false;
     h->linearized = false;
-    if (!has_drift) return ASC_OK;
-    if (!drift_meas || !sigma_drift) return fail(ASC_ERR_INVALID, "null argument");
+    if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }   // the link table is a kernel argument of the captured loop
+    if (!has) return ASC_OK;
+    if (!meas || !sigma) return fail(ASC_ERR_INVALID, "null argument");
     const int P = h->P, N = h->N;
-    for (int i = 0; i < N; ++i) if (!(sigma_drift[i] > 0)) return fail(ASC_ERR_INVALID, "drift sigma must be positive");
+    for (int i = 0; i < N; ++i) if (!(sigma[i] > 0)) return fail(ASC_ERR_INVALID, "link sigma must be positive");
     std::vector<uint8_t> hd((size_t)P + 1, 0);
-    for (int p = 1; p < P; ++p) hd[p] = has_drift[p] ? 1 : 0;   // a link needs a predecessor; [P] stays 0 (kernels read p + 1)
+    for (int p = 1; p < P; ++p) hd[p] = has[p] ? 1 : 0;   // a link needs a predecessor; [P] stays 0 (kernels read p + 1)
     std::vector<double> w(N);
-    for (int i = 0; i < N; ++i) { h->pc.inv_sigma_drift[i] = 1.0 / sigma_drift[i]; w[i] = h->pc.inv_sigma_drift[i] * h->pc.inv_sigma_drift[i]; }
+    for (int i = 0; i < N; ++i) { h->pc.inv_sigma_link[kind][i] = 1.0 / sigma[i]; w[i] = h->pc.inv_sigma_link[kind][i] * h->pc.inv_sigma_link[kind][i]; }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (h->d_has_drift) { cudaFree(h->d_has_drift); cudaFree(h->d_drift_meas); cudaFree(h->d_drift_w); h->d_has_drift = nullptr; }
-    CUDA_TRY(cudaMalloc((void**)&h->d_has_drift, (size_t)P + 1));
-    CUDA_TRY(cudaMalloc((void**)&h->d_drift_meas, sizeof(double) * (size_t)P * N));
-    CUDA_TRY(cudaMalloc((void**)&h->d_drift_w, sizeof(double) * N));
-    CUDA_TRY(cudaMemcpyAsync(h->d_has_drift, hd.data(), (size_t)P + 1, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_drift_meas, drift_meas, sizeof(double) * (size_t)P * N, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->d_drift_w, w.data(), sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+    if (h->d_has_link[kind]) { cudaFree(h->d_has_link[kind]); cudaFree(h->d_link_meas[kind]); cudaFree(h->d_link_w[kind]); h->d_has_link[kind] = nullptr; }
+    CUDA_TRY(cudaMalloc((void**)&h->d_has_link[kind], (size_t)P + 1));
+    CUDA_TRY(cudaMalloc((void**)&h->d_link_meas[kind], sizeof(double) * (size_t)P * N));
+    CUDA_TRY(cudaMalloc((void**)&h->d_link_w[kind], sizeof(double) * N));
+    CUDA_TRY(cudaMemcpyAsync(h->d_has_link[kind], hd.data(), (size_t)P + 1, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_link_meas[kind], meas, sizeof(double) * (size_t)P * N, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_link_w[kind], w.data(), sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    h->drift_set = true;
-    if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }   // the drift table is a kernel argument of the captured loop
+    h->link_set[kind] = true;
     return ASC_OK;
+}
+
+int asc_set_drift(asc_handle* h, const uint8_t* has_drift, const double* drift_meas, const double* sigma_drift) {
+    return set_links(h, 0, has_drift, drift_meas, sigma_drift);
+}
+
+int asc_set_velocity(asc_handle* h, const uint8_t* has_velocity, const double* velocity_meas, const double* sigma_velocity) {
+    return set_links(h, 1, has_velocity, velocity_meas, sigma_velocity);
 }
 
 int asc_set_values(asc_handle* h, const double* q, const double* l, const double* x) {

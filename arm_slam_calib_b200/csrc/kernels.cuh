@@ -44,7 +44,7 @@ struct PriorConst {
     double x_prior[12];
     double inv_sigma_x[6];
     double inv_sigma_enc[20];
-    double inv_sigma_drift[20];   // DriftFactor sigmas (only read when a drift table is passed)
+    double inv_sigma_link[2][20];   // DriftFactor / VelocityFactor sigmas (only read when the link table is passed)
     int continuous_mask;          // bit i set: joint i is continuous (RobotConfig.h:72-77)
     int use_dead_band;
     double dead_band;
@@ -451,16 +451,18 @@ struct LinCfg {
     static constexpr size_t kBytes = sizeof(double) * (kPerWarpDoubles * kWarps + KF);
 };
 
-// DriftFactor(q_{p-1}, q_p) links (DriftFactor.h:44-61): has[p] != 0 (has[0] = has[P] = 0), meas[p][N] = q1Encoders - q0Encoders.
-// residual (q_p - q_{p-1}) - meas[p], J0 = -I, J1 = +I, Diagonal noise: B_{p-1,p-1} += W, B_pp += W, B_{p-1,p} = -W, W = diag(1/sigma^2).
+// Link factors between consecutive configurations: kind 0 = DriftFactor(q_{p-1}, q_p) (DriftFactor.h:44-61, meas = q1Encoders -
+// q0Encoders), kind 1 = VelocityFactor (VelocityFactor.h:40-62, meas = qDot).  has[k][p] != 0 (has[k][0] = has[k][P] = 0).
+// residual (q_p - q_{p-1}) - meas[k][p], J0 = -I, J1 = +I, Diagonal noise: B_{p-1,p-1} += W, B_pp += W, B_{p-1,p} = -W, W = diag(1/sigma^2).
 struct DriftTab {
-    const uint8_t* has;    // null: no drift factors
-    const double* meas;
-    const double* w;       // [N] 1 / sigma^2
+    const uint8_t* has[2];    // null: no factors of that kind
+    const double* meas[2];
+    const double* w[2];       // [N] 1 / sigma^2
+    __host__ __device__ bool any() const { return has[0] != nullptr || has[1] != nullptr; }
 };
-// whitened residual of the link (p-1, p), joint i
-__device__ __forceinline__ double drift_residual(const PriorConst& pc, const DriftTab& dt, const double* __restrict__ q, int N, int p, int i) {
-    return ((q[(size_t)p * N + i] - q[(size_t)(p - 1) * N + i]) - dt.meas[(size_t)p * N + i]) * pc.inv_sigma_drift[i];
+// whitened residual of the link (p-1, p) of kind k, joint i
+__device__ __forceinline__ double drift_residual(const PriorConst& pc, const DriftTab& dt, int k, const double* __restrict__ q, int N, int p, int i) {
+    return ((q[(size_t)p * N + i] - q[(size_t)(p - 1) * N + i]) - dt.meas[k][(size_t)p * N + i]) * pc.inv_sigma_link[k][i];
 }
 
 // whitened EncoderFactor residual of joint i (EncoderFactor.h:60-99): (q - enc) / sigma, SO(2)-wrapped if continuous
@@ -560,15 +562,19 @@ __device__ __forceinline__ void linearize_role(const Camera& cm, const PriorCons
         double v = tot[t];
         if (hi < N) {
             if (lo == hi && with_enc) v += pc.inv_sigma_enc[lo] * pc.inv_sigma_enc[lo];
-            if (lo == hi && dt.has) v += pc.inv_sigma_drift[lo] * pc.inv_sigma_drift[lo] * (double)((dt.has[p] ? 1 : 0) + (dt.has[p + 1] ? 1 : 0));
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (lo == hi && dt.has[k]) v += pc.inv_sigma_link[k][lo] * pc.inv_sigma_link[k][lo] * (double)((dt.has[k][p] ? 1 : 0) + (dt.has[k][p + 1] ? 1 : 0));
             B[lo * N + hi] = v; B[hi * N + lo] = v;
         } else if (hi < N + 6) BK[lo * 6 + (hi - N)] = v;
         else {                                               // hi == N+6: J_q^T b, plus the encoder factor's -J^T r (J = I)
             if (with_enc) v -= encoder_residual(pc, q[(size_t)p * N + lo], enc[(size_t)p * N + lo], lo) * pc.inv_sigma_enc[lo];
-            if (dt.has) {                                    // drift links: -J1^T r (this keyframe is q1) and -J0^T r (it is q0 of the next link)
-                if (dt.has[p]) v -= drift_residual(pc, dt, q, N, p, lo) * pc.inv_sigma_drift[lo];
-                if (dt.has[p + 1]) v += drift_residual(pc, dt, q, N, p + 1, lo) * pc.inv_sigma_drift[lo];
-            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (dt.has[k]) {                             // links: -J1^T r (this keyframe is q1) and -J0^T r (it is q0 of the next link)
+                    if (dt.has[k][p]) v -= drift_residual(pc, dt, k, q, N, p, lo) * pc.inv_sigma_link[k][lo];
+                    if (dt.has[k][p + 1]) v += drift_residual(pc, dt, k, q, N, p + 1, lo) * pc.inv_sigma_link[k][lo];
+                }
             g[lo] = v;
         }
     }
@@ -598,7 +604,7 @@ linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __r
                       double* __restrict__ BpK, double* __restrict__ gp, double* __restrict__ cta_part, double2* __restrict__ b_out,
                       unsigned long long* __restrict__ cheir_count, DriftTab dt) {
     typedef LinCfg<N> Cf;
-    if (!add_priors) dt.has = nullptr;   // like the encoder factors, drift factors are added by rank 0 only
+    if (!add_priors) { dt.has[0] = nullptr; dt.has[1] = nullptr; }   // like the encoder factors, link factors are added by rank 0 only
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kf = warp / Cf::W, role = warp % Cf::W;
@@ -614,11 +620,13 @@ linearize_pose_kernel(Camera cm, PriorConst pc, int P, int64_t M, const int* __r
         const bool with_enc = add_priors && (has_enc == nullptr || has_enc[p]);
         LinRoleDispatch<N, 0, STORE_B>::run(role, cm, pc, p, M, pose_ptr, p_lm, p_uv, lm4, q, enc, with_enc, dt, J, Bpp, BpK, gp, b_out, cheir_count,
                                              s_cam, s_chain, lane);
-        if (role == 0 && (with_enc || dt.has)) {   // EncoderFactor / DriftFactor error 0.5 |r / sigma|^2 (a link is counted at its q1)
+        if (role == 0 && (with_enc || dt.any())) {   // EncoderFactor / link-factor error 0.5 |r / sigma|^2 (a link is counted at its q1)
             double e2 = 0.0;
             if (lane < N) {
                 if (with_enc) { const double wr = encoder_residual(pc, q[(size_t)p * N + lane], enc[(size_t)p * N + lane], lane); e2 = 0.5 * wr * wr; }
-                if (dt.has && dt.has[p]) { const double wd = drift_residual(pc, dt, q, N, p, lane); e2 += 0.5 * wd * wd; }
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (dt.has[k] && dt.has[k][p]) { const double wd = drift_residual(pc, dt, k, q, N, p, lane); e2 += 0.5 * wd * wd; }
             }
             e2 = warp_sum(e2);
             if (lane == 0) s_enc[kf] = e2;
@@ -1842,11 +1850,13 @@ schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int
                 for (int i = 0; i < N; ++i) t = fma(B[i], xp[i], t);
 #pragma unroll
                 for (int i = 0; i < 6; ++i) t = fma(BK[i], xK[i], t);
-                if (dt.has) {   // B_{p,p-1} x_{p-1} + B_{p,p+1} x_{p+1} = -W (x_{p-1} [link p] + x_{p+1} [link p+1])
-                    const double w = dt.w[lane];
-                    if (dt.has[p]) t -= w * x[(size_t)(p - 1) * N + lane];
-                    if (dt.has[p + 1]) t -= w * x[(size_t)(p + 1) * N + lane];
-                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (dt.has[k]) {   // B_{p,p-1} x_{p-1} + B_{p,p+1} x_{p+1} = -W (x_{p-1} [link p] + x_{p+1} [link p+1])
+                        const double w = dt.w[k][lane];
+                        if (dt.has[k][p]) t -= w * x[(size_t)(p - 1) * N + lane];
+                        if (dt.has[k][p + 1]) t -= w * x[(size_t)(p + 1) * N + lane];
+                    }
                 mine += t;
             }
             // B_pK^T x_p : lane c < 6 takes column c
@@ -2245,8 +2255,9 @@ error_prior_kernel(Camera cm, PriorConst pc, int N, int P, int L, int with_enc, 
                 e += 0.5 * w * w;
             }
         }
-        if (with_enc && dt.has && dt.has[i])   // DriftFactor(q_{i-1}, q_i), rank 0 only like the encoders
-            for (int c = 0; c < N; ++c) { const double w = drift_residual(pc, dt, q, N, i, c); e += 0.5 * w * w; }
+        for (int k = 0; k < 2; ++k)
+            if (with_enc && dt.has[k] && dt.has[k][i])   // Drift / Velocity factor on (q_{i-1}, q_i), rank 0 only like the encoders
+                for (int c = 0; c < N; ++c) { const double w = drift_residual(pc, dt, k, q, N, i, c); e += 0.5 * w * w; }
     } else if (i < P + L) {
         const int j = i - P;
         const double r0 = (lm4[4 * (size_t)j] - lm_prior[3 * (size_t)j]) * cm.inv_sigma_lm, r1 = (lm4[4 * (size_t)j + 1] - lm_prior[3 * (size_t)j + 1]) * cm.inv_sigma_lm,

@@ -97,3 +97,18 @@ def with_drift(pb, sigma=0.05):
     hd = np.ones(P, dtype=np.uint8); hd[0] = 0
     meas = np.zeros((P, N)); meas[1:] = pb.enc[1:] - pb.enc[:-1]
     return dataclasses.replace(pb, has_drift=hd, drift_meas=meas, sigma_drift=np.full(N, float(sigma)))
+
+
+def with_velocity(pb, sigma=0.01, seed=0):
+    """The same problem with VelocityFactor(q_{p-1}, q_p, velocities[p-1]) between consecutive configurations, as SimulationStep adds
+    them when use_velocity_noise is set (src/ArmSlamCalib.cpp:322-325, :1671-1686).  The measured joint velocity is synthesised as
+    the true increment plus N(0, sigma) noise (the reference records qDot + N(0, velocity_noise_level), :588); Diagonal sigma =
+    velocity_noise_level (0.01, ArmSlamCalib.h:80)."""
+    import dataclasses
+    import numpy as np
+    P, N = pb.enc.shape
+    qt = pb.meta.get("q_truth", pb.enc)
+    rng = np.random.default_rng(seed)
+    hv = np.ones(P, dtype=np.uint8); hv[0] = 0
+    meas = np.zeros((P, N)); meas[1:] = (qt[1:] - qt[:-1]) + rng.normal(0.0, sigma, size=(P - 1, N))
+    return dataclasses.replace(pb, has_vel=hv, vel_meas=meas, sigma_vel=np.full(N, float(sigma)))

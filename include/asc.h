@@ -150,6 +150,14 @@ int asc_set_problem(asc_handle* h, int32_t n_poses, int32_t n_landmarks, int64_t
  * equations.  Call after asc_set_problem (which drops earlier links); has_drift == NULL removes them.
  */
 int asc_set_drift(asc_handle* h, const uint8_t* has_drift /*[P]*/, const double* drift_meas /*[P][N]*/, const double* sigma_drift /*[N]*/);
+/*
+ * Optional VelocityFactor links (include/arm_slam_calib/VelocityFactor.h:40-62; AddVelocityFactor when use_velocity_noise is set,
+ * src/ArmSlamCalib.cpp:322-325, :1671-1686): has_velocity[p] != 0 <=> VelocityFactor(q_{p-1}, q_p, velocities[p-1]) with
+ * velocity_meas[p][N] = qDot and Diagonal noise sigma_velocity[N] (velocity_noise_level, default 0.01).  residual
+ * (q_p - q_{p-1}) - qDot; its central-difference Jacobians of a linear function are exactly J0 = -I, J1 = +I, so it is the
+ * DriftFactor's analytic twin and shares its kernels.  Same call rules as asc_set_drift; both kinds may be present.
+ */
+int asc_set_velocity(asc_handle* h, const uint8_t* has_velocity /*[P]*/, const double* velocity_meas /*[P][N]*/, const double* sigma_velocity /*[N]*/);
 int asc_set_values(asc_handle* h, const double* q /*[P][N]*/, const double* l /*[L][3]*/,
                    const double* x /*[12]*/);
 int asc_get_values(asc_handle* h, double* q, double* l, double* x);

@@ -282,6 +282,14 @@ private:
     Vector q0Encoders, q1Encoders;
 };
 
+class VelocityFactor : public NonlinearFactor {   // include/arm_slam_calib/VelocityFactor.h:20-35
+public:
+    VelocityFactor(Key q0, Key q1, const Vector& qDot_, const SharedNoiseModel& model) : qDot(qDot_) { keys_.push_back(q0); keys_.push_back(q1); noise_ = model; }
+    const Vector& measurement() const { return qDot; }
+private:
+    Vector qDot;
+};
+
 template <class CameraCalibration> class RobotProjectionFactor : public NonlinearFactor {   // RobotProjectionFactor.h:52-70
 public:
     RobotProjectionFactor(const Point2& measured, const SharedNoiseModel& model, Key robotKey, Key landmarkKey, Key extrinsicKey,
@@ -411,7 +419,9 @@ private:
         std::vector<double> uv, enc(P * N_, 0.0), lm_prior(L * 3, 0.0), x_prior(12, 0.0);
         std::vector<uint8_t> has_enc(P, 0), has_lm_prior(L, 0), has_drift(P, 0);
         std::vector<double> drift_meas(P * N_, 0.0), sigma_drift(N_, 0.05);
-        bool have_drift = false;
+        std::vector<uint8_t> has_vel(P, 0);
+        std::vector<double> vel_meas(P * N_, 0.0), sigma_vel(N_, 0.01);
+        bool have_drift = false, have_vel = false;
         bool have_x_prior = false, have_cam = false;
         double fx = 0, fy = 0, cx = 0, cy = 0;
         for (NonlinearFactorGraph::const_iterator it = graph.begin(); it != graph.end(); ++it) {
@@ -458,8 +468,18 @@ private:
                 const noiseModel::Diagonal* d = dynamic_cast<const noiseModel::Diagonal*>(df->noiseModel().get());
                 if (!d) throw std::invalid_argument("drift factors need Diagonal noise (ArmSlamCalib.cpp:678)");
                 for (int i = 0; i < N_; ++i) sigma_drift[i] = d->sigmas()(i);
+            } else if (const VelocityFactor* vf = dynamic_cast<const VelocityFactor*>(f)) {
+                // AddVelocityFactor (ArmSlamCalib.cpp:1671-1686) links consecutive configurations q_{i-1}, q_i with velocities[i-1]
+                const int p0 = pose_of.at(vf->keys()[0]), p1 = pose_of.at(vf->keys()[1]);
+                if (p1 != p0 + 1) throw std::invalid_argument("VelocityFactor must link consecutive configurations (ArmSlamCalib.cpp:1685)");
+                if (has_vel[p1]) throw std::invalid_argument("duplicate VelocityFactor on " + DefaultKeyFormatter(vf->keys()[1]));
+                has_vel[p1] = 1; have_vel = true;
+                for (int i = 0; i < N_; ++i) vel_meas[(size_t)p1 * N_ + i] = vf->measurement()(i);
+                const noiseModel::Diagonal* d = dynamic_cast<const noiseModel::Diagonal*>(vf->noiseModel().get());
+                if (!d) throw std::invalid_argument("velocity factors need Diagonal noise (ArmSlamCalib.cpp:679)");
+                for (int i = 0; i < N_; ++i) sigma_vel[i] = d->sigmas()(i);
             } else {
-                throw std::invalid_argument("factor type outside the batch path (VelocityFactor is not packed)");
+                throw std::invalid_argument("factor type outside the batch path");
             }
         }
         if (!have_x_prior) throw std::invalid_argument("the graph has no PriorFactor<Pose3> on K0 (ArmSlamCalib.cpp:685)");
@@ -479,6 +499,7 @@ private:
         check(asc_set_problem(h_, (int32_t)P, (int32_t)L, (int64_t)pose_idx.size(), pose_idx.data(), lm_idx.data(), uv.data(), enc.data(),
                               has_enc.data(), lm_prior.data(), x_prior.data()), h_);
         if (have_drift) check(asc_set_drift(h_, has_drift.data(), drift_meas.data(), sigma_drift.data()), h_);
+        if (have_vel) check(asc_set_velocity(h_, has_vel.data(), vel_meas.data(), sigma_vel.data()), h_);
         check(asc_set_values(h_, q.data(), l.data(), x.data()), h_);
     }
 

@@ -34,8 +34,8 @@ def _load():
         L.orc_error.argtypes = [_vp, _vp, _vp, _vp]
         L.orc_linearize.restype = C.c_double
         L.orc_linearize.argtypes = [_vp] + [_vp] * 16
-        L.orc_set_drift.restype = None
-        L.orc_set_drift.argtypes = [_vp, _vp, _vp, _vp]
+        L.orc_set_links.restype = None
+        L.orc_set_links.argtypes = [_vp, C.c_int, _vp, _vp, _vp]
         L.orc_extrinsic_marginal.restype = C.c_int
         L.orc_extrinsic_marginal.argtypes = [_vp, _vp, _vp, _vp, _vp]
         L.orc_solve_damped.restype = C.c_int
@@ -78,15 +78,18 @@ class Oracle:
                                    pb.fx, pb.fy, pb.cx, pb.cy, self.P, self.Lm, self.M, _p(k["pi"]), _p(k["li"]), _p(k["uv"]),
                                    _p(k["enc"]), _p(k["he"]), _p(k["lp"]), _p(k["xp"]))
         if getattr(pb, "has_drift", None) is not None:
-            self.set_drift(pb.has_drift, pb.drift_meas, pb.sigma_drift)
+            self.set_links(0, pb.has_drift, pb.drift_meas, pb.sigma_drift)
+        if getattr(pb, "has_vel", None) is not None:
+            self.set_links(1, pb.has_vel, pb.vel_meas, pb.sigma_vel)
 
-    def set_drift(self, has_drift, meas, sigma):
-        """DriftFactor(q_{p-1}, q_p) where has_drift[p] != 0 (DriftFactor.h:44-61); meas [P][N] = q1Encoders - q0Encoders."""
-        if has_drift is None:
-            self.L.orc_set_drift(self.h, None, None, None)
+    def set_links(self, kind, has, meas, sigma):
+        """Link factors on (q_{p-1}, q_p) where has[p] != 0: kind 0 = DriftFactor (DriftFactor.h:44-61, meas = q1Encoders - q0Encoders),
+        kind 1 = VelocityFactor (VelocityFactor.h:40-62, meas = qDot)."""
+        if has is None:
+            self.L.orc_set_links(self.h, kind, None, None, None)
             return
-        hd = np.ascontiguousarray(has_drift, dtype=np.uint8); m = _f64(meas); sg = _f64(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (self.N,)))
-        self.L.orc_set_drift(self.h, _p(hd), _p(m), _p(sg))
+        hd = np.ascontiguousarray(has, dtype=np.uint8); m = _f64(meas); sg = _f64(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (self.N,)))
+        self.L.orc_set_links(self.h, kind, _p(hd), _p(m), _p(sg))
 
     def close(self):
         if self.h:

@@ -88,13 +88,15 @@ def whitened_residuals(pb, prm, q, l, x12):
 
 
 def drift_residuals(pb, q):
-    """DriftFactor (DriftFactor.h:44-61): (q1 - q0) - (q1Encoders - q0Encoders), Diagonal sigma; linear, no robust weight."""
+    """DriftFactor (DriftFactor.h:44-61): (q1 - q0) - (q1Encoders - q0Encoders); VelocityFactor (VelocityFactor.h:40-62):
+    (q1 - q0) - qDot.  Diagonal sigma; linear, no robust weight."""
     out = []
-    if getattr(pb, "has_drift", None) is not None:
-        sg = np.broadcast_to(np.asarray(pb.sigma_drift, dtype=np.float64), (pb.n_dof,))
-        for p in range(1, pb.n_poses):
-            if pb.has_drift[p]:
-                out.append(((q[p] - q[p - 1]) - pb.drift_meas[p]) / sg)
+    for has, meas, sigma in (("has_drift", "drift_meas", "sigma_drift"), ("has_vel", "vel_meas", "sigma_vel")):
+        if getattr(pb, has, None) is not None:
+            sg = np.broadcast_to(np.asarray(getattr(pb, sigma), dtype=np.float64), (pb.n_dof,))
+            for p in range(1, pb.n_poses):
+                if getattr(pb, has)[p]:
+                    out.append(((q[p] - q[p - 1]) - getattr(pb, meas)[p]) / sg)
     return out
 
 

@@ -171,7 +171,12 @@ def test_extrinsic_marginal_matches_oracle(asc, oracle_cls, problems, name):
 def test_drift_factors_match_oracle(asc, oracle_cls, problems, name):
     """DriftFactor(q_{p-1}, q_p) links (DriftFactor.h:44-61): error, keyframe blocks, exact damped step, both optimisers."""
     pb = asc.with_drift(problems[name])
+    if name == "small":     # both link kinds at once: VelocityFactor (VelocityFactor.h:40-62) on top of the drift links, with a gap
+        pb = asc.with_velocity(pb)
+        pb.has_vel[3] = 0
     prm = asc.default_params()
+    if name == "small":
+        prm.max_iterations = 15     # the stiff velocity links make LM crawl towards GTSAM's convergence test; compare 15 iterations
     opt = asc.BatchOptimizer(pb, prm)
     orc = oracle_cls(pb, prm)
     base = oracle_cls(problems[name], prm)
