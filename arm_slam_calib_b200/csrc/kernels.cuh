@@ -340,56 +340,9 @@ __device__ __forceinline__ void gram_finish(double (&acc)[GramCfg<D>::H]) {
     }
 }
 
-// Register-blocked variant used by the linearise kernel: the D x D Gram matrix is cut into 4x4 blocks, one lane per
-// lower-triangular block pair; per observation row a lane loads 2 x 4 values (LDS.128, broadcast across lanes that share
-// a block) and issues 16 FMAs.  The per-pair variant above is shared-memory-bandwidth bound (1 LDS per FMA); this one is
-// balanced between the LDS and the fp64 pipe.  Rows are padded to Dp = 4*ceil(D/4) with zeros.
-template <int D>
-struct GramBlk {
-    static constexpr int Dp = (D + 3) / 4 * 4;
-    static constexpr int NB = Dp / 4;
-    static constexpr int NPAIR = NB * (NB + 1) / 2;
-    static constexpr int G = NPAIR <= 16 ? 2 : 1;    // two half-warps split the two residual rows when they fit
-    static constexpr int GS = 32 / G;
-    static constexpr int LD = Dp + 2;                // LD/2 odd: 16-byte chunks of consecutive lanes fall in distinct bank groups
-    static_assert(NPAIR <= 32, "DOF too large for one warp of block pairs");
-};
-
-template <int D>
-__device__ __forceinline__ void gram4_pair(int lane, int& bi, int& bj, bool& active) {
-    const int q = lane % GramBlk<D>::GS;
-    active = q < GramBlk<D>::NPAIR;
-    bi = 0;
-    while ((bi + 1) * (bi + 2) / 2 <= q) ++bi;
-    bj = q - bi * (bi + 1) / 2;
-    if (!active) { bi = 0; bj = 0; }
-}
-
-template <int D>
-__device__ __forceinline__ void gram4_tile(const double* __restrict__ A, int count, int lane, int bi, int bj, bool active, double (&acc)[16]) {
-    typedef GramBlk<D> Cf;
-    if (!active) return;
-    const int g = lane / Cf::GS;
-    for (int o = 0; o < count; ++o) {
-#pragma unroll
-        for (int rr = 0; rr < 2 / Cf::G; ++rr) {
-            const int r = Cf::G == 2 ? g : rr;
-            const double* row = A + (r * 32 + o) * Cf::LD;
-            const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * bi), a23 = *reinterpret_cast<const double2*>(row + 4 * bi + 2);
-            const double2 b01 = *reinterpret_cast<const double2*>(row + 4 * bj), b23 = *reinterpret_cast<const double2*>(row + 4 * bj + 2);
-            const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[4 * x + y] = fma(a[x], b[y], acc[4 * x + y]);
-        }
-    }
-}
-
-// ---- Gram accumulation without shared memory: every lane forms the D(D+1)/2 products of ITS OWN factor rows in
-// registers, and 32 products at a time are summed across the warp by a butterfly "transpose-reduce" (31 shuffles for
-// 32 sums, fixed tree): afterwards lane l holds the warp total of product number l.  Measured background: the
-// shared-memory tile variants of this step were LDS-wavefront bound (20 wavefronts per factor, ncu l1tex 83 %).
+// ---- Warp totals of per-lane accumulators: 32 values per lane are summed across the warp by a butterfly
+// "transpose-reduce" (31 shuffles for 32 sums, fixed tree); afterwards lane l holds the warp total of value number l.
+// Used once per keyframe by K1 and once per warp by K1b.
 template <int D>
 __host__ __device__ constexpr int tri_row(int e) { int a = 0, rem = e; while (rem >= D - a) { rem -= D - a; ++a; } return a; }
 template <int D>
