@@ -733,7 +733,8 @@ struct Engine {
         }
         CUDA_TRY(cudaGetLastError());
         const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
-        const int chunk = 8;
+        static const int chunk_env = getenv("ASC_PCG_CHUNK") ? atoi(getenv("ASC_PCG_CHUNK")) : 0;
+        const int chunk = chunk_env > 0 ? chunk_env : 8;   // iterations per graph launch / host check of the done flag
         int launched = 0;
         const double* lam_dev = h->scal + 8;
         const bool p2p = h->world > 1 && h->p2p_ok && h->use_clusters;   // peer-memory exchange instead of ncclAllReduce
