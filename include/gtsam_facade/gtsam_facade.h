@@ -24,6 +24,7 @@
 #include <exception>
 #include <map>
 #include <memory>
+#include <ostream>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -97,13 +98,35 @@ typedef std::string (*KeyFormatter)(Key);
 
 struct Point2 { double x_, y_; Point2(double x = 0, double y = 0) : x_(x), y_(y) {} double x() const { return x_; } double y() const { return y_; } };
 struct Point3 { double x_, y_, z_; Point3(double x = 0, double y = 0, double z = 0) : x_(x), y_(y), z_(z) {}
-                double x() const { return x_; } double y() const { return y_; } double z() const { return z_; } };
+                double x() const { return x_; } double y() const { return y_; } double z() const { return z_; }
+                Point3 operator-(const Point3& o) const { return Point3(x_ - o.x_, y_ - o.y_, z_ - o.z_); }     // ComputeError, ArmSlamCalib.cpp:1377
+                Point3 operator+(const Point3& o) const { return Point3(x_ + o.x_, y_ + o.y_, z_ + o.z_); }
+                double norm() const { return std::sqrt(x_ * x_ + y_ * y_ + z_ * z_); } };
+struct Quaternion { double x_, y_, z_, w_; double x() const { return x_; } double y() const { return y_; } double z() const { return z_; } double w() const { return w_; } };
 
 class Rot3 {
 public:
     Rot3() { std::memset(R, 0, sizeof R); R[0] = R[4] = R[8] = 1; }
     static Rot3 identity() { return Rot3(); }
     static Rot3 rodriguez(double wx, double wy, double wz);   // sim_genrobot.cpp:67
+    Quaternion toQuaternion() const {                          // PrintSimErrors, ArmSlamCalib.cpp:2224 (Eigen's matrix -> quaternion branches)
+        Quaternion q;
+        const double t = R[0] + R[4] + R[8];
+        if (t > 0) {
+            const double s = std::sqrt(t + 1.0) * 2;
+            q.w_ = 0.25 * s; q.x_ = (R[7] - R[5]) / s; q.y_ = (R[2] - R[6]) / s; q.z_ = (R[3] - R[1]) / s;
+        } else {
+            int i = 0;
+            if (R[4] > R[0]) i = 1;
+            if (R[8] > R[4 * i]) i = 2;
+            const int j = (i + 1) % 3, k = (i + 2) % 3;
+            const double s = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0) * 2;
+            double v[3];
+            v[i] = 0.25 * s; v[j] = (R[3 * j + i] + R[3 * i + j]) / s; v[k] = (R[3 * k + i] + R[3 * i + k]) / s;
+            q.x_ = v[0]; q.y_ = v[1]; q.z_ = v[2]; q.w_ = (R[3 * k + j] - R[3 * j + k]) / s;
+        }
+        return q;
+    }
     double R[9];   // row-major
 };
 
@@ -321,6 +344,23 @@ public:
     size_t size() const { return factors_.size(); }
     void resize(size_t n) { factors_.resize(n); }
     const NonlinearFactor::shared_ptr& at(size_t i) const { return factors_.at(i); }
+    // `*newGraph = graph->clone();` (ArmSlamCalib.cpp:2209).  The facade's factors are immutable data holders, so sharing them is a deep
+    // copy in effect.
+    NonlinearFactorGraph clone() const { return *this; }
+    // graphviz dot of the factor graph, `graph->saveGraph(os, currentEstimate)` (ArmSlamCalib.cpp:1910-1913): one node per variable,
+    // one point per factor, edges factor -- variable
+    void saveGraph(std::ostream& os, const Values& values, KeyFormatter fmt = DefaultKeyFormatter) const {
+        os << "graph {\n  size=\"5,5\";\n\n";
+        for (Values::const_iterator it = values.begin(); it != values.end(); ++it)
+            os << "  var" << (*it).key << "[label=\"" << fmt((*it).key) << "\"];\n";
+        os << "\n";
+        for (size_t i = 0; i < factors_.size(); ++i) {
+            if (!factors_[i]) continue;
+            os << "  factor" << i << "[label=\"\", shape=point];\n";
+            for (size_t k = 0; k < factors_[i]->keys().size(); ++k) os << "  var" << factors_[i]->keys()[k] << "--factor" << i << ";\n";
+        }
+        os << "}\n";
+    }
 private:
     std::vector<NonlinearFactor::shared_ptr> factors_;
 };

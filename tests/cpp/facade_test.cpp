@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sstream>
 #include <string>
 
 #include "gtsam_facade/gtsam_facade.h"
@@ -117,6 +118,15 @@ int main(int argc, char** argv) {
     for (int j = 0; j < L; ++j)
         if (currentEstimate.find(LandmarkSymbol(lm_id[j])) != currentEstimate.end()) { (void)currentEstimate.at<gtsam::Point3>(LandmarkSymbol(lm_id[j])); ++found; }
     printf("RESULT %d %.12g %.12g %.12g %.12g %zu\n", iterations, total_error, X.translation().x(), X.translation().y(), X.translation().z(), found);
+    if (argc > 3 && std::string(argv[3]) == "dot") {
+        // the rest of the GTSAM surface ArmSlamCalib.cpp touches: saveGraph (:1910-1913), clone (:2209), Rot3::toQuaternion (:2224), Point3 ops (:1377)
+        std::ostringstream os;
+        graph->saveGraph(os, currentEstimate);
+        NonlinearFactorGraph copy = graph->clone();
+        const Quaternion qx = X.rotation().toQuaternion();
+        const double d = (currentEstimate.at<Point3>(LandmarkSymbol(lm_id[0])) - Point3(lt[0], lt[1], lt[2])).norm();
+        printf("DOT %zu %zu %.6f %.6f\n", os.str().size(), copy.size(), qx.w() * qx.w() + qx.x() * qx.x() + qx.y() * qx.y() + qx.z() * qx.z(), d);
+    }
     if (argc > 3 && std::string(argv[3]) == "marginal") {
         // batch counterpart of  extrinsicMarginals = isam2.marginalCovariance(ExtrinsicSymbol());  (src/ArmSlamCalib.cpp:490-493)
         try {

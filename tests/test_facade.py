@@ -65,3 +65,13 @@ def test_drift_factors_through_the_facade_match_the_oracle(asc, oracle_cls, faca
     ref = oracle_cls(pb, asc.default_params()).optimize(pb.q0, pb.l0, pb.x0, mode=0, solver=0)
     assert iters == ref["iterations"]
     assert abs(err - ref["error"]) <= 1e-6 * ref["error"]
+
+
+@pytest.mark.gpu
+def test_remaining_gtsam_surface_through_the_facade(facade_exe):
+    """saveGraph (src/ArmSlamCalib.cpp:1910-1913), NonlinearFactorGraph::clone (:2209), Rot3::toQuaternion (:2224), Point3 ops (:1377)."""
+    r = subprocess.run([facade_exe, "BatchLM", "20", "dot"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    tok = [l for l in r.stdout.splitlines() if l.startswith("DOT")][0].split()
+    dot_bytes, n_factors, qnorm, moved = int(tok[1]), int(tok[2]), float(tok[3]), float(tok[4])
+    assert dot_bytes > 1000 and n_factors > 20 and abs(qnorm - 1.0) < 1e-6 and moved >= 0.0
