@@ -3,7 +3,7 @@ import ctypes as C
 
 ASC_MAX_DOF = 20
 
-ASC_OK, ASC_ERR_INVALID, ASC_ERR_CUDA, ASC_ERR_INDETERMINATE, ASC_ERR_COMM = range(5)
+ASC_OK, ASC_ERR_INVALID, ASC_ERR_CUDA, ASC_ERR_INDETERMINATE, ASC_ERR_COMM, ASC_ERR_NOT_CONVERGED = range(6)
 ASC_BATCH_LM, ASC_BATCH_DOGLEG = 0, 1
 ASC_POSE3_FIRST_ORDER_CAYLEY, ASC_POSE3_FIRST_ORDER_EXPMAP, ASC_POSE3_FULL_EXPMAP = 0, 1, 2
 
@@ -33,9 +33,10 @@ class AscParams(C.Structure):
         ("device", C.c_int32),
         ("pcg_cluster_max", C.c_int32),
         ("pcg_cluster_covis", C.c_double),
-        ("pcg_coarse_max_dim", C.c_int32),
-        ("pcg_coarse_fp32", C.c_int32),
-        ("pcg_coarse_agg", C.c_int32),
+        ("pcg_coarse_levels", C.c_int32),
+        ("pcg_ml_degree", C.c_int32),
+        ("pcg_ml_agg", C.c_int32),
+        ("pcg_ml_top_dim", C.c_int32),
     ]
 
 
@@ -49,6 +50,9 @@ class AscIterLog(C.Structure):
         ("lambda_or_delta", C.c_double),
         ("linearize_ms", C.c_double),
         ("solve_ms", C.c_double),
+        ("prepare_ms", C.c_double),
+        ("coarse_ms", C.c_double),
+        ("pcg_ms", C.c_double),
     ]
 
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libasc_b200.so")
 SOURCES = ["asc_api.cu", "sim_generator.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "host_math.h", os.path.join("..", "..", "include", "asc.h")]
+DEPS = SOURCES + ["kernels.cuh", "coarse_ml.cuh", "host_math.h", os.path.join("..", "..", "include", "asc.h")]
 
 
 STAMP = LIB + ".dofs"   # which DOF instantiations the existing library holds ("all" = the default list)
@@ -35,7 +35,7 @@ def build(force=False, verbose=False, dof_list=None):
         cmd += ["-Xptxas", "-v"]
     if dof_list:
         cmd += ["-DASC_DOF_LIST(X)=" + " ".join("X(%d)" % n for n in dof_list)]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lgomp", "-lcusolver", "-lcublas", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lgomp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "asc_restore_values": (C.c_int, [_vp]),
     "asc_launch_count": (C.c_int64, [_vp]),
     "asc_solver_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "asc_coarse_info": (C.c_int, [_vp, C.POINTER(C.c_int32), _vp, _vp, C.c_int32, C.POINTER(C.c_int32)]),
     "asc_timer_start": (C.c_int, [_vp]),
     "asc_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "asc_profile_begin": (C.c_int, [_vp, C.c_int32, C.c_int32]),
@@ -318,6 +319,14 @@ class BatchOptimizer:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int64()
         self._check(self.L.asc_solver_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def coarse_info(self):
+        """Hierarchy of the multilevel coarse solve: dict(levels=[(nodes, nonzero N x N blocks), ...], degree=Chebyshev degree); the last
+        level is the dense top level.  Empty list: no coarse level."""
+        n, deg = C.c_int32(), C.c_int32()
+        nodes = np.zeros(16, np.int32); blocks = np.zeros(16, np.int64)
+        self._check(self.L.asc_coarse_info(self.h, C.byref(n), _ptr(nodes), _ptr(blocks), 16, C.byref(deg)))
+        return dict(levels=[(int(nodes[i]), int(blocks[i])) for i in range(min(n.value, 16))], degree=deg.value)
 
     def extrinsic_marginal(self):
         """K0 block of (A^T A)^-1 at the current values (src/ArmSlamCalib.cpp:490-493); returns (cov 6x6, PCG iterations)."""

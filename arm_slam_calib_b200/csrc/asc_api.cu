@@ -1,9 +1,7 @@
 // Host side of the B200 batch optimiser: the C ABI of include/asc.h, problem packing, the
 // LM / Dogleg controllers and the kernel launch sequences.
 // There is no CPU fallback in this file: every compute entry point needs an sm_100 device.
-#include <cublas_v2.h>
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types only; the library is dlopen()ed when a communicator is requested
 #include <omp.h>
@@ -20,6 +18,7 @@
 #include "../../include/asc.h"
 #include "host_math.h"
 #include "kernels.cuh"
+#include "coarse_ml.cuh"
 
 using namespace asck;
 
@@ -97,12 +96,14 @@ namespace {
 // order); ptr[b] = start of bucket b.  Host packing of a 2M-observation graph is on the end-to-end path of every optimize().
 template <typename KeyFn>
 void parallel_bucket_sort(int64_t n, int nb, KeyFn key, std::vector<int>& ptr, int* dest) {
-    const int T = std::max(1, std::min(omp_get_max_threads(), 16));
-    std::vector<int> hist((size_t)T * nb, 0);
+    const int Tmax = std::max(1, std::min(omp_get_max_threads(), 16));
+    std::vector<int> hist((size_t)Tmax * nb, 0);
     ptr.assign((size_t)nb + 1, 0);
-#pragma omp parallel num_threads(T)
+    // The team may be SMALLER than requested (nested region with nesting off, OMP_DYNAMIC, OMP_THREAD_LIMIT, a cgroup
+    // limit): every slice is derived from the team size the runtime actually delivered, never from Tmax.
+#pragma omp parallel num_threads(Tmax)
     {
-        const int t = omp_get_thread_num();
+        const int T = omp_get_num_threads(), t = omp_get_thread_num();
         const int64_t lo = n * t / T, hi = n * (t + 1) / T;
         int* h = hist.data() + (size_t)t * nb;
         for (int64_t i = lo; i < hi; ++i) h[key(i)]++;
@@ -125,6 +126,89 @@ void parallel_bucket_sort(int64_t n, int nb, KeyFn key, std::vector<int>& ptr, i
 
 }  // namespace
 
+
+// ---- host side of the multilevel coarse solve (coarse_ml.cuh): patterns, aggregates and index lists, built once per packed graph
+namespace {
+
+struct MlHostLevel {
+    int n = 0;
+    std::vector<int> row_ptr, col, diag_pos;   // BSR pattern, both triangles, columns ascending
+    std::vector<double> w;                     // static edge weight per block (shared-landmark pair count, summed on coarsening)
+    std::vector<int> agg, mptr, midx;          // aggregation to the next level
+    std::vector<int> cptr, cidx;               // children of each block of the NEXT level among this level's blocks
+    int n_next = 0;
+};
+
+// Greedy heavy-edge aggregation: seeds in order of decreasing weighted degree; an aggregate grows by the unassigned neighbour
+// with the largest total weight to its current members (ties: smallest index) until it holds `gs` nodes.  Deterministic.
+void ml_aggregate(const MlHostLevel& L, int gs, std::vector<int>& agg, int& na) {
+    const int n = L.n;
+    agg.assign(n, -1);
+    na = 0;
+    std::vector<double> deg(n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int k = L.row_ptr[i]; k < L.row_ptr[i + 1]; ++k)
+            if (L.col[k] != i) deg[i] += L.w[k];
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+    std::vector<double> cand(n, 0.0);
+    std::vector<int> touched;
+    for (int seed : order) {
+        if (agg[seed] >= 0) continue;
+        touched.clear();
+        int size = 0, cur = seed;
+        for (;;) {
+            agg[cur] = na; ++size;
+            for (int k = L.row_ptr[cur]; k < L.row_ptr[cur + 1]; ++k) {
+                const int j = L.col[k];
+                if (agg[j] < 0) { if (cand[j] == 0.0) touched.push_back(j); cand[j] += L.w[k] > 0 ? L.w[k] : 1e-300; }
+            }
+            if (size >= gs) break;
+            int best = -1; double bw = 0.0;
+            for (int j : touched)
+                if (agg[j] < 0 && (cand[j] > bw || (cand[j] == bw && best >= 0 && j < best))) { best = j; bw = cand[j]; }
+            if (best < 0) break;
+            cur = best;
+        }
+        for (int j : touched) cand[j] = 0.0;
+        ++na;
+    }
+}
+
+// next level's pattern = image of this level's blocks under the aggregation; child lists in block order
+void ml_coarsen_pattern(MlHostLevel& L, MlHostLevel& C) {
+    const int na = L.n_next;
+    C.n = na;
+    std::vector<std::vector<std::pair<int, int>>> rows(na);   // per coarse row: (coarse col, fine block)
+    for (int i = 0; i < L.n; ++i)
+        for (int k = L.row_ptr[i]; k < L.row_ptr[i + 1]; ++k) rows[L.agg[i]].push_back({L.agg[L.col[k]], k});
+    C.row_ptr.assign(na + 1, 0); C.col.clear(); C.w.clear(); C.diag_pos.assign(na, -1);
+    L.cptr.assign(1, 0); L.cidx.clear();
+    for (int a = 0; a < na; ++a) {
+        auto& r = rows[a];
+        std::stable_sort(r.begin(), r.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first < y.first; });
+        size_t q = 0;
+        while (q < r.size()) {
+            const int cb = r[q].first;
+            double wsum = 0.0;
+            if (cb == a) C.diag_pos[a] = (int)C.col.size();
+            while (q < r.size() && r[q].first == cb) { L.cidx.push_back(r[q].second); wsum += L.w[r[q].second]; ++q; }
+            C.col.push_back(cb); C.w.push_back(wsum);
+            L.cptr.push_back((int)L.cidx.size());
+        }
+        C.row_ptr[a + 1] = (int)C.col.size();
+    }
+    L.mptr.assign(na + 1, 0);
+    for (int i = 0; i < L.n; ++i) L.mptr[L.agg[i] + 1]++;
+    for (int a = 0; a < na; ++a) L.mptr[a + 1] += L.mptr[a];
+    L.midx.assign(L.n, 0);
+    std::vector<int> fill(L.mptr.begin(), L.mptr.end() - 1);
+    for (int i = 0; i < L.n; ++i) L.midx[fill[L.agg[i]]++] = i;
+}
+
+}  // namespace
+
 struct asc_handle {
     asc_params prm;
     int dev = 0;
@@ -132,6 +216,8 @@ struct asc_handle {
     cudaStream_t stream2 = nullptr;              // side stream: cluster blocks run beside the coarse factorisation (single GPU)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries inside one damped solve (asc_iter_log)
+    double ms_prepare = 0, ms_coarse = 0, ms_pcg = 0, ms_error = 0;                        // accumulated over the inner steps of one iterate()
     int N = 0, P = 0, L = 0;
     int64_t M = 0;
     bool chain_set = false, cam_set = false, problem_set = false, values_set = false, linearized = false;
@@ -147,8 +233,6 @@ struct asc_handle {
     // peer-memory exchange of the PCG loop (kernels.cuh, PeerComm): one IPC-shared buffer per rank
     PeerComm pcm{};
     bool p2p_ok = false;
-    bool coarse_sharded = false;    // the rows of E^-1 are computed 1/G per rank and all-gathered
-    int crow0 = 0, crows = 0, crows_per_rank = 0;
     char* xbuf = nullptr;           // this rank's exchange buffer [flags 256 B | slot 0 | slot 1]
     size_t xbuf_bytes = 0;
     void* peer_map[kMaxPeers] = {nullptr};   // cudaIpcOpenMemHandle mappings of the peers' buffers
@@ -187,8 +271,6 @@ struct asc_handle {
     double *partA = nullptr, *partB = nullptr, *partC = nullptr, *partL = nullptr, *partR = nullptr, *errblk = nullptr;
     int nCtaPose = 0, nBlkLm = 0, nErrBlk = 0;
     int nBlkB = 0;               // CTAs of schur_pass_b_kernel (kPassBLmPerBlock landmarks each)
-    double *grpC = nullptr, *grpB = nullptr;     // group rows of pass C / pass B partials (kernels.cuh, grouped_rows_reduce)
-    unsigned *tickC = nullptr, *tickB = nullptr, *tickG = nullptr;   // their ticket counters; tickG: coarse GEMV
     int nBlkLmK2 = 0;            // CTAs of landmark_blocks_kernel (kLmPerBlock landmarks each)
     double* lmerr = nullptr;     // their landmark-prior error partials
     double *scal = nullptr, *status = nullptr;
@@ -208,25 +290,30 @@ struct asc_handle {
     int *cl_ptr = nullptr, *pose_cluster = nullptr, *p_run_lo = nullptr, *p_run_hi = nullptr;
     long long* cl_off = nullptr;
     double *Wm = nullptr, *Mc = nullptr;
-    // coarse level (two-level additive preconditioner)
+    // coarse level (two-level additive preconditioner; multilevel V-cycle on its block-sparse operator, coarse_ml.cuh)
     bool use_coarse = false;
-    int nz = 0, nInc = 0, nDest = 0;
-    int nA = 0, aggS = 1;           // coarse aggregates: aggS consecutive clusters each
-    int *agg_pose_ptr = nullptr, *agg_inc_ptr = nullptr, *pose_agg = nullptr;
-    double* rca = nullptr;          // aggregated restriction (length nz)
-    double *ryc = nullptr, *qc = nullptr;   // side-branch GEMV: Z^T y and Einv Z^T y
+    int n1 = 0, nz = 0, nInc = 0, nDest = 0;   // n1 = nC * N cluster unknowns of the coarse space, nz = n1 + 6
+    int* pose_agg = nullptr;                   // keyframe -> coarse node (= its cluster)
+    double *ryc = nullptr;                     // side branch: Z^T y
     cudaEvent_t ev_c = nullptr, ev_q = nullptr;
-    int *inc_lo = nullptr, *inc_hi = nullptr, *inc_lm = nullptr, *dest_ptr = nullptr, *dest_ca = nullptr, *dest_cb = nullptr;
+    int *inc_lo = nullptr, *inc_hi = nullptr, *inc_lm = nullptr, *dest_ptr = nullptr, *pos_lo = nullptr, *pos_up = nullptr;
     int *pair_a = nullptr, *pair_b = nullptr, *cl_inc_ptr = nullptr, *cl_inc = nullptr;
-    double *Vinc = nullptr, *Tinc = nullptr, *E = nullptr, *rc = nullptr, *zc = nullptr, *yc = nullptr, *SKK = nullptr, *work = nullptr;
-    int lwork = 0, lworkf = 0;
-    float *Ef = nullptr, *workf = nullptr, *Einvf = nullptr;
-    float *Xf = nullptr, *Tf = nullptr;   // U^-1 and a GEMM scratch of the single-GPU inverse (invert_from_cholesky_f32)
-    bool coarse_f32_active = false;   // E^-1 currently lives in Ef (fp32) rather than in E (fp64)
-    bool coarse_refit = false;      // this solve reuses an older inverse: fit its scalar against the freshly assembled E
-    bool coarse_valid = false;      // E holds a factorised inverse (possibly from an earlier lambda / linearisation)
-    bool coarse_fresh = false;      // ... computed for exactly the current system
-    int coarse_ref_iters = 0;       // PCG iterations of the solve that followed the last refresh
+    double *Vinc = nullptr, *Tinc = nullptr, *rc = nullptr, *zc = nullptr, *SKK = nullptr;
+    struct MlLevel {                // one level of the hierarchy; the last one is the dense top level
+        int n = 0, nnzb = 0, n_next = 0;
+        int *row_ptr = nullptr, *col = nullptr, *diag_pos = nullptr;          // BSR pattern (both triangles)
+        int *agg = nullptr, *mptr = nullptr, *midx = nullptr;                 // node -> aggregate; members of each aggregate
+        int *cptr = nullptr, *cidx = nullptr;                                 // blocks of THIS level that sum into each block of the next
+        double *Eb = nullptr, *Dinv = nullptr, *lmax = nullptr;
+        double *r = nullptr, *za = nullptr, *zb = nullptr, *d = nullptr;      // V-cycle vectors (r of level 0 is the caller's)
+    };
+    std::vector<MlLevel> ml;
+    double *mlblk = nullptr;        // [Eb of level 0 | EK]: one all-reduce in a multi-GPU run
+    double *EK = nullptr, *Yb = nullptr, *Ski = nullptr;   // extrinsic border of level 1, Y = V E_cK, S_k^-1
+    double *Atop = nullptr, *ztop = nullptr, *mlpart = nullptr, *mlcol = nullptr;
+    int ntop = 0, ml_degree = 4;
+    double ml_frac = 10.0;
+    const double* ml_out = nullptr;  // where the V-cycle leaves its result (static for a given hierarchy and degree)
     int coarse_last_iters = 0;
     int outer_iteration = 0;
     bool warm_ok = false;           // vx holds the solution of an earlier damping value of the SAME linearisation
@@ -234,8 +321,6 @@ struct asc_handle {
     // CUDA graph of one chunk of PCG iterations (single GPU; all kernel arguments are handle-lifetime pointers)
     cudaGraphExec_t pcg_graph = nullptr;
     int pcg_graph_key = -1, pcg_graph_launches = 0;        // LM/Dogleg iterate() count inside the running asc_optimize call
-    cusolverDnHandle_t solver = nullptr;
-    cublasHandle_t blas = nullptr;
     double* h_status = nullptr;  // pinned: status(32) + scal(8)
     int* h_flags = nullptr;      // pinned
 };
@@ -283,6 +368,55 @@ int allreduce(asc_handle* h, double* buf, size_t count) {
     return ASC_OK;
 }
 
+
+// Multi-GPU: every rank must build the same coarse hierarchy, but a rank only sees the cluster pairs its own landmarks couple.
+// Union of the sorted key lists of all ranks (weights summed), through two all-gathers of padded device buffers.
+int union_block_keys(asc_handle* h, std::vector<long long>& keys, std::vector<double>& w) {
+    if (!g_nccl.AllGather) return fail(ASC_ERR_COMM, "libnccl has no ncclAllGather");
+    const int G = h->world;
+    long long* d_cnt = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_cnt, sizeof(long long) * G));
+    long long mine = (long long)keys.size();
+    CUDA_TRY(cudaMemcpyAsync(d_cnt + h->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    if (g_nccl.AllGather(d_cnt + h->rank, d_cnt, 1, ncclInt64, h->comm, h->stream) != ncclSuccess) { cudaFree(d_cnt); return fail(ASC_ERR_COMM, "ncclAllGather failed"); }
+    std::vector<long long> cnt(G);
+    CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * G, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(d_cnt);
+    size_t nmax = 1;
+    for (int r = 0; r < G; ++r) nmax = std::max(nmax, (size_t)cnt[r]);
+    long long* d_keys = nullptr; double* d_w = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_keys, sizeof(long long) * nmax * G));
+    CUDA_TRY(cudaMalloc((void**)&d_w, sizeof(double) * nmax * G));
+    CUDA_TRY(cudaMemcpyAsync(d_keys + nmax * h->rank, keys.data(), sizeof(long long) * keys.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_w + nmax * h->rank, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice, h->stream));
+    if (g_nccl.AllGather(d_keys + nmax * h->rank, d_keys, nmax, ncclInt64, h->comm, h->stream) != ncclSuccess ||
+        g_nccl.AllGather(d_w + nmax * h->rank, d_w, nmax, ncclDouble, h->comm, h->stream) != ncclSuccess) {
+        cudaFree(d_keys); cudaFree(d_w);
+        return fail(ASC_ERR_COMM, "ncclAllGather failed");
+    }
+    std::vector<long long> ak(nmax * G);
+    std::vector<double> aw(nmax * G);
+    CUDA_TRY(cudaMemcpyAsync(ak.data(), d_keys, sizeof(long long) * nmax * G, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(aw.data(), d_w, sizeof(double) * nmax * G, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(d_keys); cudaFree(d_w);
+    // G-way merge of sorted lists
+    std::vector<size_t> pos(G, 0);
+    keys.clear(); w.clear();
+    for (;;) {
+        long long best = -1;
+        for (int r = 0; r < G; ++r)
+            if (pos[r] < (size_t)cnt[r]) { const long long k = ak[nmax * r + pos[r]]; if (best < 0 || k < best) best = k; }
+        if (best < 0) break;
+        double ws = 0.0;
+        for (int r = 0; r < G; ++r)
+            if (pos[r] < (size_t)cnt[r] && ak[nmax * r + pos[r]] == best) { ws += aw[nmax * r + pos[r]]; ++pos[r]; }
+        keys.push_back(best); w.push_back(ws);
+    }
+    return ASC_OK;
+}
+
 inline void prof_start(asc_handle* h, int id) {
     if (h->prof_id == id && 2 * h->prof_n + 1 < (int)h->prof_ev.size()) cudaEventRecord(h->prof_ev[2 * h->prof_n], h->stream);
 }
@@ -305,63 +439,6 @@ ChainConst<N> make_chain_const(const asc_handle* h) {
     return cc;
 }
 
-// ---- E^-1 from its Cholesky factor, single GPU (all column-major, leading dimension ld).
-// cuSOLVER's potrs with an identity right-hand side runs two n x n TRSMs (2 n^3 flop, 14.2 ms at n = 6006 on a B200, 30 TFLOP/s).
-// Here U^-1 comes from a block recursion ( [U11 U12; 0 U22]^-1 = [X11 -X11 U12 X22; 0 X22], TRSM leaves, SGEMM for the
-// off-diagonal block: 4.7 ms ) and E^-1 = U^-1 U^-T from a 2 x 2 blocked SYRK that skips the zero block (2.9 ms).
-__global__ void ident_block_f32_kernel(float* A, int m, int ld) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (size_t)m * m) { const int c = (int)(i / m), r = (int)(i % m); A[(size_t)c * ld + r] = (r == c) ? 1.0f : 0.0f; }
-}
-
-int inv_upper_f32(asc_handle* h, const float* U, float* X, int m, int ld, float* T) {
-    const float one = 1.f, zero = 0.f, mone = -1.f;
-    if (m <= 1024) {
-        ident_block_f32_kernel<<<cdiv((int64_t)m * m, 256), 256, 0, h->stream>>>(X, m, ld);
-        if (cublasStrsm(h->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, m, m, &one, U, ld, X, ld) != CUBLAS_STATUS_SUCCESS)
-            return fail(ASC_ERR_CUDA, "cublasStrsm failed");
-        return ASC_OK;
-    }
-    const int m1 = (m / 2 + 31) / 32 * 32, m2 = m - m1;
-    int rc = inv_upper_f32(h, U, X, m1, ld, T);
-    if (rc) return rc;
-    rc = inv_upper_f32(h, U + (size_t)m1 * ld + m1, X + (size_t)m1 * ld + m1, m2, ld, T);
-    if (rc) return rc;
-    if (cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, m1, m2, m2, &one, U + (size_t)m1 * ld, ld, X + (size_t)m1 * ld + m1, ld, &zero, T, m1) != CUBLAS_STATUS_SUCCESS ||
-        cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, m1, m2, m1, &mone, X, ld, T, m1, &zero, X + (size_t)m1 * ld, ld) != CUBLAS_STATUS_SUCCESS)
-        return fail(ASC_ERR_CUDA, "cublasSgemm failed");
-    return ASC_OK;
-}
-
-// Ef holds U (potrf, UPPER); on return Einvf holds the full symmetric inverse (row-major == column-major)
-int invert_from_cholesky_f32(asc_handle* h, int n) {
-    const float one = 1.f, zero = 0.f;
-    CUDA_TRY(cudaMemsetAsync(h->Xf, 0, sizeof(float) * (size_t)n * n, h->stream));
-    int rc = inv_upper_f32(h, h->Ef, h->Xf, n, n, h->Tf);
-    if (rc) return rc;
-    if (n < 128) {   // tiny coarse spaces: one SYRK
-        if (cublasSsyrk(h->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, n, n, &one, h->Xf, n, &zero, h->Einvf, n) != CUBLAS_STATUS_SUCCESS)
-            return fail(ASC_ERR_CUDA, "cublasSsyrk failed");
-        const int nbs = cdiv(n, 32);
-        mirror_lower_f32_kernel<<<dim3(nbs, nbs), 256, 0, h->stream>>>(h->Einvf, n);
-        CUDA_TRY(cudaGetLastError());
-        return ASC_OK;
-    }
-    const int m1 = (n / 2 + 31) / 32 * 32, m2 = n - m1;
-    const float *X11 = h->Xf, *X12 = h->Xf + (size_t)m1 * n, *X22 = h->Xf + (size_t)m1 * n + m1;
-    float *C11 = h->Einvf, *C12 = h->Einvf + (size_t)m1 * n, *C22 = h->Einvf + (size_t)m1 * n + m1;
-    if (cublasSsyrk(h->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, m1, m1, &one, X11, n, &zero, C11, n) != CUBLAS_STATUS_SUCCESS ||
-        cublasSsyrk(h->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, m1, m2, &one, X12, n, &one, C11, n) != CUBLAS_STATUS_SUCCESS ||
-        cublasSgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, m1, m2, m2, &one, X12, n, X22, n, &zero, C12, n) != CUBLAS_STATUS_SUCCESS ||
-        cublasSsyrk(h->blas, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, m2, m2, &one, X22, n, &zero, C22, n) != CUBLAS_STATUS_SUCCESS)
-        return fail(ASC_ERR_CUDA, "cuBLAS syrk/gemm failed in the coarse inverse");
-    // column-major UPPER == row-major lower: complete the rows
-    const int nb = cdiv(n, 32);
-    mirror_lower_f32_kernel<<<dim3(nb, nb), 256, 0, h->stream>>>(h->Einvf, n);
-    CUDA_TRY(cudaGetLastError());
-    return ASC_OK;
-}
-
 // ------------------------------------------------------------------ launch sequences (templated on DOF)
 template <int N>
 struct Engine {
@@ -374,20 +451,21 @@ struct Engine {
         return ASC_OK;
     }
 
-    static int setup_attrs() {
-        static bool done = false;
-        if (done) return ASC_OK;
+    static int setup_attrs(const asc_handle* h) {
+        static bool done[64] = {false};   // the opt-in is per device (and per template instance)
+        const int dev = h->dev < 64 ? h->dev : 63;
+        if (done[dev] && h->dev < 63) return ASC_OK;
         CUDA_TRY(cudaFuncSetAttribute(pose_schur_diag_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PrecSmem<N>::kBytes));
         CUDA_TRY(cudaFuncSetAttribute(cluster_schur_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(cluster_schur_cta_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(cluster_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        done = true;
+        done[dev] = true;
         return ASC_OK;
     }
 
     // FK + K1/K2b + K2a + finish.  Leaves the undamped blocks and the error on the device.
     static int linearize(asc_handle* h, bool store_b, float* ms_lin, float* ms_asm) {
-        int rc = setup_attrs();
+        int rc = setup_attrs(h);
         if (rc) return rc;
         const int add_priors = h->rank == 0 ? 1 : 0;
         CUDA_TRY(cudaMemsetAsync(h->cheir, 0, sizeof(unsigned long long), h->stream));
@@ -434,7 +512,7 @@ struct Engine {
             rc = allreduce(h, h->poseblk, count);
             if (rc) return rc;
         }
-        pad3to4_kernel<<<cdiv((int64_t)h->L * 4, 256), 256, 0, h->stream>>>(h->L, h->gl, h->gl4);
+        if (h->L) pad3to4_kernel<<<cdiv((int64_t)h->L * 4, 256), 256, 0, h->stream>>>(h->L, h->gl, h->gl4);
         CUDA_TRY(cudaGetLastError());
         if (h->L) CUDA_TRY(cudaMemcpyAsync(h->lml, h->lm4, sizeof(double) * 4 * h->L, cudaMemcpyDeviceToDevice, h->stream));
         if (h->use_clusters && h->M) {
@@ -456,6 +534,7 @@ struct Engine {
 
     // damped landmark inverses, Schur-diagonal preconditioner, reduced right-hand side
     static int prepare(asc_handle* h, double lambda) {
+        CUDA_TRY(cudaEventRecord(h->ev_stage[0], h->stream));
         const int big = 0x7fffffff;
         int init_flags[16] = {0, big, big, big, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [8]: peer-exchange timeout
         h->launches += 5;
@@ -464,8 +543,8 @@ struct Engine {
         CUDA_TRY(cudaGetLastError());
         DBG_SYNC(h, "landmark_invert");
         // Single GPU: the cluster blocks (cluster_schur + cluster_invert, ~3 ms on C2) depend only on the landmark inverses, and
-        // so does the coarse operator (assembly + cuSOLVER factorisation, ~25 ms): the former run on a side stream beside the
-        // latter and are joined at the end of prepare().  Multi-GPU keeps one stream (the blocks go through an all-reduce).
+        // so does the coarse operator (assembly + multilevel set-up): the former run on a side stream beside the latter and
+        // are joined at the end of prepare().  Multi-GPU keeps one stream (the blocks go through an all-reduce).
         static const bool no_side = getenv("ASC_NO_SIDE_STREAM") != nullptr;
         const bool side = h->world == 1 && h->use_clusters && !no_side;
         cudaStream_t cs = side ? h->stream2 : h->stream;
@@ -515,101 +594,16 @@ struct Engine {
             const size_t sm = sizeof(double) * (size_t)h->nmax * (h->nmax | 1);
             if (!side) cluster_invert_kernel<<<h->nC, 256, sm, h->stream>>>(N, h->cl_ptr, h->cl_off, h->Dloc, h->gr, h->rloc, h->Mc, h->rhs, h->flags + 2);
             DBG_SYNC(h, "cluster_invert");
-            // The coarse operator is only a preconditioner: any SPD E^-1 keeps PCG exact, so a factorisation from an
-            // earlier lambda / linearisation is reused until it visibly costs iterations (deterministic policy).
-            const bool refresh = h->use_coarse && (!h->coarse_valid || h->coarse_last_iters > h->coarse_ref_iters + h->coarse_ref_iters / 4 + 8);
-            h->coarse_fresh = refresh;
-            h->coarse_refit = false;
-            if (refresh || (h->use_coarse && h->coarse_f32_active)) {
-                // E = Z^T S Z for the CURRENT system: needed for a rebuild, and (cheap, <1 ms) for re-fitting a reused inverse
-                CUDA_TRY(cudaGetLastError());
-                const int nz = h->nz;
-                inc_v_kernel<N><<<cdiv(std::max(h->nInc, 1), 4), 128, 0, h->stream>>>(h->nInc, h->inc_lo, h->inc_hi, h->inc_lm, h->l_perm, h->Wm, h->Cinv,
-                                                                                  h->Vinc, h->Tinc);
-                DBG_SYNC(h, "inc_v");
-                CUDA_TRY(cudaMemsetAsync(h->E, 0, sizeof(double) * (size_t)nz * nz, h->stream));
-                coarse_blocks_kernel<N><<<cdiv(std::max(h->nDest, 1), 4), 128, 0, h->stream>>>(h->nDest, h->dest_ptr, h->dest_ca, h->dest_cb, h->pair_a,
-                                                                                           h->pair_b, h->Vinc, h->Tinc, h->E, nz);
-                DBG_SYNC(h, "coarse_blocks");
-                if (h->rank == 0) coarse_diag_kernel<<<cdiv((int64_t)h->nA * N * N, 256), 256, 0, h->stream>>>(h->nA, N, lambda, h->agg_pose_ptr, h->Bpp, h->E, nz);
-                coarse_k_kernel<<<cdiv(std::max<int64_t>((int64_t)h->nA * N * 6, 36), 256), 256, 0, h->stream>>>(h->nA, N, h->rank == 0 ? 1 : 0, h->agg_pose_ptr, h->agg_inc_ptr,
-                                                                                                       h->cl_inc, h->inc_lm, h->Tinc, h->WK, h->BpK, h->SKK, h->E, nz);
-                CUDA_TRY(cudaGetLastError());
-                DBG_SYNC(h, "coarse_diag / coarse_k");
-                h->launches += 5;
-                if (h->world > 1) {   // S_KK is already global; undo its world-fold replication, then sum the shard contributions
-                    int rc2 = allreduce(h, h->E, (size_t)nz * nz);
-                    if (rc2) return rc2;
-                    // every rank wrote the same S_KK: rescale the 6x6 corner
-                    scale_block_kernel<<<1, 64, 0, h->stream>>>(h->E, nz, h->nA * N, 1.0 / h->world);
-                }
-                h->coarse_refit = !refresh;
+            CUDA_TRY(cudaEventRecord(h->ev_stage[1], h->stream));
+            if (h->use_coarse) {
+                int rcc = coarse_refresh(h, lambda);
+                if (rcc) return rcc;
             }
-            if (refresh) {
-                const int nz = h->nz;
-                h->coarse_valid = true;
-                static const bool timing = getenv("ASC_TIMING") != nullptr;
-                cudaEvent_t e0, e1, e2;
-                if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, h->stream); }
-                bool f32_ok = false;
-                if (h->prm.pcg_coarse_fp32 && h->Ef) {
-                    const size_t nn = (size_t)nz * nz;
-                    to_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->E, h->Ef, nn);
-                    CUDA_TRY(cudaGetLastError());
-                    if (getenv("ASC_DEBUG_SYNC")) { CUDA_TRY(cudaStreamSynchronize(h->stream)); fprintf(stderr, "[asc] pre-potrf ok: E %p Ef %p workf %p lworkf %d flags %p nz %d\n", (void*)h->E, (void*)h->Ef, (void*)h->workf, h->lworkf, (void*)h->flags, nz); }
-                    {
-                        const cusolverStatus_t st = cusolverDnSpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->Ef, nz, h->workf, h->lworkf, h->flags + 6);
-                        if (st != CUSOLVER_STATUS_SUCCESS)
-                            return fail(ASC_ERR_CUDA, "cusolverDnSpotrf failed: status %d, lwork %d, cuda: %s", (int)st, h->lworkf, cudaGetErrorString(cudaGetLastError()));
-                    }
-                    if (timing) cudaEventRecord(e1, h->stream);
-                    // E^-1 = solve(U^T U, I): two TRSMs run much closer to peak than cuSOLVER's potri.
-                    // Multi-GPU: every rank solves only for ITS columns of the identity = its rows of the (symmetric) inverse,
-                    // written in place at their row offset, and one in-place ncclAllGather completes the matrix on every rank
-                    // (1/G of the triangular-solve work each; the per-iteration product stays local).
-                    h->coarse_sharded = h->world > 1 && g_nccl.AllGather && getenv("ASC_NO_COARSE_SHARD") == nullptr;
-                    h->crows_per_rank = h->coarse_sharded ? (cdiv(nz, h->world) + 3) / 4 * 4 : nz;
-                    h->crow0 = h->coarse_sharded ? std::min(nz, h->rank * h->crows_per_rank) : 0;
-                    h->crows = h->coarse_sharded ? std::max(0, std::min(nz, h->crow0 + h->crows_per_rank) - h->crow0) : nz;
-                    float* slice = h->Einvf + (size_t)h->crow0 * nz;
-                    static const bool use_potrs = getenv("ASC_POTRS") != nullptr;
-                    if (h->world == 1 && h->Xf && !use_potrs) {   // single GPU: own inverse from the factor (see invert_from_cholesky_f32)
-                        int rci = invert_from_cholesky_f32(h, nz);
-                        if (rci) return rci;
-                    } else if (h->coarse_sharded) identity_slice_f32_kernel<<<cdiv((int64_t)nz * std::max(h->crows, 1), 256), 256, 0, h->stream>>>(slice, nz, h->crow0, h->crows);
-                    else identity_f32_kernel<<<cdiv((int64_t)nn, 256), 256, 0, h->stream>>>(h->Einvf, nz);
-                    if (!(h->world == 1 && h->Xf && !use_potrs) && h->crows > 0 &&
-                        cusolverDnSpotrs(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->crows, h->Ef, nz, slice, nz, h->flags + 7) != CUSOLVER_STATUS_SUCCESS)
-                        return fail(ASC_ERR_CUDA, "cusolverDnSpotrs failed");
-                    if (h->coarse_sharded) {
-                        const size_t cnt = (size_t)h->crows_per_rank * nz;   // Einvf holds world * cnt floats (padding rows after the last)
-                        if (g_nccl.AllGather(h->Einvf + (size_t)h->rank * cnt, h->Einvf, cnt, ncclFloat, h->comm, h->stream) != ncclSuccess)
-                            return fail(ASC_ERR_COMM, "ncclAllGather of the coarse inverse failed");
-                    }
-                    CUDA_TRY(cudaGetLastError());
-                    int info[2] = {0, 0};
-                    CUDA_TRY(cudaMemcpyAsync(info, h->flags + 6, sizeof info, cudaMemcpyDeviceToHost, h->stream));
-                    CUDA_TRY(cudaStreamSynchronize(h->stream));
-                    f32_ok = info[0] == 0 && info[1] == 0;   // not positive definite in fp32: redo in fp64 below
-                }
-                h->coarse_f32_active = f32_ok;
-                if (!f32_ok) h->coarse_sharded = false;   // the fp64 fallback factorises and inverts on every rank
-                if (!f32_ok) {
-                    if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 4) != CUSOLVER_STATUS_SUCCESS)
-                        return fail(ASC_ERR_CUDA, "cusolverDnDpotrf failed");
-                    if (timing) cudaEventRecord(e1, h->stream);
-                    if (cusolverDnDpotri(h->solver, CUBLAS_FILL_MODE_UPPER, nz, h->E, nz, h->work, h->lwork, h->flags + 5) != CUSOLVER_STATUS_SUCCESS)
-                        return fail(ASC_ERR_CUDA, "cusolverDnDpotri failed");
-                }
-                if (timing) {
-                    cudaEventRecord(e2, h->stream); cudaEventSynchronize(e2);
-                    float a = 0, b = 0, c = 0; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2); cudaEventElapsedTime(&c, h->ev[3], e0);
-                    fprintf(stderr, "[asc] coarse nz=%d %s potrf %.2f ms potri %.2f ms (since solve start %.2f ms)\n", nz, f32_ok ? "fp32" : "fp64", a, b, c);
-                    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-                }
-            }
+            CUDA_TRY(cudaEventRecord(h->ev_stage[2], h->stream));
         } else {
             pose_invert_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, lambda, h->Bpp, h->gr, h->Dloc, h->rloc, h->Minv, h->rhs, h->flags + 2);
+            CUDA_TRY(cudaEventRecord(h->ev_stage[1], h->stream));
+            CUDA_TRY(cudaEventRecord(h->ev_stage[2], h->stream));
         }
         CUDA_TRY(cudaGetLastError());
         if (side) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -618,10 +612,8 @@ struct Engine {
     }
 
     // one application y = S x written into ybuf; K rows handled by the caller's kernels.
-    // grouped: passes B and C also leave group rows of their CTA partials in grpB / grpC (PCG loop); fuse_mid: the CTA of
-    // pass C that finishes last runs pcg_mid_body (single GPU, inside the loop)
     static int schur_apply_launch(asc_handle* h, double lambda, bool update_p, double* x, const int* done, const double* lambda_dev = nullptr,
-                                  bool to_slot = false, bool grouped = false, const MidArgs* mid = nullptr) {
+                                  bool to_slot = false) {
         h->launches += 3;
         prof_start(h, 3);
         if (update_p)
@@ -634,58 +626,158 @@ struct Engine {
         prof_stop(h, 3);
         prof_start(h, 4);
         schur_pass_b_kernel<false><<<h->nBlkB, kPassBThreads, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, x + (size_t)h->P * N, done,
-                                                                             nullptr, h->u4, h->partB, grouped ? h->grpB : nullptr, grouped ? h->tickB : nullptr);
+                                                                             nullptr, h->u4, h->partB);
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 4);
         prof_start(h, 5);
-        MidArgs none{};
         schur_pass_c_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, h->rank == 0 ? 1 : 0, h->pose_ptr, h->p_lm, h->J, h->u4, x,
                                                                          h->Bpp, h->BpK, done, h->ybuf, h->partC, lambda_dev, h->chain, h->lml,
                                                                          to_slot ? h->pcm.ctr : nullptr, to_slot ? h->pcm.x[h->rank] : nullptr, h->pcm.stride,
-                                                                         grouped ? h->grpC : nullptr, grouped ? h->tickC : nullptr, mid ? 1 : 0, mid ? *mid : none,
                                                                          h->drift());
         CUDA_TRY(cudaGetLastError());
         prof_stop(h, 5);
         return ASC_OK;
     }
 
-    // zc = E^-1 (A rc) (coarse correction of the preconditioner; A sums the per-cluster restriction over each aggregate)
-    static const double* coarse_rhs(const asc_handle* h) { return h->aggS > 1 ? h->rca : h->rc; }
-    static int coarse_apply(asc_handle* h, const int* done, const EndArgs* end = nullptr) {
-        h->launches += 1;
-        if (h->aggS > 1) {
-            coarse_aggregate_kernel<<<cdiv(h->nz, 256), 256, 0, h->stream>>>(h->rc, h->rca, h->nz, h->nA, h->nC, N, h->aggS, done);
-            CUDA_TRY(cudaGetLastError());
+    // ---- multilevel coarse solve (coarse_ml.cuh)
+    static MlLevelDev level_dev(const asc_handle::MlLevel& L) {
+        MlLevelDev d;
+        d.n = L.n; d.row_ptr = L.row_ptr; d.col = L.col; d.Eb = L.Eb; d.Dinv = L.Dinv; d.lmax = L.lmax;
+        return d;
+    }
+
+    // t = V rin : one symmetric V-cycle on the cluster part of the coarse operator.  The result is left at h->ml_out (the
+    // buffer sequence is static for a given hierarchy and degree).  Kernels only: capturable, runs on any stream.
+    static int vcycle(asc_handle* h, const double* rin, const int* done, cudaStream_t st) {
+        const int nl = (int)h->ml.size() - 1;   // smoothed levels; ml[nl] is the dense top level
+        const int m = h->ml_degree;
+        std::vector<const double*> cur(nl + 1, nullptr);
+        for (int l = 0; l < nl; ++l) {   // down: pre-smooth from zero, restrict the residual
+            asc_handle::MlLevel& L = h->ml[l];
+            const MlLevelDev ld = level_dev(L);
+            const double* r = l == 0 ? rin : L.r;
+            const int grid = cdiv(L.n, 4);
+            double* bufs[2] = {L.za, L.zb};
+            for (int k = 0; k < m; ++k)   // step k writes bufs[k & 1]; step 0 starts from zero and reads no z
+                ml_cheb_step_kernel<N><<<grid, 128, 0, st>>>(ld, h->ml_frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], L.d, nullptr, nullptr, done);
+            cur[l] = bufs[(m - 1) & 1];
+            asc_handle::MlLevel& C = h->ml[l + 1];
+            ml_residual_restrict_kernel<N><<<cdiv(C.n, 4), 128, 0, st>>>(ld, C.n, L.mptr, L.midx, r, cur[l], C.r, done);
+            h->launches += m + 1;
+        }
+        {   // top: explicit dense inverse
+            asc_handle::MlLevel& T = h->ml[nl];
+            const double* r = nl == 0 ? rin : T.r;
+            ml_dense_gemv_kernel<<<cdiv(h->ntop, 4), 128, 0, st>>>(h->Atop, r, h->ztop, h->ntop, done);
+            cur[nl] = h->ztop;
             h->launches += 1;
         }
-        if (h->coarse_f32_active) {
-            EndArgs none{};
-            prof_start(h, 8);
-            {
-                coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream>>>(h->Einvf, coarse_rhs(h), h->zc, h->nz, done, h->scal + 9, end ? *end : none,
-                                                                             end ? h->tickG : nullptr);
+        for (int l = nl - 1; l >= 0; --l) {   // up: prolong (inside the first step), post-smooth
+            asc_handle::MlLevel& L = h->ml[l];
+            const MlLevelDev ld = level_dev(L);
+            const double* r = l == 0 ? rin : L.r;
+            const int grid = cdiv(L.n, 4);
+            const double* zi = cur[l];
+            for (int k = 0; k < m; ++k) {
+                double* zo = zi == L.za ? L.zb : L.za;
+                ml_cheb_step_kernel<N><<<grid, 128, 0, st>>>(ld, h->ml_frac, k, 0, r, zi, zo, L.d, k == 0 ? cur[l + 1] : nullptr, k == 0 ? L.agg : nullptr, done);
+                zi = zo;
             }
-            CUDA_TRY(cudaGetLastError());
-            prof_stop(h, 8);
-        } else {
-            const double one = 1.0, zero = 0.0;
-            if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, coarse_rhs(h), 1, &zero, h->zc, 1) != CUBLAS_STATUS_SUCCESS)
-                return fail(ASC_ERR_CUDA, "cublasDsymv failed");
+            cur[l] = zi;
+            h->launches += m;
         }
+        CUDA_TRY(cudaGetLastError());
+        if (h->ml_out && h->ml_out != cur[0]) return fail(ASC_ERR_INVALID, "internal: V-cycle output buffer moved");
+        h->ml_out = cur[0];
         return ASC_OK;
     }
 
-    // block-Jacobi PCG on the reduced system; solution left in vx.  Returns iterations through *iters.
+    // Assemble the level-1 operator for the current system, set up every level (diagonal-block inverses, spectral bound,
+    // Galerkin block sums), invert the dense top level, and eliminate the extrinsic border: Y = V E_cK, S_k^-1.
+    static int coarse_refresh(asc_handle* h, double lambda) {
+        const int nl = (int)h->ml.size() - 1;
+        asc_handle::MlLevel& L0 = h->ml[0];
+        inc_v_kernel<N><<<cdiv(std::max(h->nInc, 1), 4), 128, 0, h->stream>>>(h->nInc, h->inc_lo, h->inc_hi, h->inc_lm, h->l_perm, h->Wm, h->Cinv, h->Vinc, h->Tinc);
+        DBG_SYNC(h, "inc_v");
+        ml_blocks_l1_kernel<N><<<cdiv(std::max(h->nDest, 1), 4), 128, 0, h->stream>>>(h->nDest, h->dest_ptr, h->pos_lo, h->pos_up, h->pair_a, h->pair_b, h->Vinc, h->Tinc, L0.Eb);
+        DBG_SYNC(h, "ml_blocks_l1");
+        if (h->rank == 0) ml_diag_l1_kernel<<<cdiv((int64_t)h->nC * N * N, 256), 256, 0, h->stream>>>(h->nC, N, lambda, h->cl_ptr, h->Bpp, L0.diag_pos, L0.Eb);
+        ml_border_l1_kernel<<<cdiv((int64_t)h->nC * N * 6, 256), 256, 0, h->stream>>>(h->nC, N, h->rank == 0 ? 1 : 0, h->cl_ptr, h->cl_inc_ptr, h->cl_inc, h->inc_lm, h->Tinc,
+                                                                                   h->WK, h->BpK, h->EK);
+        CUDA_TRY(cudaGetLastError());
+        DBG_SYNC(h, "ml_diag_l1 / ml_border_l1");
+        h->launches += 4;
+        if (h->world > 1) {   // sum the shard contributions: block-sparse operator + border (C2: 8 MB; the dense matrix of round 1 was 288 MB)
+            int rc2 = allreduce(h, h->mlblk, (size_t)L0.nnzb * N * N + (size_t)h->n1 * 6);
+            if (rc2) return rc2;
+        }
+        for (int l = 0; l < nl; ++l) {
+            asc_handle::MlLevel& L = h->ml[l];
+            asc_handle::MlLevel& C = h->ml[l + 1];
+            ml_dinv_kernel<N><<<cdiv(L.n, 64), 64, 0, h->stream>>>(L.n, L.diag_pos, L.Eb, L.Dinv, h->flags + 4);
+            // lambda_max(D^-1 E): 16 power steps from a fixed start vector, estimate = |w_16| / |w_15|
+            const int grid = cdiv(L.n, 4);
+            ml_power_init_kernel<<<cdiv(L.n * N, 256), 256, 0, h->stream>>>(L.n * N, L.za);
+            double *v = L.za, *w = L.zb;
+            constexpr int kPowerSteps = 16;
+            for (int k = 0; k < kPowerSteps; ++k) {
+                double* part = k == kPowerSteps - 2 ? h->mlpart : (k == kPowerSteps - 1 ? h->mlpart + grid : nullptr);
+                ml_power_step_kernel<N><<<grid, 128, 0, h->stream>>>(L.n, L.row_ptr, L.col, L.Eb, L.Dinv, v, w, part);
+                std::swap(v, w);
+            }
+            ml_power_finish_kernel<<<1, 256, 0, h->stream>>>(h->mlpart, h->mlpart + grid, grid, L.lmax);
+            ml_coarsen_kernel<<<C.nnzb, N * N, 0, h->stream>>>(C.nnzb, N * N, L.cptr, L.cidx, L.Eb, C.Eb);
+            CUDA_TRY(cudaGetLastError());
+            DBG_SYNC(h, "ml level set-up");
+            h->launches += kPowerSteps + 4;
+        }
+        {   // dense top level
+            asc_handle::MlLevel& T = h->ml[nl];
+            CUDA_TRY(cudaMemsetAsync(h->Atop, 0, sizeof(double) * (size_t)h->ntop * h->ntop, h->stream));
+            ml_top_assemble_kernel<<<T.n, N * N, 0, h->stream>>>(T.n, N, T.row_ptr, T.col, T.Eb, h->Atop);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(kTopCtas); cfg.blockDim = dim3(kTopThreads); cfg.dynamicSmemBytes = sizeof(double) * (size_t)h->ntop; cfg.stream = h->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = kTopCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ml_top_invert_kernel, h->Atop, h->ntop, h->flags + 4));
+            DBG_SYNC(h, "ml top level");
+            h->launches += 2;
+        }
+        // extrinsic border: Y = V E_cK column by column, then S_k = S_KK - E_Kc Y
+        for (int c = 0; c < 6; ++c) {
+            ml_border_column_kernel<<<cdiv(h->n1, 256), 256, 0, h->stream>>>(h->n1, c, h->EK, h->mlcol);
+            int rcv = vcycle(h, h->mlcol, nullptr, h->stream);
+            if (rcv) return rcv;
+            ml_store_column_kernel<<<cdiv(h->n1, 256), 256, 0, h->stream>>>(h->n1, c, h->ml_out, h->Yb);
+            h->launches += 2;
+        }
+        ml_border_schur_kernel<<<1, 256, 0, h->stream>>>(h->n1, h->EK, h->Yb, h->SKK, h->Ski, h->flags + 5);
+        CUDA_TRY(cudaGetLastError());
+        DBG_SYNC(h, "ml border");
+        h->launches += 1;
+        return ASC_OK;
+    }
+
+    static BorderArgs border_args(const asc_handle* h, const double* srcK, const double* alpha) {
+        BorderArgs b;
+        b.t = h->ml_out; b.EK = h->EK; b.Y = h->Yb; b.Ski = h->Ski; b.srcK = srcK; b.alpha = alpha; b.zc = h->zc; b.n1 = h->n1;
+        return b;
+    }
+
+    // block-Jacobi (+ multilevel coarse level) PCG on the reduced system; solution left in vx.  Returns iterations through *iters.
     static int pcg(asc_handle* h, double lambda, int* iters) {
         const size_t PN = (size_t)h->P * N;
         const int nUpd = h->use_clusters ? h->nC : h->nCtaPose;
         h->launches += 3;
-        const double tol2_ = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
+        const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
         // A rejected LM step is re-solved with a 10x larger lambda on the same linearisation; while lambda is far below the
         // spectrum of S the solution hardly moves, so start from it (GTSAM refactorises from scratch each time).
         const bool warm = h->warm_ok && h->use_clusters && h->warm_rz_ref > 0.0;
         PeerComm single{};   // world = 0: kernels take their single-GPU path
         single.world = 1;
+        BorderArgs no_border{};
         if (warm) {
             int rcw = schur_apply_launch(h, lambda, false, h->vx, nullptr, nullptr);   // ybuf = S x0 (keyframe rows)
             if (rcw) return rcw;
@@ -709,70 +801,52 @@ struct Engine {
             pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(warm ? 2 : 1, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp, h->scal,
                                                                   h->flags, h->partA, rc_, single);
             pcg_init_k_kernel<<<1, 32, 0, h->stream>>>((int64_t)PN, h->rhs, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->status + 40,
-                                                      rc_ ? rc_ + (size_t)h->nC * N : nullptr, warm ? h->ybuf + PN : nullptr);
+                                                      rc_ ? rc_ + h->n1 : nullptr, warm ? h->ybuf + PN : nullptr);
             CUDA_TRY(cudaGetLastError());
-            if (h->use_coarse) {
-                set_scalar_kernel<<<1, 1, 0, h->stream>>>(h->scal + 9, 1.0);
-                int rc3 = coarse_apply(h, nullptr);
+            if (h->use_coarse) {   // zc = B rc: V-cycle on the cluster part, border finished inside pcg_init_end
+                int rc3 = vcycle(h, h->rc, nullptr, h->stream);
                 if (rc3) return rc3;
-                if (h->coarse_refit && h->coarse_f32_active) {   // reused inverse: alpha = (rc.zc)/(zc.E zc) against the current E
-                    const double one = 1.0, zero = 0.0;
-                    if (cublasDsymv(h->blas, CUBLAS_FILL_MODE_UPPER, h->nz, &one, h->E, h->nz, h->zc, 1, &zero, h->yc, 1) != CUBLAS_STATUS_SUCCESS)
-                        return fail(ASC_ERR_CUDA, "cublasDsymv failed");
-                    coarse_refit_kernel<<<1, kReduceThreads, 0, h->stream>>>(coarse_rhs(h), h->zc, h->yc, h->nz, h->scal + 9);
-                    CUDA_TRY(cudaGetLastError());
-                    h->launches += 2;
-                }
             }
             pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, h->status + 40, h->scal, h->flags, rc_, h->zc, h->nz, h->vz + PN, h->vp + PN, lambda,
-                                                         warm ? h->warm_rz_ref : 0.0, tol2_, h->nC, h->nA, N, h->aggS);
+                                                         warm ? h->warm_rz_ref : 0.0, tol2, h->use_coarse ? border_args(h, h->rc + h->n1, nullptr) : no_border);
         } else {
             pcg_init_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->rhs, h->Minv, h->MinvK, h->vx, h->vr, h->vz, h->vp, h->partA);
             CUDA_TRY(cudaGetLastError());
-            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr, lambda, 0.0, tol2_, 0, 0, N, 1);
+            pcg_init_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(h->partA, nUpd, nullptr, h->scal, h->flags, nullptr, nullptr, 0, nullptr, nullptr, lambda, 0.0, tol2, no_border);
         }
         CUDA_TRY(cudaGetLastError());
-        const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol;
         static const int chunk_env = getenv("ASC_PCG_CHUNK") ? atoi(getenv("ASC_PCG_CHUNK")) : 0;
         const int chunk = chunk_env > 0 ? chunk_env : 8;   // iterations per graph launch / host check of the done flag
         int launched = 0;
         const double* lam_dev = h->scal + 8;
         const bool p2p = h->world > 1 && h->p2p_ok && h->use_clusters;   // peer-memory exchange instead of ncclAllReduce
         const bool profiling = h->prof_id != 0 && 2 * h->prof_n + 1 < (int)h->prof_ev.size();   // event-bracketed launches cannot be captured
-        // "last CTA" fusion (kernels.cuh): pcg_mid inside pass C (single GPU), pcg_end inside the fp32 coarse GEMV, with the CTA
-        // partials of passes B / C pre-reduced in groups.  MEASURED SLOWER on C2 (166.6 vs 157.8 ms per step: the per-CTA
-        // __threadfence + ticket costs more than the two kernel boundaries it saves), so it is off unless ASC_FUSE=1.
-        static const bool fuse = getenv("ASC_FUSE") != nullptr;
-        const bool fuse_mid = fuse && !profiling && h->world == 1;
-        const bool fuse_end = fuse && !profiling && h->use_clusters && h->use_coarse && h->coarse_f32_active;
-        // coarse GEMV off the critical path (single GPU, fp32 inverse, one cluster per aggregate): see EndArgs in kernels.cuh
-        static const bool no_side_gemv = getenv("ASC_NO_SIDE_GEMV") != nullptr;
-        const bool side_gemv = !no_side_gemv && h->world == 1 && h->use_clusters && h->use_coarse && h->coarse_f32_active && h->aggS == 1 && !fuse_end;
-        const int nGrpC = cdiv(h->nCtaPose, kRowGroup), nGrpB = cdiv(h->nBlkB, kRowGroup);
-        CUDA_TRY(cudaMemsetAsync(h->tickC, 0, sizeof(unsigned) * (nGrpC + 2), h->stream));
-        CUDA_TRY(cudaMemsetAsync(h->tickB, 0, sizeof(unsigned) * (nGrpB + 2), h->stream));
-        CUDA_TRY(cudaMemsetAsync(h->tickG, 0, sizeof(unsigned) * 4, h->stream));
-        if (side_gemv) CUDA_TRY(cudaMemsetAsync(h->ryc + (size_t)h->nC * N, 0, sizeof(double) * 6, h->stream));   // K entries of Z^T y are added in pcg_end
+        // Coarse V-cycle off the critical path (single GPU): t = V (Z^T y) runs on a side branch of the graph beside pcg_mid and the
+        // cluster update, and pcg_end advances the coarse correction by linearity: zc <- zc - alpha B [Z^T y; y_K].
+        static const bool no_side_v = getenv("ASC_NO_SIDE_VCYCLE") != nullptr;
+        const bool side_v = !no_side_v && h->world == 1 && h->use_clusters && h->use_coarse;
         auto one_iteration = [&]() -> int {
             double* rowC = h->ybuf + PN + 8;
             double* rowB = rowC + kPartCols;
             MidArgs mid{};
             mid.P = h->P; mid.N = N; mid.lambda_val = lambda; mid.lambda_dev = lam_dev;
-            mid.partC = fuse ? h->grpC : h->partC; mid.nC = fuse ? nGrpC : h->nCtaPose; mid.partB = fuse ? h->grpB : h->partB; mid.nB = fuse ? nGrpB : h->nBlkB;
+            mid.partC = h->partC; mid.nC = h->nCtaPose; mid.partB = h->partB; mid.nB = h->nBlkB;
             mid.BKK = h->BKK; mid.MinvK = h->MinvK; mid.p = h->vp; mid.x = h->vx; mid.r = h->vr; mid.z = h->vz;
             mid.yK_out = h->ybuf + PN; mid.scal = h->scal; mid.done = h->flags;
-            mid.rcK = h->use_coarse ? h->rc + (size_t)h->nC * N : nullptr;
-            int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev, p2p, fuse, fuse_mid ? &mid : nullptr);
+            mid.rcK = h->use_coarse ? h->rc + h->n1 : nullptr;
+            int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev, p2p);
             if (rc) return rc;
-            if (side_gemv) {   // fork: qc = Einv Z^T y on the side stream, beside pcg_mid + the cluster update
+            if (side_v) {   // fork: t = V (Z^T y) on the side stream
                 CUDA_TRY(cudaEventRecord(h->ev_c, h->stream));
                 CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_c, 0));
                 coarse_restrict_y_kernel<<<cdiv(h->nC, 4), 128, 0, h->stream2>>>(h->nC, N, h->cl_ptr, h->ybuf, h->ryc, h->flags);
-                EndArgs none{};
-                coarse_gemv_f32_kernel<<<cdiv(h->nz, 4), 128, 0, h->stream2>>>(h->Einvf, h->ryc, h->qc, h->nz, h->flags, h->scal + 9, none, nullptr);
                 CUDA_TRY(cudaGetLastError());
+                h->launches += 1;
+                prof_start(h, 8);
+                rc = vcycle(h, h->ryc, h->flags, h->stream2);
+                prof_stop(h, 8);
+                if (rc) return rc;
                 CUDA_TRY(cudaEventRecord(h->ev_q, h->stream2));
-                h->launches += 2;
             }
             if (p2p) {
                 pcg_signal_kernel<<<1, 1024, 0, h->stream>>>(h->pcm, mid.partC, mid.nC, mid.partB, mid.nB, h->flags);
@@ -787,34 +861,33 @@ struct Engine {
                 if (rc) return rc;
                 mid.partC = rowC; mid.partB = rowB; mid.nC = 1; mid.nB = 1;
             }
-            if (!fuse_mid) {
-                pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(mid, p2p ? h->pcm : single, rowC);
-                CUDA_TRY(cudaGetLastError());
-                h->launches += 1;
-            }
+            pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(mid, p2p ? h->pcm : single, rowC);
+            CUDA_TRY(cudaGetLastError());
+            h->launches += 1;
             EndArgs end{};
             end.P = h->P; end.N = N; end.part = h->partA; end.nPart = nUpd; end.tol2 = tol2; end.max_iters = h->prm.pcg_max_iters;
             end.p = h->vp; end.z = h->vz; end.scal = h->scal; end.done = h->flags; end.rc = h->use_coarse ? h->rc : nullptr; end.zc = h->zc;
-            end.nz = h->nz; end.nC = h->nC; end.nA = h->nA; end.S = h->aggS;
+            end.nz = h->nz;
             if (h->use_clusters) {
                 prof_start(h, 9);
                 pcg_cluster_update_kernel<<<h->nC, 128, 0, h->stream>>>(0, N, h->cl_ptr, h->cl_off, h->Mc, h->rhs, h->ybuf, h->vx, h->vr, h->vz, h->vp,
                                                                       h->scal, h->flags, h->partA, h->use_coarse ? h->rc : nullptr, p2p ? h->pcm : single);
                 prof_stop(h, 9);
-                if (side_gemv) {   // join; pcg_end advances zc by linearity
+                if (side_v) {   // join; pcg_end advances zc by linearity
                     CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_q, 0));
-                    end.zc_rw = h->zc; end.qc = h->qc; end.EinvK = h->Einvf + (size_t)h->nC * N; end.yK = h->ybuf + PN; end.gemv_scale = h->scal + 9;
-                } else if (h->use_coarse) { int rc3 = coarse_apply(h, h->flags, fuse_end ? &end : nullptr); if (rc3) return rc3; }
+                    end.border = border_args(h, h->ybuf + PN, h->scal);
+                } else if (h->use_coarse) {   // zc = B rc recomputed from the new residual
+                    int rc3 = vcycle(h, h->rc, h->flags, h->stream);
+                    if (rc3) return rc3;
+                    end.border = border_args(h, h->rc + h->n1, nullptr);
+                }
             } else {
                 pcg_update_kernel<N><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->vp, h->ybuf, h->Minv, h->vx, h->vr, h->vz, h->scal, h->flags, h->partA);
             }
             CUDA_TRY(cudaGetLastError());
-            h->launches += 1;
-            if (!fuse_end) {
-                pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(end);
-                CUDA_TRY(cudaGetLastError());
-                h->launches += 1;
-            }
+            pcg_end_kernel<<<1, kReduceThreads, 0, h->stream>>>(end);
+            CUDA_TRY(cudaGetLastError());
+            h->launches += 2;
             return ASC_OK;
         };
         // one chunk = `chunk` iterations; kernels return immediately once the device-side done flag is set
@@ -822,8 +895,8 @@ struct Engine {
         // multi-GPU: with the peer-memory exchange the loop holds kernels only and is captured like the single-GPU one (a captured
         // ncclAllReduce hung on this stack: NCCL 2.28.9, driver 580); ASC_NO_GRAPH_MGPU=1 falls back to plain launches
         static const bool no_graph_mgpu = getenv("ASC_NO_GRAPH_MGPU") != nullptr;
-        const bool can_graph = !no_graph && (h->world == 1 || (p2p && !no_graph_mgpu)) && !profiling && (!h->use_coarse || h->coarse_f32_active);
-        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (h->coarse_f32_active ? 4 : 0) | (p2p ? 8 : 0) | (fuse_mid ? 16 : 0) | (fuse_end ? 32 : 0) | (side_gemv ? 64 : 0);
+        const bool can_graph = !no_graph && (h->world == 1 || (p2p && !no_graph_mgpu)) && !profiling;
+        const int graph_key = (h->use_clusters ? 1 : 0) | (h->use_coarse ? 2 : 0) | (p2p ? 8 : 0) | (side_v ? 64 : 0);
         for (;;) {
             if (can_graph) {
                 if (!h->pcg_graph || h->pcg_graph_key != graph_key) {
@@ -854,7 +927,6 @@ struct Engine {
             if (h->h_flags[0] || launched >= h->prm.pcg_max_iters + chunk) break;
         }
         if (iters) *iters = (int)h->h_status[32 + 5];
-        if (p2p && h->h_flags[8] != 0) return fail(ASC_ERR_COMM, "peer-memory exchange timed out waiting for a peer rank");
         if (!warm) h->warm_rz_ref = h->h_status[32 + 3];
         return ASC_OK;
     }
@@ -866,8 +938,44 @@ struct Engine {
                                                                                 nullptr, h->p_inv, h->chain, h->lml);
         CUDA_TRY(cudaGetLastError());
         schur_pass_b_kernel<true><<<h->nBlkB, kPassBThreads, 0, h->stream>>>(h->L, h->lm_ptr, h->v4, h->WK, h->Cinv, h->vx + (size_t)h->P * N, nullptr,
-                                                                   h->cg4, h->dl4, nullptr, nullptr, nullptr);
+                                                                   h->cg4, h->dl4, nullptr);
         CUDA_TRY(cudaGetLastError());
+        return ASC_OK;
+    }
+
+    // Multi-GPU: the failure flags that steer the host (non-PD landmark block of ONE shard, a peer-exchange timeout seen by ONE
+    // rank) are rank-local; every rank must take the same branch or the next collective deadlocks.  One small all-reduce makes
+    // the decision global: afterwards h_flags[1..5, 8] are "somebody failed" indicators on every rank (own index kept if it has one).
+    static int agree_on_failures(asc_handle* h) {
+        if (h->world <= 1) return ASC_OK;
+        const int big = 0x7fffffff;
+        double* d = h->status + 48;
+        double v[8] = {h->h_flags[1] != big ? 1.0 : 0.0, h->h_flags[2] != big ? 1.0 : 0.0, h->h_flags[3] != big ? 1.0 : 0.0,
+                       h->h_flags[4] != 0 ? 1.0 : 0.0, h->h_flags[5] != 0 ? 1.0 : 0.0, h->h_flags[8] != 0 ? 1.0 : 0.0, 0.0, 0.0};
+        CUDA_TRY(cudaMemcpyAsync(d, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
+        int rc = allreduce(h, d, 8);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(v, d, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (v[0] > 0 && h->h_flags[1] == big) h->h_flags[1] = -1;   // failed on another rank: index unknown here
+        if (v[1] > 0 && h->h_flags[2] == big) h->h_flags[2] = -1;
+        if (v[2] > 0 && h->h_flags[3] == big) h->h_flags[3] = -1;
+        if (v[3] > 0) h->h_flags[4] = 1;
+        if (v[4] > 0) h->h_flags[5] = 1;
+        if (v[5] > 0) h->h_flags[8] = 1;
+        return ASC_OK;
+    }
+
+    static int check_solve_flags(asc_handle* h) {
+        const int big = 0x7fffffff;
+        if (h->h_flags[8] != 0) return fail(ASC_ERR_COMM, "peer-memory exchange timed out waiting for a peer rank");
+        if (h->h_flags[1] != big) { h->fail_kind = 'l'; h->fail_index = h->h_flags[1]; return fail(ASC_ERR_INDETERMINATE, "landmark block %d is not positive definite", h->h_flags[1]); }
+        if (h->h_flags[2] != big) { h->fail_kind = 'q'; h->fail_index = h->h_flags[2]; return fail(ASC_ERR_INDETERMINATE, "pose block %d is not positive definite", h->h_flags[2]); }
+        if (h->h_flags[3] != big) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "extrinsic block is not positive definite"); }
+        if (h->use_coarse && (h->h_flags[4] != 0 || h->h_flags[5] != 0)) { h->fail_kind = 'q'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "coarse-level blocks are not positive definite (levels %d, border %d)", h->h_flags[4], h->h_flags[5]); }
+        const double bd = h->h_status[32 + 6];
+        if (bd == 3.0) return fail(ASC_ERR_NOT_CONVERGED, "PCG stopped at pcg_max_iters = %d above pcg_rel_tol", h->prm.pcg_max_iters);
+        if (bd != 0.0) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, bd == 1.0 ? "PCG breakdown: p^T S p <= 0" : "PCG breakdown: r^T M^-1 r is negative or not finite"); }
         return ASC_OK;
     }
 
@@ -875,17 +983,26 @@ struct Engine {
     static int solve(asc_handle* h, double lambda, int* iters) {
         int rc = prepare(h, lambda);
         if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_stage[3], h->stream));
         int its_local = 0;
         rc = pcg(h, lambda, &its_local);
         if (iters) *iters = its_local;
         if (rc) return rc;
-        if (h->use_coarse) { if (h->coarse_fresh) h->coarse_ref_iters = its_local; h->coarse_last_iters = its_local; }
-        const int big = 0x7fffffff;
-        if (h->h_flags[1] != big) { h->fail_kind = 'l'; h->fail_index = h->h_flags[1]; return fail(ASC_ERR_INDETERMINATE, "landmark block %d is not positive definite", h->h_flags[1]); }
-        if (h->h_flags[2] != big) { h->fail_kind = 'q'; h->fail_index = h->h_flags[2]; return fail(ASC_ERR_INDETERMINATE, "pose block %d is not positive definite", h->h_flags[2]); }
-        if (h->h_flags[3] != big) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "extrinsic block is not positive definite"); }
-        if (h->use_coarse && (h->h_flags[4] != 0 || h->h_flags[5] != 0)) { h->fail_kind = 'q'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "coarse-level factorisation failed (info %d/%d)", h->h_flags[4], h->h_flags[5]); }
-        if (h->h_status[32 + 6] != 0.0) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "PCG breakdown: p^T S p <= 0"); }
+        CUDA_TRY(cudaEventRecord(h->ev_stage[4], h->stream));
+        {   // stage times of this solve (the PCG loop has synchronised the stream already)
+            CUDA_TRY(cudaEventSynchronize(h->ev_stage[4]));
+            float a = 0, b = 0, c = 0, d = 0;
+            CUDA_TRY(cudaEventElapsedTime(&a, h->ev_stage[0], h->ev_stage[1]));
+            CUDA_TRY(cudaEventElapsedTime(&b, h->ev_stage[1], h->ev_stage[2]));
+            CUDA_TRY(cudaEventElapsedTime(&c, h->ev_stage[2], h->ev_stage[3]));
+            CUDA_TRY(cudaEventElapsedTime(&d, h->ev_stage[3], h->ev_stage[4]));
+            h->ms_prepare += a + c; h->ms_coarse += b; h->ms_pcg += d;
+        }
+        h->coarse_last_iters = its_local;
+        rc = agree_on_failures(h);
+        if (rc) return rc;
+        rc = check_solve_flags(h);
+        if (rc) return rc;
         h->warm_ok = true;
         return backsub(h);
     }
@@ -893,7 +1010,6 @@ struct Engine {
     // (S^-1)_KK of the undamped reduced system: six PCG solves with unit right-hand sides on the K0 rows
     static int marginal(asc_handle* h, double* cov36, int* iters_total) {
         const size_t PN = (size_t)h->P * N;
-        h->coarse_valid = false;
         int rc = prepare(h, 0.0);
         if (rc) return rc;
         int total = 0;
@@ -906,11 +1022,14 @@ struct Engine {
             rc = pcg(h, 0.0, &its);
             total += its;
             if (rc) return rc;
-            const int big = 0x7fffffff;
-            if (h->h_flags[1] != big || h->h_flags[2] != big || h->h_flags[3] != big || h->h_status[32 + 6] != 0.0) {
+            rc = agree_on_failures(h);
+            if (rc) return rc;
+            rc = check_solve_flags(h);
+            if (rc == ASC_ERR_INDETERMINATE) {
                 h->fail_kind = 'K'; h->fail_index = 0;
                 return fail(ASC_ERR_INDETERMINATE, "the undamped reduced system is not positive definite");
             }
+            if (rc) return rc;
             double col[6];
             CUDA_TRY(cudaMemcpyAsync(col, h->vx + PN, sizeof col, cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -983,7 +1102,7 @@ int dispatch_schur_c(asc_handle* h, double lambda, double* x, double* u4_in) {
     case n:                                                                                                                       \
         schur_pass_c_kernel<n><<<h->nCtaPose, kCtaThreads, 0, h->stream>>>(h->P, h->M, lambda, 0, h->pose_ptr, h->p_lm, h->J, u4_in, x, \
                                                                          h->Bpp, h->BpK, nullptr, h->ybuf, h->partC, nullptr, h->chain, h->lml, nullptr, nullptr, 0, \
-                                                                         nullptr, nullptr, 0, MidArgs{}, DriftTab{{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}}); \
+                                                                         DriftTab{{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}}); \
         break;
     switch (h->N) { ASC_DOF_LIST(X) default: return fail(ASC_ERR_INVALID, "no kernels compiled for %d DOF", h->N); }
 #undef X
@@ -1089,6 +1208,7 @@ bool converged(const asc_params& p, double e0, double e1) {
 int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
     const asc_params& p = h->prm;
     float ms = 0;
+    h->ms_prepare = h->ms_coarse = h->ms_pcg = 0.0;
     int rc = dispatch_linearize(h, false, nullptr, nullptr);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
@@ -1097,7 +1217,8 @@ int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
         rc = dispatch_solve(h, *lambda, &its);
         lg->inner_steps++;
         lg->pcg_iterations += its;
-        if (rc != ASC_OK && rc != ASC_ERR_INDETERMINATE) return rc;
+        // an indeterminate system or a PCG that ran out of iterations both count as "not solved": lambda goes up (Appendix C.2)
+        if (rc != ASC_OK && rc != ASC_ERR_INDETERMINATE && rc != ASC_ERR_NOT_CONVERGED) return rc;
         const bool solved = rc == ASC_OK;
         bool ok = false, stop = false;
         double new_error = 0.0;
@@ -1119,13 +1240,6 @@ int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
         }
         if (ok) {
             accept_try(h);
-            // a step that changed the error a lot changed the robust weights (hence S) a lot: rebuild the coarse operator
-            // (C2: a stale operator costs ~1000 extra PCG iterations after a 30 % drop, ~15 after a 20 % drop; a rebuild costs ~110)
-            // and the first steps from an initial estimate re-weight almost every factor even when the error barely moves
-            // (a reused inverse is additionally re-fitted by a scalar, which narrows but does not close that gap)
-            static const int force_iters = getenv("ASC_COARSE_FORCE_ITERS") ? atoi(getenv("ASC_COARSE_FORCE_ITERS")) : 2;
-            static const double drop_frac = getenv("ASC_COARSE_DROP") ? atof(getenv("ASC_COARSE_DROP")) : 0.25;
-            if ((*error - new_error) > drop_frac * *error || h->outer_iteration < force_iters) h->coarse_valid = false;
             *error = new_error;
             *lambda = std::max(*lambda / p.lambda_factor, p.lambda_lower_bound);
             lg->accepted = 1;
@@ -1141,6 +1255,7 @@ int lm_iterate(asc_handle* h, double* error, double* lambda, asc_iter_log* lg) {
     lg->linearize_ms = ms;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[3], h->ev[2]));
     lg->solve_ms = ms;
+    lg->prepare_ms = h->ms_prepare; lg->coarse_ms = h->ms_coarse; lg->pcg_ms = h->ms_pcg;
     return ASC_OK;
 }
 
@@ -1178,6 +1293,7 @@ int dogleg_gHg(asc_handle* h, double* out) {
 // [DEP] DoglegOptimizer::iterate + DoglegOptimizerImpl::Iterate(ONE_STEP_PER_ITERATION)
 int dogleg_iterate(asc_handle* h, double* error, double* Delta, asc_iter_log* lg) {
     float ms = 0;
+    h->ms_prepare = h->ms_coarse = h->ms_pcg = 0.0;
     int rc = dispatch_linearize(h, false, nullptr, nullptr);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
@@ -1197,7 +1313,7 @@ int dogleg_iterate(asc_handle* h, double* error, double* Delta, asc_iter_log* lg
     const double uu = step * step * gg, un = step * ng;
     const double f0 = *error;
     double f_new = f0, cu = 0.0, cn = 1.0;
-    bool stay = true;
+    bool stay = true, moved = true;
     while (stay) {
         lg->inner_steps++;
         const double D2 = *Delta * *Delta;
@@ -1223,17 +1339,22 @@ int dogleg_iterate(asc_handle* h, double* error, double* Delta, asc_iter_log* lg
             *Delta = std::max(*Delta, 3.0 * dn); stay = false;
         } else if (rho >= 0.25) stay = false;
         else if (rho >= 0.0) { if (*Delta > 1e-5) *Delta *= 0.5; stay = false; }
-        else { if (*Delta > 1e-5) { *Delta *= 0.5; stay = true; } else stay = false; }
+        else {
+            // f increased (or the trial error is not finite: every comparison above is false for a NaN rho).  Retry with a smaller
+            // region; at the minimum region DoglegOptimizerImpl::Iterate zeroes dx_d and keeps f_error: the error never increases.
+            if (*Delta > 1e-5) { *Delta *= 0.5; stay = true; }
+            else { stay = false; moved = false; }
+        }
     }
-    accept_try(h);
-    *error = f_new;
-    lg->accepted = 1;
+    if (moved) { accept_try(h); *error = f_new; lg->accepted = 1; }
+    else { *error = f0; lg->accepted = 0; }
     CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
     CUDA_TRY(cudaEventSynchronize(h->ev[2]));
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]));
     lg->linearize_ms = ms;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[3], h->ev[2]));
     lg->solve_ms = ms;
+    lg->prepare_ms = h->ms_prepare; lg->coarse_ms = h->ms_coarse; lg->pcg_ms = h->ms_pcg;
     return ASC_OK;
 }
 
@@ -1333,9 +1454,10 @@ void asc_default_params(asc_params* p) {
     p->device = -1;
     p->pcg_cluster_max = 10;
     p->pcg_cluster_covis = 0.25;
-    p->pcg_coarse_max_dim = 16384;
-    p->pcg_coarse_fp32 = 1;
-    p->pcg_coarse_agg = 1;
+    p->pcg_coarse_levels = 8;
+    p->pcg_ml_degree = 4;
+    p->pcg_ml_agg = 8;
+    p->pcg_ml_top_dim = 640;
 }
 
 const char* asc_last_error(void) { return g_last_error.c_str(); }
@@ -1363,6 +1485,7 @@ int asc_create(const asc_params* params, asc_handle** out) {
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_c, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming));
     for (auto& ev : h->ev) CUDA_TRY(cudaEventCreate(&ev));
+    for (auto& ev : h->ev_stage) CUDA_TRY(cudaEventCreate(&ev));
     CUDA_TRY(cudaMallocHost((void**)&h->h_status, 64 * sizeof(double)));
     CUDA_TRY(cudaMallocHost((void**)&h->h_flags, 16 * sizeof(int)));
     h->t_base.resize(12);
@@ -1391,14 +1514,11 @@ int asc_destroy(asc_handle* h) {
     }
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
-    if (h->solver) cusolverDnDestroy(h->solver);
-    if (h->blas) cublasDestroy(h->blas);
     free_device(h);
     if (h->arena) cudaFree(h->arena);
     for (int k = 0; k < 2; ++k) if (h->d_has_link[k]) { cudaFree(h->d_has_link[k]); cudaFree(h->d_link_meas[k]); cudaFree(h->d_link_w[k]); }
-    if (h->work) cudaFree(h->work);
-    if (h->workf) cudaFree(h->workf);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->ev_stage) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_ev) cudaEventDestroy(ev);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -1459,7 +1579,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     h->P = P; h->L = L; h->M = M;
     h->values_set = false; h->linearized = false; h->lin_lambda = -1.0;
     h->link_set[0] = h->link_set[1] = false;   // link factors belong to the packed graph: set them again after asc_set_problem
-    h->coarse_valid = false; h->coarse_ref_iters = 0; h->coarse_last_iters = 0;
+    h->coarse_last_iters = 0;
     if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }
     // constants
     const asc_params& pr = h->prm;
@@ -1529,7 +1649,8 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     h->use_clusters = gmax > 1;
     struct PairRec { long long key; int a, b; };
     std::vector<PairRec> pairs;
-    std::vector<int> inc_lo, inc_hi, inc_lm, inc_cl, dest_ptr, dest_ca, dest_cb, pair_a, pair_b, cl_inc_ptr, cl_inc;
+    std::vector<int> inc_lo, inc_hi, inc_lm, inc_cl, dest_ptr, pos_lo, pos_up, pair_a, pair_b, cl_inc_ptr, cl_inc;
+    std::vector<MlHostLevel> hl;   // multilevel hierarchy of the coarse operator (host patterns)
     std::vector<int> cl_ptr, pose_cluster(P, 0);
     std::vector<long long> cl_off;
     if (h->use_clusters) {
@@ -1576,19 +1697,19 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         if (no_pin) { run_lo.resize(M); run_hi.resize(M); }
         else { resize_pinned(run_lo, M, reg_i[6]); resize_pinned(run_hi, M, reg_i[7]); }
         h->dup_obs = false;
-        h->aggS = std::max(1, pr.pcg_coarse_agg);
-        h->nA = cdiv(h->nC, h->aggS);
-        h->nz = h->nA * N + 6;
-        h->use_coarse = pr.pcg_coarse_max_dim > 0 && h->nz <= pr.pcg_coarse_max_dim && h->nC > 1;
+        h->n1 = h->nC * N;
+        h->nz = h->n1 + 6;
+        h->use_coarse = pr.pcg_coarse_levels > 0 && h->nC > 1;
         {   // incidences = (landmark, cluster) runs of the landmark-major list; built per thread over landmark ranges, then concatenated
             const int T = std::max(1, std::min(omp_get_max_threads(), 16));
             struct Local { std::vector<int> lo, hi, lm, cl; std::vector<PairRec> pairs; bool dup = false; };
             std::vector<Local> loc(T);
 #pragma omp parallel num_threads(T)
             {
-                const int t = omp_get_thread_num();
+                // slices follow the team size actually delivered (it may be smaller than T); unused Local entries stay empty
+                const int t = omp_get_thread_num(), Tn = omp_get_num_threads();
                 Local& Lc = loc[t];
-                const int j0 = (int)((int64_t)L * t / T), j1 = (int)((int64_t)L * (t + 1) / T);
+                const int j0 = (int)((int64_t)L * t / Tn), j1 = (int)((int64_t)L * (t + 1) / Tn);
                 for (int j = j0; j < j1; ++j) {
                     int a = lm_ptr[j];
                     const size_t first_inc = Lc.lo.size();
@@ -1604,8 +1725,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                     if (h->use_coarse)   // block updates of E = Z^T S Z: lower triangle of cluster pairs, in landmark order (local incidence ids)
                         for (size_t ia = first_inc; ia < Lc.lo.size(); ++ia)
                             for (size_t ib = first_inc; ib < Lc.lo.size(); ++ib)
-                                if (Lc.cl[ia] / h->aggS >= Lc.cl[ib] / h->aggS)
-                                    Lc.pairs.push_back({(long long)(Lc.cl[ia] / h->aggS) * h->nA + Lc.cl[ib] / h->aggS, (int)ia, (int)ib});
+                                if (Lc.cl[ia] >= Lc.cl[ib]) Lc.pairs.push_back({(long long)Lc.cl[ia] * h->nC + Lc.cl[ib], (int)ia, (int)ib});
                 }
             }
             size_t ninc = 0, npair = 0;
@@ -1625,9 +1745,11 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             }
         }
         lap("runs + incidences + pairs");
+        std::vector<long long> dest_key;   // unique (ca, cb) keys of the lower triangle, ascending; after the union: of ALL ranks
+        std::vector<double> dest_w;        // shared-landmark pair count per key (summed over ranks)
         if (h->use_coarse) {
             {   // stable LSD radix sort of the pairs by (cluster a, cluster b): two parallel counting passes
-                const int nCl = h->nA;
+                const int nCl = h->nC;
                 std::vector<PairRec> tmp(pairs.size());
                 std::vector<int> bptr, dst(pairs.size());
                 for (int pass = 0; pass < 2; ++pass) {
@@ -1638,15 +1760,46 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 }
             }
             pair_a.resize(pairs.size()); pair_b.resize(pairs.size());
+            std::vector<int> loc_ptr;   // pair range of each LOCAL key
             for (size_t i = 0; i < pairs.size(); ++i) {
-                if (i == 0 || pairs[i].key != pairs[i - 1].key) {
-                    dest_ptr.push_back((int)i);
-                    dest_ca.push_back((int)(pairs[i].key / h->nA)); dest_cb.push_back((int)(pairs[i].key % h->nA));
-                }
+                if (i == 0 || pairs[i].key != pairs[i - 1].key) { loc_ptr.push_back((int)i); dest_key.push_back(pairs[i].key); }
                 pair_a[i] = pairs[i].a; pair_b[i] = pairs[i].b;
             }
-            dest_ptr.push_back((int)pairs.size());
-            h->nDest = (int)dest_ca.size();
+            loc_ptr.push_back((int)pairs.size());
+            std::vector<long long> loc_key = dest_key;
+            dest_w.resize(dest_key.size());
+            for (size_t d = 0; d < dest_key.size(); ++d) dest_w[d] = loc_ptr[d + 1] - loc_ptr[d];
+            // every cluster owns a diagonal block even without observations on this rank (rank 0 adds B_pp + lambda I to it)
+            {
+                std::vector<long long> k2; std::vector<double> w2;
+                k2.reserve(dest_key.size() + h->nC); w2.reserve(dest_key.size() + h->nC);
+                size_t q = 0;
+                for (int c = 0; c < h->nC; ++c) {
+                    const long long dk = (long long)c * h->nC + c;
+                    while (q < dest_key.size() && dest_key[q] < dk) { k2.push_back(dest_key[q]); w2.push_back(dest_w[q]); ++q; }
+                    if (q < dest_key.size() && dest_key[q] == dk) { k2.push_back(dk); w2.push_back(dest_w[q]); ++q; }
+                    else { k2.push_back(dk); w2.push_back(0.0); }
+                }
+                while (q < dest_key.size()) { k2.push_back(dest_key[q]); w2.push_back(dest_w[q]); ++q; }
+                dest_key.swap(k2); dest_w.swap(w2);
+            }
+            if (h->world > 1) {   // union of the block patterns of all shards (every rank must hold the same hierarchy)
+                int rcu = union_block_keys(h, dest_key, dest_w);
+                if (rcu) return rcu;
+            }
+            // pair ranges against the (global) key list: empty for blocks this rank has no landmark in (the local keys are a
+            // subsequence of the global ones, and the pairs are sorted by key)
+            dest_ptr.assign(dest_key.size() + 1, 0);
+            {
+                size_t q = 0;
+                int pos = 0;
+                for (size_t d = 0; d < dest_key.size(); ++d) {
+                    dest_ptr[d] = pos;
+                    if (q < loc_key.size() && loc_key[q] == dest_key[d]) { pos = loc_ptr[q + 1]; ++q; }
+                }
+                dest_ptr[dest_key.size()] = pos;
+            }
+            h->nDest = (int)dest_key.size();
         }
         h->nInc = (int)inc_lo.size();
         cl_inc_ptr.assign(h->nC + 1, 0);
@@ -1657,17 +1810,51 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             std::vector<int> f(cl_inc_ptr.begin(), cl_inc_ptr.end() - 1);
             for (size_t i = 0; i < inc_cl.size(); ++i) cl_inc[f[inc_cl[i]]++] = (int)i;
         }
-    } else { h->nC = 0; h->nmax = 0; h->scTotal = 0; h->use_coarse = false; h->nA = 0; h->aggS = 1; }
-    std::vector<int> agg_pose_ptr, agg_inc_ptr, pose_agg;
-    if (h->use_coarse) {
-        agg_pose_ptr.resize(h->nA + 1); agg_inc_ptr.resize(h->nA + 1); pose_agg.resize(P);
-        for (int a = 0; a <= h->nA; ++a) {
-            const int c = std::min(a * h->aggS, h->nC);
-            agg_pose_ptr[a] = cl_ptr[c]; agg_inc_ptr[a] = cl_inc_ptr[c];
+        if (h->use_coarse) {   // ---- multilevel hierarchy (coarse_ml.cuh)
+            const int gs = std::max(2, pr.pcg_ml_agg), top_dim = std::max(6 * N, pr.pcg_ml_top_dim), max_levels = std::max(1, pr.pcg_coarse_levels);
+            hl.clear();
+            hl.emplace_back();
+            MlHostLevel& L0 = hl[0];
+            L0.n = h->nC;
+            {   // BSR of level 1 from the lower-triangle keys
+                std::vector<int> cntr(h->nC + 1, 0);
+                for (long long k : dest_key) { const int a = (int)(k / h->nC), b = (int)(k % h->nC); cntr[a + 1]++; if (a != b) cntr[b + 1]++; }
+                for (int c = 0; c < h->nC; ++c) cntr[c + 1] += cntr[c];
+                L0.row_ptr = cntr;
+                L0.col.assign(cntr[h->nC], 0); L0.w.assign(cntr[h->nC], 0.0); L0.diag_pos.assign(h->nC, -1);
+                pos_lo.assign(dest_key.size(), 0); pos_up.assign(dest_key.size(), 0);
+                // keys ascend by (a, b) with b <= a.  Row r holds first its lower part (b < r, from the keys (r, b), already in
+                // ascending b), then the diagonal, then its upper part (columns a > r from the keys (a, r), ascending a).
+                std::vector<int> nlow(h->nC, 0), fill_lo(h->nC, 0), fill_up(h->nC, 0);
+                for (long long k : dest_key) { const int a = (int)(k / h->nC), b = (int)(k % h->nC); if (a != b) nlow[a]++; }
+                for (size_t d = 0; d < dest_key.size(); ++d) {
+                    const int a = (int)(dest_key[d] / h->nC), b = (int)(dest_key[d] % h->nC);
+                    if (a == b) { const int pos = cntr[a] + nlow[a]; L0.col[pos] = a; L0.w[pos] = dest_w[d]; L0.diag_pos[a] = pos; pos_lo[d] = pos; pos_up[d] = pos; }
+                    else {
+                        const int plo = cntr[a] + fill_lo[a]++;
+                        const int pup = cntr[b] + nlow[b] + 1 + fill_up[b]++;
+                        L0.col[plo] = b; L0.w[plo] = dest_w[d]; L0.col[pup] = a; L0.w[pup] = dest_w[d];
+                        pos_lo[d] = plo; pos_up[d] = pup;
+                    }
+                }
+            }
+            while ((int)hl.size() <= max_levels && hl.back().n * N > top_dim) {
+                MlHostLevel& L = hl.back();
+                int na = 0;
+                ml_aggregate(L, gs, L.agg, na);
+                if (na >= L.n) break;   // no coarsening possible (no couplings): stop here
+                L.n_next = na;
+                hl.emplace_back();
+                ml_coarsen_pattern(hl[hl.size() - 2], hl.back());
+            }
+            h->ntop = hl.back().n * N;
+            if (h->ntop > 4096) {   // the graph did not coarsen (e.g. no couplings between clusters): cluster-Jacobi alone
+                h->use_coarse = false;
+                hl.clear();
+            }
         }
-        for (int p = 0; p < P; ++p) pose_agg[p] = pose_cluster[p] / h->aggS;
-    }
-    lap("pair sort + coarse CSR");
+    } else { h->nC = 0; h->nmax = 0; h->scTotal = 0; h->use_coarse = false; h->n1 = 0; h->nz = 0; }
+    lap("pair sort + coarse hierarchy");
 
     const size_t PN = (size_t)P * N, Mz = (size_t)M;
     h->nCtaPose = cdiv(P, kWarpsPerCta);
@@ -1695,30 +1882,54 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         ALLOC(Wm, Mz * 3 * N); ALLOC(Mc, h->scTotal);
         ALLOC(inc_lo, h->nInc); ALLOC(inc_hi, h->nInc); ALLOC(inc_lm, h->nInc); ALLOC(cl_inc_ptr, h->nC + 1); ALLOC(cl_inc, h->nInc);
     }
+    h->ml.clear();
+    h->ml_out = nullptr;
     if (h->use_coarse) {
-        const size_t ni = h->nInc, nd = h->nDest, np = pair_a.size(), nz = h->nz;
-        ALLOC(dest_ptr, nd + 1); ALLOC(dest_ca, nd); ALLOC(dest_cb, nd);
+        const size_t ni = h->nInc, nd = h->nDest, np = pair_a.size(), nz = h->nz, NN = (size_t)N * N;
+        ALLOC(dest_ptr, nd + 1); ALLOC(pos_lo, nd); ALLOC(pos_up, nd);
         ALLOC(pair_a, np); ALLOC(pair_b, np);
-        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(E, nz * nz); ALLOC(rc, (size_t)h->nC * N + 6); ALLOC(zc, nz); ALLOC(yc, nz); ALLOC(rca, nz); ALLOC(ryc, nz); ALLOC(qc, nz);
-        ALLOC(agg_pose_ptr, h->nA + 1); ALLOC(agg_inc_ptr, h->nA + 1); ALLOC(pose_agg, P);
-        if (pr.pcg_coarse_fp32) {
-            ALLOC(Ef, nz * nz); ALLOC(Einvf, nz * (nz + 4 * (size_t)std::max(h->world, 1)));
-            if (h->world == 1) { ALLOC(Xf, nz * nz); ALLOC(Tf, (nz / 2 + 64) * (nz / 2 + 64)); } else { h->Xf = nullptr; h->Tf = nullptr; }
-        } else { h->Ef = nullptr; h->Einvf = nullptr; h->Xf = nullptr; h->Tf = nullptr; }
-        if (!h->solver) {
-            if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cusolverDnCreate failed");
-            if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(ASC_ERR_CUDA, "cublasCreate failed");
-            cusolverDnSetStream(h->solver, h->stream);
-            cublasSetStream(h->blas, h->stream);
+        ALLOC(Vinc, ni * 3 * N); ALLOC(Tinc, ni * 3 * N); ALLOC(rc, nz); ALLOC(zc, nz); ALLOC(ryc, nz);
+        ALLOC(pose_agg, P);
+        h->ml.resize(hl.size());   // fixed size from here on: the arena requests keep pointers into it
+        h->ml_degree = std::max(1, std::min(pr.pcg_ml_degree, 12));
+        {
+            static const double frac_of_degree[13] = {4, 4, 4, 8, 10, 15, 20, 25, 30, 35, 40, 45, 50};   // Chebyshev interval [hi / frac, hi]
+            h->ml_frac = frac_of_degree[h->ml_degree];
         }
+        ALLOC(mlblk, (size_t)hl[0].col.size() * NN + (size_t)h->n1 * 6);
+        size_t max_grid = 1;
+        for (size_t l = 0; l < hl.size(); ++l) {
+            const MlHostLevel& H = hl[l];
+            asc_handle::MlLevel& D = h->ml[l];
+            D.n = H.n; D.nnzb = (int)H.col.size(); D.n_next = H.n_next;
+            const bool top = l + 1 == hl.size();
+            reqs.push_back(ArenaReq{(void**)&D.row_ptr, sizeof(int) * (size_t)(H.n + 1)});
+            reqs.push_back(ArenaReq{(void**)&D.col, sizeof(int) * std::max<size_t>(H.col.size(), 1)});
+            reqs.push_back(ArenaReq{(void**)&D.diag_pos, sizeof(int) * (size_t)H.n});
+            if (l > 0) reqs.push_back(ArenaReq{(void**)&D.Eb, sizeof(double) * H.col.size() * NN});
+            reqs.push_back(ArenaReq{(void**)&D.r, sizeof(double) * (size_t)H.n * N});
+            if (!top) {
+                reqs.push_back(ArenaReq{(void**)&D.agg, sizeof(int) * (size_t)H.n});
+                reqs.push_back(ArenaReq{(void**)&D.mptr, sizeof(int) * (size_t)(H.n_next + 1)});
+                reqs.push_back(ArenaReq{(void**)&D.midx, sizeof(int) * (size_t)H.n});
+                reqs.push_back(ArenaReq{(void**)&D.cptr, sizeof(int) * H.cptr.size()});
+                reqs.push_back(ArenaReq{(void**)&D.cidx, sizeof(int) * std::max<size_t>(H.cidx.size(), 1)});
+                reqs.push_back(ArenaReq{(void**)&D.Dinv, sizeof(double) * (size_t)H.n * NN});
+                reqs.push_back(ArenaReq{(void**)&D.lmax, sizeof(double) * 4});
+                reqs.push_back(ArenaReq{(void**)&D.za, sizeof(double) * (size_t)H.n * N});
+                reqs.push_back(ArenaReq{(void**)&D.zb, sizeof(double) * (size_t)H.n * N});
+                reqs.push_back(ArenaReq{(void**)&D.d, sizeof(double) * (size_t)H.n * N});
+                max_grid = std::max<size_t>(max_grid, (size_t)cdiv(H.n, 4));
+            }
+        }
+        ALLOC(Yb, (size_t)h->n1 * 6); ALLOC(Ski, 36); ALLOC(mlcol, h->n1);
+        ALLOC(Atop, (size_t)h->ntop * h->ntop); ALLOC(ztop, h->ntop); ALLOC(mlpart, 2 * max_grid + 2);
     }
     ALLOC(Minv, PN * N); ALLOC(MinvK, 36); ALLOC(rhs, PN + 8);
     ALLOC(vx, PN + 8); ALLOC(vr, PN + 8); ALLOC(vz, PN + 8); ALLOC(vp, PN + 8);
     ALLOC(ybuf, PN + 8 + 2 * kPartCols);
     const size_t nStep = (size_t)cdiv(std::max<int64_t>((int64_t)PN + 6, (int64_t)L * 4), 256);
     ALLOC(partA, std::max<size_t>(std::max<size_t>((size_t)P + 1024, nStep), (size_t)h->nC) * kPartCols); ALLOC(partC, (size_t)h->nCtaPose * kPartCols);
-    ALLOC(grpC, (size_t)(cdiv(h->nCtaPose, kRowGroup) + 1) * kPcgCols); ALLOC(grpB, (size_t)(cdiv(h->nBlkB, kRowGroup) + 1) * kPcgCols);
-    ALLOC(tickC, cdiv(h->nCtaPose, kRowGroup) + 2); ALLOC(tickB, cdiv(h->nBlkB, kRowGroup) + 2); ALLOC(tickG, 4);
     ALLOC(partB, (size_t)h->nBlkB * kPartCols); ALLOC(partL, (size_t)h->nBlkLm * kPartCols); ALLOC(partR, 64 * kPartCols);
     h->nErrBlk = cdiv(M, 256) + cdiv((int64_t)P + L, 256) + h->nBlkLm + 8;
     ALLOC(errblk, h->nErrBlk); ALLOC(lmerr, h->nBlkLmK2);
@@ -1730,28 +1941,11 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     h->Dloc = h->precblk; h->rloc = h->Dloc + h->regionA; h->krow = h->rloc + PN;
     rc = setup_peer_exchange(h);
     if (rc) return rc;
-    if (h->use_coarse) {   // cuSOLVER workspaces: separate grow-only allocations
-        int lw1 = 0, lw2 = 0, lf1 = 0;
-        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw1) != CUSOLVER_STATUS_SUCCESS ||
-            cusolverDnDpotri_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->E, h->nz, &lw2) != CUSOLVER_STATUS_SUCCESS)
-            return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
-        if (std::max(lw1, lw2) > h->lwork) {
-            if (h->work) cudaFree(h->work);
-            h->lwork = std::max(lw1, lw2);
-            CUDA_TRY(cudaMalloc((void**)&h->work, sizeof(double) * (size_t)h->lwork));
-        }
-        if (pr.pcg_coarse_fp32) {
-            int lf2 = 0;
-            if (cusolverDnSpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->Ef, h->nz, &lf1) != CUSOLVER_STATUS_SUCCESS ||
-                cusolverDnSpotri_bufferSize(h->solver, CUBLAS_FILL_MODE_UPPER, h->nz, h->Ef, h->nz, &lf2) != CUSOLVER_STATUS_SUCCESS)
-                return fail(ASC_ERR_CUDA, "cusolver workspace query failed");
-            lf1 = std::max(std::max(lf1, lf2), 1 << 16);
-            if (lf1 > h->lworkf) {
-                if (h->workf) cudaFree(h->workf);
-                h->lworkf = lf1;
-                CUDA_TRY(cudaMalloc((void**)&h->workf, sizeof(float) * (size_t)h->lworkf));
-            }
-        }
+    if (h->use_coarse) {
+        h->ml[0].Eb = h->mlblk;
+        h->EK = h->mlblk + hl[0].col.size() * (size_t)N * N;
+        if ((size_t)h->ntop * sizeof(double) > 200 * 1024) return fail(ASC_ERR_INVALID, "pcg_ml_top_dim too large for the top-level kernel");
+        CUDA_TRY(cudaFuncSetAttribute(ml_top_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     lap("cudaMalloc + memset");
 #define UP(dst, src, bytes) CUDA_TRY(cudaMemcpyAsync(h->dst, src, (bytes), cudaMemcpyHostToDevice, h->stream))
@@ -1774,12 +1968,23 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
         }
     }
     if (h->use_coarse) {
-        UP(agg_pose_ptr, agg_pose_ptr.data(), sizeof(int) * (h->nA + 1)); UP(agg_inc_ptr, agg_inc_ptr.data(), sizeof(int) * (h->nA + 1));
-        UP(pose_agg, pose_agg.data(), sizeof(int) * P);
-    }
-    if (h->use_coarse && h->nDest) {
-        UP(dest_ptr, dest_ptr.data(), sizeof(int) * (h->nDest + 1)); UP(dest_ca, dest_ca.data(), sizeof(int) * h->nDest); UP(dest_cb, dest_cb.data(), sizeof(int) * h->nDest);
-        UP(pair_a, pair_a.data(), sizeof(int) * pair_a.size()); UP(pair_b, pair_b.data(), sizeof(int) * pair_b.size());
+        UP(pose_agg, pose_cluster.data(), sizeof(int) * P);
+        UP(dest_ptr, dest_ptr.data(), sizeof(int) * (h->nDest + 1)); UP(pos_lo, pos_lo.data(), sizeof(int) * h->nDest); UP(pos_up, pos_up.data(), sizeof(int) * h->nDest);
+        if (!pair_a.empty()) { UP(pair_a, pair_a.data(), sizeof(int) * pair_a.size()); UP(pair_b, pair_b.data(), sizeof(int) * pair_b.size()); }
+        for (size_t l = 0; l < hl.size(); ++l) {
+            const MlHostLevel& H = hl[l];
+            asc_handle::MlLevel& D = h->ml[l];
+            CUDA_TRY(cudaMemcpyAsync(D.row_ptr, H.row_ptr.data(), sizeof(int) * (H.n + 1), cudaMemcpyHostToDevice, h->stream));
+            if (!H.col.empty()) CUDA_TRY(cudaMemcpyAsync(D.col, H.col.data(), sizeof(int) * H.col.size(), cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(D.diag_pos, H.diag_pos.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
+            if (l + 1 < hl.size()) {
+                CUDA_TRY(cudaMemcpyAsync(D.agg, H.agg.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(D.mptr, H.mptr.data(), sizeof(int) * (H.n_next + 1), cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(D.midx, H.midx.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(D.cptr, H.cptr.data(), sizeof(int) * H.cptr.size(), cudaMemcpyHostToDevice, h->stream));
+                if (!H.cidx.empty()) CUDA_TRY(cudaMemcpyAsync(D.cidx, H.cidx.data(), sizeof(int) * H.cidx.size(), cudaMemcpyHostToDevice, h->stream));
+            }
+        }
     }
     UP(enc, enc, sizeof(double) * PN);
     if (L) UP(lm_prior, lm_prior, sizeof(double) * 3 * L);
@@ -1888,7 +2093,6 @@ int asc_optimize(asc_handle* h, int32_t mode, asc_iter_log* log, int32_t log_cap
     if (mode != ASC_BATCH_LM && mode != ASC_BATCH_DOGLEG) return fail(ASC_ERR_INVALID, "unknown optimisation mode %d", mode);
     const asc_params& p = h->prm;
     double error = 0.0, lambda = p.lambda_initial, Delta = p.delta_initial;
-    h->coarse_valid = false;   // every optimize() call is self-contained and bitwise repeatable
     rc = dispatch_error(h, h->q, h->lm4, h->X, &error);   // NonlinearOptimizer state at construction
     if (rc) return rc;
     int iterations = 0;
@@ -1980,7 +2184,6 @@ int asc_solve_damped(asc_handle* h, double lambda, double* dq, double* dl, doubl
     if (rc) return rc;
     if (!h->linearized) { rc = dispatch_linearize(h, false, nullptr, nullptr); if (rc) return rc; }
     int its = 0;
-    h->coarse_valid = false;
     rc = dispatch_solve(h, lambda, &its);
     if (pcg_iterations) *pcg_iterations = its;
     if (rc) return rc;
@@ -2036,6 +2239,18 @@ int asc_solver_info(asc_handle* h, int32_t* n_clusters, int32_t* coarse_dim, int
     if (n_clusters) *n_clusters = h->nC;
     if (coarse_dim) *coarse_dim = h->use_coarse ? h->nz : 0;
     if (cluster_block_doubles) *cluster_block_doubles = (int64_t)h->scTotal;
+    return ASC_OK;
+}
+
+int asc_coarse_info(asc_handle* h, int32_t* n_levels, int32_t* level_nodes, int64_t* level_blocks, int32_t capacity, int32_t* degree) {
+    if (!h || !h->problem_set) return fail(ASC_ERR_INVALID, "set the problem first");
+    const int nl = h->use_coarse ? (int)h->ml.size() : 0;
+    if (n_levels) *n_levels = nl;
+    for (int l = 0; l < nl && l < capacity; ++l) {
+        if (level_nodes) level_nodes[l] = h->ml[l].n;
+        if (level_blocks) level_blocks[l] = h->ml[l].nnzb;
+    }
+    if (degree) *degree = h->ml_degree;
     return ASC_OK;
 }
 

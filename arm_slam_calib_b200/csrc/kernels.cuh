@@ -1259,158 +1259,7 @@ inc_v_kernel(int nInc, const int* __restrict__ inc_lo, const int* __restrict__ i
     }
 }
 
-// E[ca][cb] = - sum over the destination's (incidence a, incidence b) pairs of T_a V_b^T ; one warp per destination block
-template <int N>
-__global__ void __launch_bounds__(128)
-coarse_blocks_kernel(int nDest, const int* __restrict__ dest_ptr, const int* __restrict__ dest_ca, const int* __restrict__ dest_cb,
-                     const int* __restrict__ pair_a, const int* __restrict__ pair_b, const double* __restrict__ V, const double* __restrict__ T,
-                     double* __restrict__ E, int nz) {
-    constexpr int NE = (N * N + 31) / 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int d = blockIdx.x * 4 + warp;
-    if (d >= nDest) return;
-    double acc[NE];
-#pragma unroll
-    for (int i = 0; i < NE; ++i) acc[i] = 0.0;
-    for (int pr = dest_ptr[d]; pr < dest_ptr[d + 1]; ++pr) {
-        const double* Ta = T + (size_t)__ldg(pair_a + pr) * 3 * N;
-        const double* Vb = V + (size_t)__ldg(pair_b + pr) * 3 * N;
-#pragma unroll
-        for (int i = 0; i < NE; ++i) {
-            const int e = lane + 32 * i;
-            if (e < N * N) {
-                const int a = e / N, b = e % N;
-                acc[i] += Ta[3 * a] * Vb[3 * b] + Ta[3 * a + 1] * Vb[3 * b + 1] + Ta[3 * a + 2] * Vb[3 * b + 2];
-            }
-        }
-    }
-    const int ca = dest_ca[d], cb = dest_cb[d];
-#pragma unroll
-    for (int i = 0; i < NE; ++i) {
-        const int e = lane + 32 * i;
-        if (e < N * N) E[(size_t)(ca * N + e / N) * nz + cb * N + e % N] = -acc[i];
-    }
-}
-
-// E[c][c] += sum_{p in c} (B_pp + lambda I)     (rank 0 only in a multi-GPU run); thread per (c, a, b)
-__global__ void coarse_diag_kernel(int nC, int N, double lambda, const int* __restrict__ cl_ptr, const double* __restrict__ Bpp,
-                                   double* __restrict__ E, int nz) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nC * N * N) return;
-    const int c = i / (N * N), a = (i / N) % N, b = i % N;
-    double s = 0.0;
-    for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) s += Bpp[(size_t)p * N * N + a * N + b];
-    if (a == b) s += lambda * (cl_ptr[c + 1] - cl_ptr[c]);
-    E[(size_t)(c * N + a) * nz + c * N + b] += s;
-}
-
-// fp64 -> fp32 copy of the coarse matrix (only a preconditioner: single precision is enough, and it makes the
-// factorisation ~4x cheaper and the per-iteration product half the bytes).  Accumulation stays fp64 in the product.
-__global__ void __launch_bounds__(256) to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (float)in[i];
-}
-
-__global__ void __launch_bounds__(256) identity_f32_kernel(float* __restrict__ A, int n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (size_t)n * n) A[i] = (i / n == i % n) ? 1.0f : 0.0f;
-}
-
-// cuSOLVER leaves the inverse in the row-major lower triangle (column-major UPPER); mirror it so rows are complete
-__global__ void __launch_bounds__(256) mirror_lower_f32_kernel(float* __restrict__ A, int n) {
-    __shared__ float tile[32][33];
-    const int bx = blockIdx.x, by = blockIdx.y;
-    if (bx > by) return;   // blocks on or below the diagonal hold valid data (row >= col)
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {
-        const int row = by * 32 + r, col = bx * 32 + tx;
-        tile[r][tx] = (row < n && col < n && row >= col) ? A[(size_t)row * n + col] : 0.0f;
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int row = bx * 32 + r, col = by * 32 + tx;   // transposed position
-        if (row < n && col < n && col > row) A[(size_t)row * n + col] = tile[tx][r];
-    }
-}
-
-// Coarse-space index maps.  The restriction Z^T r is produced per CLUSTER (rc, length nC N + 6, by the cluster update
-// kernel); the coarse unknowns live per AGGREGATE of S consecutive clusters (length nz = nA N + 6).
-__device__ __forceinline__ int coarse_index_of(int i, int nC, int nA, int N, int S) {   // cluster-vector index -> coarse index
-    if (i >= nC * N) return nA * N + (i - nC * N);
-    const int c = i / N;
-    return (c / S) * N + (i - c * N);
-}
-
-// aggregated restriction A rc (only launched when an aggregate holds more than one cluster)
-__global__ void __launch_bounds__(256) coarse_aggregate_kernel(const double* __restrict__ rc, double* __restrict__ rca, int n, int nA, int nC, int N, int S,
-                                                                const int* __restrict__ done) {
-    if (done && *done) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double v;
-    if (i >= nA * N) v = rc[nC * N + (i - nA * N)];
-    else {
-        const int a = i / N, t = i - a * N;
-        const int c1 = min((a + 1) * S, nC);
-        v = 0.0;
-        for (int c = a * S; c < c1; ++c) v += rc[c * N + t];
-    }
-    rca[i] = v;
-}
-
-// Multi-GPU coarse level: rank r solves U^T U X = I[:, r0 : r0 + m] after the replicated factorisation (1/G of the
-// triangular-solve work); X is rows r0 .. r0+m-1 of the symmetric inverse.  B is column-major n x m.
-__global__ void __launch_bounds__(256) identity_slice_f32_kernel(float* __restrict__ B, int n, int r0, int m) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (size_t)n * m) B[i] = ((int)(i % n) == r0 + (int)(i / n)) ? 1.0f : 0.0f;
-}
-
-// A coarse inverse kept from an earlier linearisation is mostly off by a scalar (the robust weights move together while the
-// optimiser converges).  Given zc = Einv_old rc and y = E_new zc, the best scalar is alpha = (rc.zc) / (zc.y): the exact line
-// search of the coarse correction in the E_new norm.  Writes alpha and rescales zc in place.  One block of 1024 threads.
-__global__ void __launch_bounds__(kReduceThreads) coarse_refit_kernel(const double* __restrict__ rc, double* __restrict__ zc,
-                                                                    const double* __restrict__ y, int n, double* __restrict__ alpha) {
-    __shared__ double s1[kReduceThreads], s2[kReduceThreads];
-    double a = 0.0, b = 0.0;
-    for (int i = threadIdx.x; i < n; i += kReduceThreads) { a += rc[i] * zc[i]; b += zc[i] * y[i]; }
-    s1[threadIdx.x] = a; s2[threadIdx.x] = b;
-    __syncthreads();
-    for (int o = kReduceThreads / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
-        __syncthreads();
-    }
-    const double al = (s2[0] > 0.0 && s1[0] > 0.0) ? s1[0] / s2[0] : 1.0;
-    for (int i = threadIdx.x; i < n; i += kReduceThreads) zc[i] *= al;
-    if (threadIdx.x == 0) *alpha = al;
-}
-
 __global__ void set_scalar_kernel(double* p, double v) { *p = v; }
-
-__global__ void scale_block_kernel(double* E, int nz, int off, double s) {
-    const int i = threadIdx.x;
-    if (i < 36) E[(size_t)(off + i / 6) * nz + off + i % 6] *= s;
-}
-
-// K rows: E[K r][c a] = sum_{p in c} B_pK[a][r] - sum over the cluster's incidences of (T W_Kj^T)[a][r]; thread per (c, a, r)
-__global__ void coarse_k_kernel(int nC, int N, int add_diag, const int* __restrict__ cl_ptr, const int* __restrict__ cl_inc_ptr,
-                                const int* __restrict__ cl_inc, const int* __restrict__ inc_lm, const double* __restrict__ T,
-                                const double* __restrict__ WK, const double* __restrict__ BpK, const double* __restrict__ SKK,
-                                double* __restrict__ E, int nz) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 36) E[(size_t)(nC * N + i / 6) * nz + nC * N + i % 6] = SKK[i];
-    if (i >= nC * N * 6) return;
-    const int c = i / (N * 6), a = (i / 6) % N, r = i % 6;
-    double s = 0.0;
-    if (add_diag)
-        for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) s += BpK[(size_t)p * N * 6 + a * 6 + r];
-    for (int k = cl_inc_ptr[c]; k < cl_inc_ptr[c + 1]; ++k) {
-        const int inc = cl_inc[k];
-        const double* t = T + (size_t)inc * 3 * N + 3 * a;
-        const double* w = WK + 18 * (size_t)inc_lm[inc] + 3 * r;
-        s -= t[0] * w[0] + t[1] * w[1] + t[2] * w[2];
-    }
-    E[(size_t)(nC * N + r) * nz + c * N + a] = s;
-}
 
 // ------------------------------------------------------------------ K3: implicit Schur complement  y = S x
 // J_q is never read back in the PCG passes.  Column i of an observation's J_q is -J_l (a_i x (l - o_i))
@@ -1616,61 +1465,6 @@ __device__ __forceinline__ void pcg_mid_body(const MidArgs& a) {
     }
 }
 
-// "Last CTA" hand-over: every thread has made its global writes visible (__threadfence), the CTA takes a ticket, and the
-// CTA that draws the last one runs the single-CTA tail of the step inside the same launch (saves a kernel boundary of
-// ~8 us per fused pair in the PCG loop).  The partial sums are combined in a fixed order by that one CTA, so the result
-// does not depend on which CTA it is.
-__device__ __forceinline__ bool last_cta_arrives(unsigned* ticket) {
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned total = gridDim.x * gridDim.y;
-        const bool last = atomicAdd(ticket, 1u) == total - 1;
-        if (last) *ticket = 0;   // ready for the next launch
-        s_last = last ? 1 : 0;
-    }
-    __syncthreads();
-    if (s_last) __threadfence();
-    return s_last != 0;
-}
-
-// Two-level variant for kernels with thousands of CTAs: CTAs are grouped by 32 (consecutive blockIdx); the CTA that
-// completes a group sums the group's partial rows [8 columns] in row order into grp_rows[g]; the CTA that completes the
-// last group gets `true`.  tickets: [nGroups + 1] counters that return to zero.  The consumer then reads nGroups rows
-// instead of gridDim.x rows -- short enough for a 128-thread tail.
-constexpr int kRowGroup = 32;
-__device__ __forceinline__ bool grouped_rows_reduce(const double* cta_part, double* grp_rows, unsigned* tickets) {
-    __shared__ int s_flag;
-    const int nCta = gridDim.x, nGroups = (nCta + kRowGroup - 1) / kRowGroup;
-    const int g = blockIdx.x / kRowGroup, g0 = g * kRowGroup, gsize = min(kRowGroup, nCta - g0);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const bool last = atomicAdd(tickets + g, 1u) == (unsigned)(gsize - 1);
-        if (last) tickets[g] = 0;
-        s_flag = last ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_flag) return false;
-    __threadfence();
-    if (threadIdx.x < kPcgCols) {
-        double t = 0.0;
-        for (int r = 0; r < gsize; ++r) t += __ldcg(cta_part + (size_t)(g0 + r) * kPcgCols + threadIdx.x);
-        grp_rows[(size_t)g * kPcgCols + threadIdx.x] = t;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const bool last = atomicAdd(tickets + nGroups, 1u) == (unsigned)(nGroups - 1);
-        if (last) tickets[nGroups] = 0;
-        s_flag = last ? 1 : 0;
-    }
-    __syncthreads();
-    if (s_flag) __threadfence();
-    return s_flag != 0;
-}
-
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_mid_kernel(MidArgs a, PeerComm pcm, double* __restrict__ rows_local) {
     if (*a.done) return;
@@ -1702,8 +1496,7 @@ template <bool BACKSUB>
 __global__ void __launch_bounds__(kPassBThreads)
 schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const double* __restrict__ v4,
                     const double* __restrict__ WK, const double* __restrict__ Cinv, const double* __restrict__ xK,
-                    const int* __restrict__ done, const double* __restrict__ cg4, double* __restrict__ u4, double* __restrict__ blk_part,
-                    double* __restrict__ grp_rows, unsigned* __restrict__ grp_tickets) {
+                    const int* __restrict__ done, const double* __restrict__ cg4, double* __restrict__ u4, double* __restrict__ blk_part) {
     if (done && *done) return;
     const int j = blockIdx.x * kPassBLmPerBlock + (threadIdx.x >> 3);
     const int sub = threadIdx.x & 7;
@@ -1746,7 +1539,6 @@ schur_pass_b_kernel(int L, const int* __restrict__ lm_ptr, const double* __restr
             for (int w = 0; w < kPassBThreads / 32; ++w) t += s[w][threadIdx.x];
         blk_part[(size_t)blockIdx.x * kPcgCols + threadIdx.x] = t;
     }
-    if (grp_tickets) grouped_rows_reduce(blk_part, grp_rows, grp_tickets);
 }
 
 // pass C (pose-major): yloc_p = - sum_m J_q^T (J_l u_j); then (if add_diag) y_p = (B_pp + lambda) x_p + B_pK x_K + yloc_p.
@@ -1757,8 +1549,7 @@ schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int
                     const double2* __restrict__ J, const double* __restrict__ u4, const double* __restrict__ x, const double* __restrict__ Bpp,
                     const double* __restrict__ BpK, const int* __restrict__ done, double* __restrict__ y, double* __restrict__ cta_part,
                     const double* __restrict__ lambda_dev, const double* __restrict__ chain, const double* __restrict__ lml,
-                    const unsigned* __restrict__ xctr, double* __restrict__ xbase, long long xstride, double* __restrict__ grp_rows,
-                    unsigned* __restrict__ grp_tickets, int fuse_mid, MidArgs mid, DriftTab dt) {
+                    const unsigned* __restrict__ xctr, double* __restrict__ xbase, long long xstride, DriftTab dt) {
     if (done && *done) return;
     if (xctr) y = xbase + (size_t)((*xctr + 1u) & 1u) * xstride;   // multi-GPU: the next exchange slot of this rank
     const double lambda = lambda_dev ? *lambda_dev : lambda_val;   // device-resident inside the captured PCG graph
@@ -1832,10 +1623,6 @@ schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int
             for (int w = 0; w < kWarpsPerCta; ++w) s += s_part[w][threadIdx.x];
         cta_part[(size_t)blockIdx.x * kPcgCols + threadIdx.x] = s;
     }
-    if (grp_tickets) {
-        const bool fin = grouped_rows_reduce(cta_part, grp_rows, grp_tickets);
-        if (fin && fuse_mid) pcg_mid_body<kCtaThreads>(mid);   // single GPU: alpha and the K rows in the same launch
-    }
 }
 
 // K rows of y = S x from the pass B / pass C partial sums (used for the warm-start residual).  One block of 1024 threads.
@@ -1894,7 +1681,7 @@ pcg_update_kernel(int P, const double* __restrict__ p, const double* __restrict_
 }
 
 // Z^T y over the keyframe rows: ry[c N + t] = sum of y[p N + t] over the keyframes p of cluster c (K entries of ry stay 0).
-// One warp per cluster; feeds the side-stream GEMV qc = Einv ry while pcg_mid / the cluster update run on the main stream.
+// One warp per cluster; feeds the side-stream V-cycle t = V (Z^T y) while pcg_mid / the cluster update run on the main stream.
 __global__ void __launch_bounds__(128) coarse_restrict_y_kernel(int nC, int N, const int* __restrict__ cl_ptr, const double* __restrict__ y,
                                                                  double* __restrict__ ry, const int* __restrict__ done) {
     if (done && *done) return;
@@ -1903,6 +1690,60 @@ __global__ void __launch_bounds__(128) coarse_restrict_y_kernel(int nC, int N, c
     double a = 0.0;
     for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) a += y[(size_t)p * N + lane];
     ry[(size_t)c * N + lane] = a;
+}
+
+// Coarse correction zc = B [rc; rc_K] of the two-level preconditioner from the V-cycle output t = V rc (coarse_ml.cuh):
+//   z_K = S_k^-1 (src_K - E_Kc t),   z = t - Y z_K            (bordering of the extrinsic columns around the V-cycle)
+// direct mode (alpha == null):  zc  = [z; z_K]                  with src_K = K entries of the restriction rc
+// linear mode (alpha != null):  zc -= alpha [z; z_K]            with src_K = y_K and t = V (Z^T y): the correction is advanced by
+//                               linearity, so the V-cycle of an iteration runs on a side stream beside pcg_mid / the cluster update
+struct BorderArgs {
+    const double* t;       // [n1] V-cycle output (null: no coarse level)
+    const double* EK;      // [n1][6]
+    const double* Y;       // [n1][6]
+    const double* Ski;     // [36]
+    const double* srcK;    // [6]
+    const double* alpha;   // null = direct mode
+    double* zc;            // [n1 + 6]
+    int n1;
+};
+
+template <int T>
+__device__ __forceinline__ void coarse_border_apply(const BorderArgs& b) {
+    __shared__ double sg[T / 32][8];
+    __shared__ double szk[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < b.n1; i += T) {
+        const double ti = __ldcg(b.t + i);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) g[r] = fma(b.EK[(size_t)i * 6 + r], ti, g[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { const double w = warp_sum(g[r]); if (lane == 0) sg[warp][r] = w; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double tot = 0.0;
+        for (int w = 0; w < T / 32; ++w) tot += sg[w][threadIdx.x];
+        sg[0][threadIdx.x] = __ldcg(b.srcK + threadIdx.x) - tot;   // only row 0 of sg is read below; every thread < 6 wrote after reading its column
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double zk = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) zk = fma(b.Ski[6 * threadIdx.x + r], sg[0][r], zk);
+        szk[threadIdx.x] = zk;
+    }
+    __syncthreads();
+    const double al = b.alpha ? *b.alpha : 0.0;
+    for (int i = threadIdx.x; i < b.n1; i += T) {
+        double z = __ldcg(b.t + i);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) z = fma(-b.Y[(size_t)i * 6 + r], szk[r], z);
+        b.zc[i] = b.alpha ? b.zc[i] - al * z : z;
+    }
+    if (threadIdx.x < 6) b.zc[b.n1 + threadIdx.x] = b.alpha ? b.zc[b.n1 + threadIdx.x] - al * szk[threadIdx.x] : szk[threadIdx.x];
+    __syncthreads();
 }
 
 // rz_new, beta, convergence test, p_K <- z_K + beta p_K.  One CTA of T threads.
@@ -1914,18 +1755,9 @@ struct EndArgs {
     int max_iters;
     double *p, *z, *scal;
     int* done;
-    const double *rc, *zc;
-    int nz, nC, nA, S;
-    // side-branch mode (single GPU): the coarse correction is advanced by linearity instead of recomputed,
-    //   zc <- zc - alpha * scale * (qc + EinvK^T yK),   qc = Einv [Z^T y (clusters) ; 0]  from the side stream,
-    // EinvK = Einv + (offset of the 6 extrinsic COLUMNS): exactly the entries Einv[i][K] the direct product would use -- the
-    // fp32 inverse is symmetric only to ~1e-7, and using the extrinsic rows instead stalls CG at a 1e-7 relative residual,
-    // because the recursion accumulates that mismatch in absolute terms.  yK = K rows of y (pcg_mid), alpha = scal[0]
-    double* zc_rw;           // null: zc was recomputed by the GEMV
-    const double* qc;
-    const float* EinvK;
-    const double* yK;
-    const double* gemv_scale;
+    const double *rc, *zc;   // restriction Z^T r (length n1 + 6) and coarse correction (same length); null: no coarse level
+    int nz;                  // n1 + 6
+    BorderArgs border;       // border.t != null: finish the coarse correction here first
 };
 
 template <int T>
@@ -1933,25 +1765,13 @@ __device__ __forceinline__ void pcg_end_body(const EndArgs& a) {
     __shared__ double scratch[T];
     __shared__ double so[1];
     const int lane = threadIdx.x & 31, P = a.P, N = a.N;
-    if (a.zc_rw) {
-        const double alpha = a.scal[0], sc = a.gemv_scale ? *a.gemv_scale : 1.0;
-        double yk[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) yk[r] = a.yK[r];
-        for (int i = threadIdx.x; i < a.nz; i += T) {
-            double kq = 0.0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) kq = fma((double)a.EinvK[(size_t)i * a.nz + r], yk[r], kq);   // row i, extrinsic columns
-            a.zc_rw[i] -= alpha * (a.qc[i] + sc * kq);   // qc already carries the GEMV's scale
-        }
-        __syncthreads();
-    }
+    if (a.border.t) coarse_border_apply<T>(a.border);
     block_sum_cols<1, T>(a.part, a.nPart, so, scratch);
     double t = so[0];
     if (a.rc) {   // r . (Z zc) = (Z^T r) . zc ; and the K rows of z get their coarse part
         __shared__ double prod[T];
         double acc = 0.0;
-        for (int i = threadIdx.x; i < a.nC * N + 6; i += T) acc += __ldcg(a.rc + i) * __ldcg(a.zc + coarse_index_of(i, a.nC, a.nA, N, a.S));
+        for (int i = threadIdx.x; i < a.nz; i += T) acc += __ldcg(a.rc + i) * __ldcg(a.zc + i);
         prod[threadIdx.x] = acc;
         __syncthreads();
         block_sum_cols<1, T, false>(prod, T, so, scratch);
@@ -1967,7 +1787,12 @@ __device__ __forceinline__ void pcg_end_body(const EndArgs& a) {
         __syncwarp();
         if (lane == 0) {
             a.scal[1] = beta; a.scal[2] = rz_new; a.scal[5] = it;
-            if (!(rz_new > a.tol2 * a.scal[3]) || it >= a.max_iters || a.scal[6] != 0.0) *a.done = 1;
+            // scal[6]: 0 = fine, 1 = p^T S p <= 0 (pcg_mid), 2 = r^T M^-1 r negative or NaN (indefinite / garbage
+            // preconditioner), 3 = iteration limit reached above the tolerance.  Only rz_new in [0, tol^2 rz0] is convergence.
+            const bool conv = rz_new >= 0.0 && !(rz_new > a.tol2 * a.scal[3]);
+            if (!conv && !(rz_new > 0.0) && a.scal[6] == 0.0) a.scal[6] = 2.0;
+            if (!conv && it >= a.max_iters && a.scal[6] == 0.0) a.scal[6] = 3.0;
+            if (conv || a.scal[6] != 0.0) *a.done = 1;
         }
     }
 }
@@ -1975,36 +1800,6 @@ __device__ __forceinline__ void pcg_end_body(const EndArgs& a) {
 __global__ void __launch_bounds__(kReduceThreads) pcg_end_kernel(EndArgs a) {
     if (*a.done) return;
     pcg_end_body<kReduceThreads>(a);
-}
-
-// zc = Einv(fp32, full symmetric, row-major) * x, one warp per row, fp64 accumulation.  x is the restriction itself
-// (one cluster per aggregate) or its aggregated copy written by coarse_aggregate_kernel.  With a ticket, the CTA that
-// finishes last also runs the end-of-iteration step (pcg_end_body) in the same launch.
-__global__ void __launch_bounds__(128) coarse_gemv_f32_kernel(const float* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
-                                                              int n, const int* __restrict__ done, const double* __restrict__ alpha,
-                                                              EndArgs end, unsigned* ticket) {
-    if (done && *done) return;
-    const double scale = alpha ? *alpha : 1.0;   // scalar re-fit of a reused (stale) coarse inverse, see coarse_refit_kernel
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 4 + warp;
-    if (row < n) {
-        const float* a = A + (size_t)row * n;
-        double acc0 = 0.0, acc1 = 0.0;
-        int i = lane * 2;
-        for (; i + 64 + 1 < n; i += 128) {
-            const float2 u = *reinterpret_cast<const float2*>(a + i);
-            const float2 v = *reinterpret_cast<const float2*>(a + i + 64);
-            acc0 = fma((double)u.x, x[i], fma((double)u.y, x[i + 1], acc0));
-            acc1 = fma((double)v.x, x[i + 64], fma((double)v.y, x[i + 65], acc1));
-        }
-        for (; i < n; i += 64) {
-            acc0 = fma((double)a[i], x[i], acc0);
-            if (i + 1 < n) acc0 = fma((double)a[i + 1], x[i + 1], acc0);
-        }
-        const double t = warp_sum(acc0 + acc1);
-        if (lane == 0) y[row] = scale * t;
-    }
-    if (ticket && last_cta_arrives(ticket)) pcg_end_body<128>(end);
 }
 
 // PCG start: x = 0, r = rhs, z = Minv r, p = z, CTA partials of r.z  (one warp per keyframe); K part by block 0 / warp 0 extra.
@@ -2058,15 +1853,16 @@ pcg_init_kernel(int P, const double* __restrict__ rhs, const double* __restrict_
 __global__ void __launch_bounds__(kReduceThreads)
 pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __restrict__ kdot, double* __restrict__ scal,
                     int* __restrict__ done, const double* __restrict__ rc, const double* __restrict__ zc, int nz, double* __restrict__ zK,
-                    double* __restrict__ pK, double lambda, double rz_ref, double tol2, int nC, int nA, int N, int S) {
+                    double* __restrict__ pK, double lambda, double rz_ref, double tol2, BorderArgs border) {
     __shared__ double scratch[kReduceThreads];
     __shared__ double so[1];
+    if (border.t) coarse_border_apply<kReduceThreads>(border);   // zc = B rc from the V-cycle output
     block_sum_cols<1>(part, nPart, so, scratch);
     double t = so[0];
     if (rc) {
         __shared__ double prod[kReduceThreads];
         double a = 0.0;
-        for (int i = threadIdx.x; i < nC * N + 6; i += kReduceThreads) a += rc[i] * zc[coarse_index_of(i, nC, nA, N, S)];
+        for (int i = threadIdx.x; i < nz; i += kReduceThreads) a += rc[i] * zc[i];
         prod[threadIdx.x] = a;
         __syncthreads();
         block_sum_cols<1, kReduceThreads, false>(prod, kReduceThreads, so, scratch);
@@ -2080,6 +1876,7 @@ pcg_init_end_kernel(const double* __restrict__ part, int nPart, const double* __
         const double ref = rz_ref > 0.0 ? rz_ref : t;
         scal[0] = 0.0; scal[1] = 0.0; scal[2] = t; scal[3] = ref; scal[4] = 0.0; scal[5] = 0.0; scal[6] = 0.0; scal[7] = 0.0;
         scal[8] = lambda;   // read by the kernels of the captured PCG graph
+        if (!(t >= 0.0)) scal[6] = 2.0;   // negative or NaN r^T M^-1 r: the preconditioner is not positive definite
         *done = (t > tol2 * ref && t > 0.0) ? 0 : 1;   // nothing to do (zero rhs, or the warm start already meets the tolerance)
     }
 }

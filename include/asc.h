@@ -35,7 +35,8 @@ enum asc_status {
     ASC_ERR_INVALID = 1,       /* bad argument / call order */
     ASC_ERR_CUDA = 2,          /* no device, launch or allocation failure */
     ASC_ERR_INDETERMINATE = 3, /* gtsam::IndeterminantLinearSystemException, ArmSlamCalib.cpp:451 */
-    ASC_ERR_COMM = 4           /* NCCL failure */
+    ASC_ERR_COMM = 4,          /* NCCL failure */
+    ASC_ERR_NOT_CONVERGED = 5  /* the PCG solve hit pcg_max_iters above pcg_rel_tol (no GTSAM analogue: Cholesky is direct) */
 };
 
 /* optimization_mode, include/arm_slam_calib/ArmSlamCalib.h:59-64 (ISAM is out of scope) */
@@ -77,13 +78,13 @@ typedef struct asc_params {
     int32_t pcg_cluster_max;         /* max keyframes per cluster (10); <=1: one block per keyframe */
     double pcg_cluster_covis;        /* start a new cluster when the share of common landmarks with the
                                         previous keyframe drops below this (0.25) */
-    int32_t pcg_coarse_max_dim;      /* second preconditioner level (one joint-offset vector per cluster + the
-                                        extrinsic, dense factorisation by cuSOLVER) is used while its dimension
-                                        nClusters*N+6 is <= this (16384); 0 switches it off */
-    int32_t pcg_coarse_fp32;         /* 1 (default): factorise/apply the coarse operator in fp32 (fp64 accumulation in the
-                                        product; falls back to fp64 if the fp32 Cholesky fails); 0: fp64 throughout */
-    int32_t pcg_coarse_agg;          /* consecutive clusters per coarse aggregate: the coarse space has one joint-offset vector
-                                        per AGGREGATE, dimension ceil(nClusters/agg)*N+6 (the factorisation costs its cube) */
+    /* second preconditioner level: coarse space = one joint-offset vector per cluster + the extrinsic; its block-sparse operator is
+       solved by a multilevel V-cycle (Chebyshev smoothers on N x N block rows, aggregation, small dense top level) written for
+       this library (csrc/coarse_ml.cuh) -- no size limit, no cuSOLVER/cuBLAS */
+    int32_t pcg_coarse_levels;       /* max smoothed levels of the V-cycle (8); 0 switches the coarse level off */
+    int32_t pcg_ml_degree;           /* Chebyshev degree of the pre- and post-smoother (4) */
+    int32_t pcg_ml_agg;              /* target nodes per aggregate (8) */
+    int32_t pcg_ml_top_dim;          /* aggregate until the coarsest level has at most this many unknowns (640); it is inverted densely */
 } asc_params;
 
 /* One record per outer iterate() of the optimiser */
@@ -95,7 +96,11 @@ typedef struct asc_iter_log {
     double error;          /* graph.error(values) after the iteration */
     double lambda_or_delta;/* lambda (LM) or Delta (Dogleg) after the iteration */
     double linearize_ms;   /* device time of the linearisation + assembly kernels */
-    double solve_ms;       /* device time of Schur/PCG/back-substitution */
+    double solve_ms;       /* device time of everything after the linearisation (all inner steps) */
+    /* per-stage device times inside solve_ms, summed over the inner steps (the role of the reference's Timer.cpp:41-89 tables) */
+    double prepare_ms;     /* landmark-block inverses, cluster blocks and their inverses, reduced right-hand side */
+    double coarse_ms;      /* coarse-level refresh: block-sparse operator, multilevel set-up, border elimination */
+    double pcg_ms;         /* the PCG loop */
 } asc_iter_log;
 
 typedef struct asc_linear_stats {
@@ -210,6 +215,9 @@ int64_t asc_launch_count(asc_handle* h);
 /* Sizes of the preconditioner of the packed problem (for byte accounting): clusters, coarse dimension (0 = no coarse level),
  * total doubles in the cluster blocks. */
 int asc_solver_info(asc_handle* h, int32_t* n_clusters, int32_t* coarse_dim, int64_t* cluster_block_doubles);
+/* Hierarchy of the multilevel coarse solve: number of levels (the last one is the dense top level; 0 = no coarse level), nodes and
+ * non-zero N x N blocks of each level (arrays of `capacity` entries), Chebyshev degree of the smoothers. */
+int asc_coarse_info(asc_handle* h, int32_t* n_levels, int32_t* level_nodes, int64_t* level_blocks, int32_t capacity, int32_t* degree);
 /* CUDA-event stopwatch recorded on the stream this handle launches its kernels on */
 int asc_timer_start(asc_handle* h);
 int asc_timer_stop(asc_handle* h, double* elapsed_ms);

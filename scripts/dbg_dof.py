@@ -13,8 +13,8 @@ for variant in ["default", "tol1e-14", "nocoarse", "fp64coarse", "percluster1"]:
     prm = asc.default_params()
     for i in range(20): prm.sigma_encoder[i] = 0.03
     if variant == "tol1e-14": prm.pcg_rel_tol = 1e-14
-    if variant == "nocoarse": prm.pcg_coarse_max_dim = 0
-    if variant == "fp64coarse": prm.pcg_coarse_fp32 = 0
+    if variant == "nocoarse": prm.pcg_coarse_levels = 0
+    if variant == "deg2": prm.pcg_ml_degree = 2
     if variant == "percluster1": prm.pcg_cluster_max = 1
     orc = Oracle(pb, prm)
     ref = orc.optimize(pb.q0, pb.l0, pb.x0, mode=0, solver=0)

@@ -16,7 +16,7 @@ prm.max_iterations = maxit
 if len(sys.argv) > 4:
     prm.pcg_rel_tol = float(sys.argv[4])
 if len(sys.argv) > 5:
-    prm.pcg_coarse_agg = int(sys.argv[5])
+    prm.pcg_ml_degree = int(sys.argv[5])
 if len(sys.argv) > 6:
     prm.pcg_cluster_max = int(sys.argv[6])
 t = time.time()

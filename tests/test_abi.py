@@ -35,8 +35,8 @@ def test_struct_mirrors_match_the_header(asc, tmp_path):
     src = tmp_path / "sz.c"
     fields = {"asc_params": ["sigma_px", "sigma_encoder", "sigma_extrinsic", "use_dead_band", "dead_band", "pose3_chart", "max_iterations",
                              "relative_error_tol", "lambda_initial", "delta_initial", "pcg_rel_tol", "pcg_max_iters", "device",
-                             "pcg_cluster_max", "pcg_cluster_covis", "pcg_coarse_max_dim", "pcg_coarse_fp32", "pcg_coarse_agg"],
-              "asc_iter_log": ["iteration", "pcg_iterations", "error", "solve_ms"],
+                             "pcg_cluster_max", "pcg_cluster_covis", "pcg_coarse_levels", "pcg_ml_degree", "pcg_ml_agg", "pcg_ml_top_dim"],
+              "asc_iter_log": ["iteration", "pcg_iterations", "error", "solve_ms", "prepare_ms", "coarse_ms", "pcg_ms"],
               "asc_linear_stats": ["error", "cheirality"],
               "asc_sim_config": ["trajectory_size", "landmark_size_x", "max_range", "seed", "min_observations", "sim_extrinsic", "extrinsic_guess",
                                  "segment_length"]}

@@ -113,16 +113,19 @@ def test_generated_chains_match_oracle(asc, oracle_cls, n_dof):
     opt.close()
 
 
-@pytest.mark.parametrize("variant", ["per_pose_blocks", "clusters_only", "coarse_fp64"])
+@pytest.mark.parametrize("variant", ["per_pose_blocks", "clusters_only", "ml_degree_2", "ml_deep"])
 def test_preconditioner_variants_give_the_same_solution(asc, oracle_cls, c1_offset_problem, variant):
     pb = c1_offset_problem
     prm = asc.default_params()
     if variant == "per_pose_blocks":
         prm.pcg_cluster_max = 1
     elif variant == "clusters_only":
-        prm.pcg_coarse_max_dim = 0
-    else:
-        prm.pcg_coarse_fp32 = 0
+        prm.pcg_coarse_levels = 0
+    elif variant == "ml_degree_2":
+        prm.pcg_ml_degree = 2
+    else:                       # several smoothed levels even on this small graph
+        prm.pcg_ml_agg = 2
+        prm.pcg_ml_top_dim = 36
     opt = asc.BatchOptimizer(pb, prm)
     vals = perturbed_values(pb)
     opt.set_values(*vals)
