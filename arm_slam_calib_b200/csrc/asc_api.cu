@@ -136,6 +136,7 @@ struct MlHostLevel {
     std::vector<double> w;                     // static edge weight per block (shared-landmark pair count, summed on coarsening)
     std::vector<int> agg, mptr, midx;          // aggregation to the next level
     std::vector<int> cptr, cidx;               // children of each block of the NEXT level among this level's blocks
+    std::vector<int> rptr, ridx;               // blocks of the rows of each aggregate, flattened (restriction kernel)
     int n_next = 0;
 };
 
@@ -205,6 +206,12 @@ void ml_coarsen_pattern(MlHostLevel& L, MlHostLevel& C) {
     L.midx.assign(L.n, 0);
     std::vector<int> fill(L.mptr.begin(), L.mptr.end() - 1);
     for (int i = 0; i < L.n; ++i) L.midx[fill[L.agg[i]]++] = i;
+    L.rptr.assign(na + 1, 0); L.ridx.clear();
+    for (int a = 0; a < na; ++a) {
+        for (int q = L.mptr[a]; q < L.mptr[a + 1]; ++q)
+            for (int k = L.row_ptr[L.midx[q]]; k < L.row_ptr[L.midx[q] + 1]; ++k) L.ridx.push_back(k);
+        L.rptr[a + 1] = (int)L.ridx.size();
+    }
 }
 
 }  // namespace
@@ -304,6 +311,7 @@ struct asc_handle {
         int *row_ptr = nullptr, *col = nullptr, *diag_pos = nullptr;          // BSR pattern (both triangles)
         int *agg = nullptr, *mptr = nullptr, *midx = nullptr;                 // node -> aggregate; members of each aggregate
         int *cptr = nullptr, *cidx = nullptr;                                 // blocks of THIS level that sum into each block of the next
+        int *rptr = nullptr, *ridx = nullptr;                                 // blocks of the rows of each aggregate (restriction)
         double *Eb = nullptr, *Dinv = nullptr, *lmax = nullptr;
         double *r = nullptr, *za = nullptr, *zb = nullptr, *d = nullptr;      // V-cycle vectors (r of level 0 is the caller's)
     };
@@ -311,6 +319,7 @@ struct asc_handle {
     double *mlblk = nullptr;        // [Eb of level 0 | EK]: one all-reduce in a multi-GPU run
     double *EK = nullptr, *Yb = nullptr, *Ski = nullptr;   // extrinsic border of level 1, Y = V E_cK, S_k^-1
     double *Atop = nullptr, *ztop = nullptr, *mlpart = nullptr, *mlcol = nullptr;
+    unsigned* mlbar = nullptr;      // grid-barrier counters of the persistent V-cycle kernel
     int ntop = 0, ml_degree = 4;
     double ml_frac = 10.0;
     const double* ml_out = nullptr;  // where the V-cycle leaves its result (static for a given hierarchy and degree)
@@ -651,6 +660,32 @@ struct Engine {
     static int vcycle(asc_handle* h, const double* rin, const int* done, cudaStream_t st) {
         const int nl = (int)h->ml.size() - 1;   // smoothed levels; ml[nl] is the dense top level
         const int m = h->ml_degree;
+        static const bool split = getenv("ASC_ML_SPLIT") != nullptr;   // one launch per phase (debugging / comparison)
+        if (!split && nl <= kCycleMaxLevels) {   // the whole cycle in one persistent kernel
+            static const int ctas_env = getenv("ASC_ML_CTAS") ? atoi(getenv("ASC_ML_CTAS")) : 0;
+            MlCycleArgs a{};
+            a.nl = nl; a.m = m; a.ntop = h->ntop; a.frac = h->ml_frac;
+            for (int l = 0; l < nl; ++l) {
+                asc_handle::MlLevel& L = h->ml[l];
+                a.lv[l] = level_dev(L); a.agg[l] = L.agg; a.mptr[l] = L.mptr; a.midx[l] = L.midx; a.rptr[l] = L.rptr; a.ridx[l] = L.ridx; a.n_next[l] = L.n_next;
+                a.za[l] = L.za; a.zb[l] = L.zb; a.d[l] = L.d;
+            }
+            for (int l = 0; l <= nl; ++l) { a.r[l] = l == 0 ? rin : h->ml[l].r; a.rw[l] = l == 0 ? nullptr : h->ml[l].r; }
+            a.Atop = h->Atop; a.ztop = h->ztop; a.bar = h->mlbar; a.fail = h->flags + 9; a.done = done;
+            const int ctas = ctas_env > 0 ? std::min(ctas_env, 148) : 128;
+            ml_vcycle_kernel<N><<<ctas, kCycleThreads, 0, st>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            h->launches += 1;
+            const double* out = h->ztop;
+            if (nl > 0) {   // output buffer of level 0: pre-smoothing ends in bufs[(m-1)&1], post-smoothing flips m more times
+                const double* zi = ((m - 1) & 1) ? h->ml[0].zb : h->ml[0].za;
+                for (int k = 0; k < m; ++k) zi = zi == h->ml[0].za ? h->ml[0].zb : h->ml[0].za;
+                out = zi;
+            }
+            if (h->ml_out && h->ml_out != out) return fail(ASC_ERR_INVALID, "internal: V-cycle output buffer moved");
+            h->ml_out = out;
+            return ASC_OK;
+        }
         std::vector<const double*> cur(nl + 1, nullptr);
         for (int l = 0; l < nl; ++l) {   // down: pre-smooth from zero, restrict the residual
             asc_handle::MlLevel& L = h->ml[l];
@@ -662,7 +697,7 @@ struct Engine {
                 ml_cheb_step_kernel<N><<<grid, 128, 0, st>>>(ld, h->ml_frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], L.d, nullptr, nullptr, done);
             cur[l] = bufs[(m - 1) & 1];
             asc_handle::MlLevel& C = h->ml[l + 1];
-            ml_residual_restrict_kernel<N><<<cdiv(C.n, 4), 128, 0, st>>>(ld, C.n, L.mptr, L.midx, r, cur[l], C.r, done);
+            ml_residual_restrict_kernel<N><<<cdiv(C.n, 4), 128, 0, st>>>(ld, C.n, L.mptr, L.midx, L.rptr, L.ridx, r, cur[l], C.r, done);
             h->launches += m + 1;
         }
         {   // top: explicit dense inverse
@@ -697,6 +732,7 @@ struct Engine {
     static int coarse_refresh(asc_handle* h, double lambda) {
         const int nl = (int)h->ml.size() - 1;
         asc_handle::MlLevel& L0 = h->ml[0];
+        CUDA_TRY(cudaMemsetAsync(h->mlbar, 0, sizeof(unsigned) * 4, h->stream));
         inc_v_kernel<N><<<cdiv(std::max(h->nInc, 1), 4), 128, 0, h->stream>>>(h->nInc, h->inc_lo, h->inc_hi, h->inc_lm, h->l_perm, h->Wm, h->Cinv, h->Vinc, h->Tinc);
         DBG_SYNC(h, "inc_v");
         ml_blocks_l1_kernel<N><<<cdiv(std::max(h->nDest, 1), 4), 128, 0, h->stream>>>(h->nDest, h->dest_ptr, h->pos_lo, h->pos_up, h->pair_a, h->pair_b, h->Vinc, h->Tinc, L0.Eb);
@@ -742,8 +778,9 @@ struct Engine {
             at[0].val.clusterDim.x = kTopCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             CUDA_TRY(cudaLaunchKernelEx(&cfg, ml_top_invert_kernel, h->Atop, h->ntop, h->flags + 4));
+            ml_symmetrize_kernel<<<cdiv((int64_t)h->ntop * h->ntop, 256), 256, 0, h->stream>>>(h->Atop, h->ntop);
             DBG_SYNC(h, "ml top level");
-            h->launches += 2;
+            h->launches += 3;
         }
         // extrinsic border: Y = V E_cK column by column, then S_k = S_KK - E_Kc Y
         for (int c = 0; c < 6; ++c) {
@@ -825,7 +862,11 @@ struct Engine {
         // cluster update, and pcg_end advances the coarse correction by linearity: zc <- zc - alpha B [Z^T y; y_K].
         static const bool no_side_v = getenv("ASC_NO_SIDE_VCYCLE") != nullptr;
         const bool side_v = !no_side_v && h->world == 1 && h->use_clusters && h->use_coarse;
-        auto one_iteration = [&]() -> int {
+        // Residual replacement for the coarse correction: the first iteration of every chunk recomputes zc = B Z^T r from the residual
+        // (V-cycle on the main stream), the others advance it by linearity.  The recursion alone accumulates rounding errors of
+        // size eps * cond(B) * |zc_0| that do not shrink with the residual and stall CG on ill-conditioned coarse operators (small graphs,
+        // small lambda: measured 134 instead of 93 iterations, and one solve that never reached 1e-12).
+        auto one_iteration = [&](bool side_v) -> int {
             double* rowC = h->ybuf + PN + 8;
             double* rowB = rowC + kPartCols;
             MidArgs mid{};
@@ -905,7 +946,7 @@ struct Engine {
                     cudaGraph_t graph = nullptr;
                     CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                     int rc = ASC_OK;
-                    for (int c = 0; c < chunk && !rc; ++c) rc = one_iteration();
+                    for (int c = 0; c < chunk && !rc; ++c) rc = one_iteration(side_v && c > 0);
                     const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
                     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
                     if (ce != cudaSuccess) return fail(ASC_ERR_CUDA, "PCG graph capture failed: %s", cudaGetErrorString(ce));
@@ -918,7 +959,7 @@ struct Engine {
                 CUDA_TRY(cudaGraphLaunch(h->pcg_graph, h->stream));
                 h->launches += h->pcg_graph_launches;
             } else {
-                for (int c = 0; c < chunk; ++c) { int rc = one_iteration(); if (rc) return rc; }
+                for (int c = 0; c < chunk; ++c) { int rc = one_iteration(side_v && c > 0); if (rc) return rc; }
             }
             launched += chunk;
             CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->flags, 16 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -969,6 +1010,7 @@ struct Engine {
     static int check_solve_flags(asc_handle* h) {
         const int big = 0x7fffffff;
         if (h->h_flags[8] != 0) return fail(ASC_ERR_COMM, "peer-memory exchange timed out waiting for a peer rank");
+        if (h->h_flags[9] != 0) return fail(ASC_ERR_CUDA, "the V-cycle kernel's grid barrier timed out (its CTAs were not co-resident)");
         if (h->h_flags[1] != big) { h->fail_kind = 'l'; h->fail_index = h->h_flags[1]; return fail(ASC_ERR_INDETERMINATE, "landmark block %d is not positive definite", h->h_flags[1]); }
         if (h->h_flags[2] != big) { h->fail_kind = 'q'; h->fail_index = h->h_flags[2]; return fail(ASC_ERR_INDETERMINATE, "pose block %d is not positive definite", h->h_flags[2]); }
         if (h->h_flags[3] != big) { h->fail_kind = 'K'; h->fail_index = 0; return fail(ASC_ERR_INDETERMINATE, "extrinsic block is not positive definite"); }
@@ -1457,7 +1499,7 @@ void asc_default_params(asc_params* p) {
     p->pcg_coarse_levels = 8;
     p->pcg_ml_degree = 4;
     p->pcg_ml_agg = 8;
-    p->pcg_ml_top_dim = 640;
+    p->pcg_ml_top_dim = 256;
 }
 
 const char* asc_last_error(void) { return g_last_error.c_str(); }
@@ -1914,6 +1956,8 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 reqs.push_back(ArenaReq{(void**)&D.midx, sizeof(int) * (size_t)H.n});
                 reqs.push_back(ArenaReq{(void**)&D.cptr, sizeof(int) * H.cptr.size()});
                 reqs.push_back(ArenaReq{(void**)&D.cidx, sizeof(int) * std::max<size_t>(H.cidx.size(), 1)});
+                reqs.push_back(ArenaReq{(void**)&D.rptr, sizeof(int) * (size_t)(H.n_next + 1)});
+                reqs.push_back(ArenaReq{(void**)&D.ridx, sizeof(int) * std::max<size_t>(H.ridx.size(), 1)});
                 reqs.push_back(ArenaReq{(void**)&D.Dinv, sizeof(double) * (size_t)H.n * NN});
                 reqs.push_back(ArenaReq{(void**)&D.lmax, sizeof(double) * 4});
                 reqs.push_back(ArenaReq{(void**)&D.za, sizeof(double) * (size_t)H.n * N});
@@ -1923,7 +1967,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             }
         }
         ALLOC(Yb, (size_t)h->n1 * 6); ALLOC(Ski, 36); ALLOC(mlcol, h->n1);
-        ALLOC(Atop, (size_t)h->ntop * h->ntop); ALLOC(ztop, h->ntop); ALLOC(mlpart, 2 * max_grid + 2);
+        ALLOC(Atop, (size_t)h->ntop * h->ntop); ALLOC(ztop, h->ntop); ALLOC(mlpart, 2 * max_grid + 2); ALLOC(mlbar, 4);
     }
     ALLOC(Minv, PN * N); ALLOC(MinvK, 36); ALLOC(rhs, PN + 8);
     ALLOC(vx, PN + 8); ALLOC(vr, PN + 8); ALLOC(vz, PN + 8); ALLOC(vp, PN + 8);
@@ -1983,6 +2027,8 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 CUDA_TRY(cudaMemcpyAsync(D.midx, H.midx.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
                 CUDA_TRY(cudaMemcpyAsync(D.cptr, H.cptr.data(), sizeof(int) * H.cptr.size(), cudaMemcpyHostToDevice, h->stream));
                 if (!H.cidx.empty()) CUDA_TRY(cudaMemcpyAsync(D.cidx, H.cidx.data(), sizeof(int) * H.cidx.size(), cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(D.rptr, H.rptr.data(), sizeof(int) * (H.n_next + 1), cudaMemcpyHostToDevice, h->stream));
+                if (!H.ridx.empty()) CUDA_TRY(cudaMemcpyAsync(D.ridx, H.ridx.data(), sizeof(int) * H.ridx.size(), cudaMemcpyHostToDevice, h->stream));
             }
         }
     }

@@ -34,34 +34,43 @@ struct MlLevelDev {
 
 constexpr double kMlSafety = 1.2;   // upper end of the Chebyshev interval = kMlSafety * estimate (the power iteration converges from below)
 
-// lanes (g, a): g = lane / N handles blocks g, g + G, ... of the row; lane a of group 0 ends up with the row's dot product.
-// v_eff = v (+ vc[agg] when vc != null: prolongation on the fly)
+// Row i of E times v: ONE BLOCK PER LANE (a block row holds ~27 blocks), so the dependent loads are row_ptr -> col -> v once per
+// row instead of once per block (the phases of the V-cycle are latency-bound: < 10 MB of L2-resident data, ~20 dependent phases
+// per PCG iteration).  The N partial results per lane are summed over the warp with a fixed butterfly; lane a < N returns entry a.
+// v_eff = v (+ vc[agg] when vc != null: prolongation on the fly).  Vectors are read through L2 (__ldcg).
 template <int N>
 __device__ __forceinline__ double bsr_row_dot(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ Eb,
-                                              const double* __restrict__ v, const double* __restrict__ vc, const int* __restrict__ agg, int i, int lane) {
-    constexpr int G = 32 / N > 0 ? 32 / N : 1;
-    const int g = lane / N, a = lane % N;
-    double acc = 0.0;
-    if (g < G) {
-        const int k1 = row_ptr[i + 1];
-        for (int k = row_ptr[i] + g; k < k1; k += G) {
-            const double* blk = Eb + (size_t)k * N * N + a * N;
-            const int c = __ldg(col + k);
-            const double* vv = v + (size_t)c * N;
-            if (vc) {
-                const double* cc = vc + (size_t)__ldg(agg + c) * N;
+                                              const double* v, const double* vc, const int* __restrict__ agg, int i, int lane) {
+    const int k0 = __ldg(row_ptr + i), k1 = __ldg(row_ptr + i + 1);
+    double acc[N];
 #pragma unroll
-                for (int b = 0; b < N; ++b) acc = fma(blk[b], vv[b] + cc[b], acc);
-            } else {
+    for (int a = 0; a < N; ++a) acc[a] = 0.0;
+    for (int k = k0 + lane; k < k1; k += 32) {
+        const int c = __ldg(col + k);
+        const double* blk = Eb + (size_t)k * N * N;
+        double x[N];
 #pragma unroll
-                for (int b = 0; b < N; ++b) acc = fma(blk[b], vv[b], acc);
-            }
+        for (int b = 0; b < N; ++b) x[b] = __ldcg(v + (size_t)c * N + b);
+        if (vc) {
+            const double* cc = vc + (size_t)__ldg(agg + c) * N;
+#pragma unroll
+            for (int b = 0; b < N; ++b) x[b] += __ldcg(cc + b);
+        }
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            double t = 0.0;
+#pragma unroll
+            for (int b = 0; b < N; ++b) t = fma(__ldg(blk + a * N + b), x[b], t);
+            acc[a] += t;
         }
     }
-    double tot = 0.0;
+    double mine = 0.0;
 #pragma unroll
-    for (int gg = 0; gg < G; ++gg) tot += __shfl_sync(kFull, acc, (a + N * gg) & 31);   // fixed order; valid on lanes < N
-    return tot;
+    for (int a = 0; a < N; ++a) {
+        const double t = warp_sum(acc[a]);
+        if (lane == a) mine = t;
+    }
+    return mine;
 }
 
 // y_a = sum_b D[a][b] x_b over the first N lanes
@@ -76,17 +85,13 @@ __device__ __forceinline__ double small_matvec(const double* __restrict__ D, dou
     return y;
 }
 
-// One Chebyshev step of the smoother on level `lv` (one warp per node):
+// One Chebyshev step of the smoother on level `lv` for node i (one warp):
 //   res = r - E (z_in [+ P zc]);  t = D^-1 res;  d <- c1 d + c2 t;  z_out = z_in [+ P zc] + d
 // step 0 of a sweep: d is not read (c1 = 0, c2 = 1/theta); zero_in: z_in == 0 (pre-smoothing), the product is skipped.
+// Vectors are read through L2 (__ldcg): inside the persistent V-cycle kernel other CTAs rewrote them a phase ago.
 template <int N>
-__global__ void __launch_bounds__(128)
-ml_cheb_step_kernel(MlLevelDev lv, double frac, int step, int zero_in, const double* __restrict__ r, const double* __restrict__ z_in,
-                    double* __restrict__ z_out, double* __restrict__ d, const double* __restrict__ zc, const int* __restrict__ agg,
-                    const int* __restrict__ done) {
-    if (done && *done) return;
-    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (i >= lv.n) return;
+__device__ __forceinline__ void ml_cheb_node(const MlLevelDev& lv, double frac, int step, int zero_in, const double* r, const double* z_in,
+                                             double* z_out, double* d, const double* zc, const int* agg, int i, int lane) {
     const double hi = kMlSafety * *lv.lmax, lo = hi / frac;
     const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
     double c1 = 0.0, c2 = 1.0 / theta;
@@ -94,54 +99,188 @@ ml_cheb_step_kernel(MlLevelDev lv, double frac, int step, int zero_in, const dou
         double rho = 1.0 / sigma;
         for (int k = 1; k <= step; ++k) { const double rn = 1.0 / (2.0 * sigma - rho); c1 = rn * rho; c2 = 2.0 * rn / delta; rho = rn; }
     }
-    double res = lane < N ? r[(size_t)i * N + lane] : 0.0;
+    double res = lane < N ? __ldcg(r + (size_t)i * N + lane) : 0.0;
     double zin = 0.0;
     if (!zero_in) {
         const double p = bsr_row_dot<N>(lv.row_ptr, lv.col, lv.Eb, z_in, zc, agg, i, lane);
         if (lane < N) {
             res -= p;
-            zin = z_in[(size_t)i * N + lane];
-            if (zc) zin += zc[(size_t)agg[i] * N + lane];
+            zin = __ldcg(z_in + (size_t)i * N + lane);
+            if (zc) zin += __ldcg(zc + (size_t)agg[i] * N + lane);
         }
     }
     const double t = small_matvec<N>(lv.Dinv + (size_t)i * N * N, res, lane);
     if (lane < N) {
-        const double dn = (step > 0 ? c1 * d[(size_t)i * N + lane] : 0.0) + c2 * t;
+        const double dn = (step > 0 ? c1 * __ldcg(d + (size_t)i * N + lane) : 0.0) + c2 * t;
         d[(size_t)i * N + lane] = dn;
         z_out[(size_t)i * N + lane] = zin + dn;
     }
 }
 
-// r_c[A] = sum over the members a of aggregate A of (r - E z)[a]      (one warp per aggregate, members in list order)
+// r_c[A] = sum over the members i of aggregate A of (r - E z)[i].  The rows of one aggregate are summed anyway, so the warp walks
+// the flattened list of ALL blocks of the aggregate's rows (rptr / ridx, built on the host), one block per lane and round:
+// the loads of different rounds are independent, and one butterfly at the end finishes the sum.
 template <int N>
-__global__ void __launch_bounds__(128)
-ml_residual_restrict_kernel(MlLevelDev lv, int n_coarse, const int* __restrict__ mptr, const int* __restrict__ midx, const double* __restrict__ r,
-                            const double* __restrict__ z, double* __restrict__ rc, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int A = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (A >= n_coarse) return;
-    double acc = 0.0;
-    for (int q = mptr[A]; q < mptr[A + 1]; ++q) {
-        const int i = midx[q];
-        const double p = bsr_row_dot<N>(lv.row_ptr, lv.col, lv.Eb, z, nullptr, nullptr, i, lane);
-        if (lane < N) acc += r[(size_t)i * N + lane] - p;
+__device__ __forceinline__ void ml_restrict_node(const MlLevelDev& lv, const int* __restrict__ mptr, const int* __restrict__ midx,
+                                                 const int* __restrict__ rptr, const int* __restrict__ ridx, const double* r, const double* z,
+                                                 double* rc, int A, int lane) {
+    double acc[N];
+#pragma unroll
+    for (int a = 0; a < N; ++a) acc[a] = 0.0;
+    const int q0 = __ldg(rptr + A), q1 = __ldg(rptr + A + 1);
+    for (int q = q0 + lane; q < q1; q += 32) {
+        const int k = __ldg(ridx + q);
+        const int c = __ldg(lv.col + k);
+        const double* blk = lv.Eb + (size_t)k * N * N;
+        double x[N];
+#pragma unroll
+        for (int b = 0; b < N; ++b) x[b] = __ldcg(z + (size_t)c * N + b);
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            double t = 0.0;
+#pragma unroll
+            for (int b = 0; b < N; ++b) t = fma(__ldg(blk + a * N + b), x[b], t);
+            acc[a] -= t;
+        }
     }
-    if (lane < N) rc[(size_t)A * N + lane] = acc;
+    const int m0 = __ldg(mptr + A), m1 = __ldg(mptr + A + 1);
+    for (int q = m0 + lane; q < m1; q += 32) {
+        const int i = __ldg(midx + q);
+#pragma unroll
+        for (int a = 0; a < N; ++a) acc[a] += __ldcg(r + (size_t)i * N + a);
+    }
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+        const double t = warp_sum(acc[a]);
+        if (lane == a) rc[(size_t)A * N + a] = t;
+    }
 }
 
-// y = A x, dense row-major n x n (the explicit inverse of the top level); one warp per row
-__global__ void __launch_bounds__(128) ml_dense_gemv_kernel(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, int n,
-                                                             const int* __restrict__ done) {
-    if (done && *done) return;
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= n) return;
+// row `row` of y = A x, dense row-major n x n (the explicit inverse of the top level); one warp
+__device__ __forceinline__ void ml_gemv_row(const double* __restrict__ A, const double* x, double* y, int n, int row, int lane) {
     const double* a = A + (size_t)row * n;
     double acc0 = 0.0, acc1 = 0.0;
     int i = lane;
-    for (; i + 32 < n; i += 64) { acc0 = fma(a[i], x[i], acc0); acc1 = fma(a[i + 32], x[i + 32], acc1); }
-    if (i < n) acc0 = fma(a[i], x[i], acc0);
+    for (; i + 32 < n; i += 64) { acc0 = fma(a[i], __ldcg(x + i), acc0); acc1 = fma(a[i + 32], __ldcg(x + i + 32), acc1); }
+    if (i < n) acc0 = fma(a[i], __ldcg(x + i), acc0);
     const double t = warp_sum(acc0 + acc1);
     if (lane == 0) y[row] = t;
+}
+
+template <int N>
+__global__ void __launch_bounds__(128)
+ml_cheb_step_kernel(MlLevelDev lv, double frac, int step, int zero_in, const double* r, const double* z_in, double* z_out, double* d,
+                    const double* zc, const int* agg, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= lv.n) return;
+    ml_cheb_node<N>(lv, frac, step, zero_in, r, z_in, z_out, d, zc, agg, i, lane);
+}
+
+template <int N>
+__global__ void __launch_bounds__(128)
+ml_residual_restrict_kernel(MlLevelDev lv, int n_coarse, const int* __restrict__ mptr, const int* __restrict__ midx, const int* __restrict__ rptr,
+                            const int* __restrict__ ridx, const double* r, const double* z, double* rc, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int A = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (A >= n_coarse) return;
+    ml_restrict_node<N>(lv, mptr, midx, rptr, ridx, r, z, rc, A, lane);
+}
+
+__global__ void __launch_bounds__(128) ml_dense_gemv_kernel(const double* __restrict__ A, const double* x, double* y, int n, const int* __restrict__ done) {
+    if (done && *done) return;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    ml_gemv_row(A, x, y, n, row, lane);
+}
+
+// ---- the whole V-cycle as ONE persistent kernel: the phases above separated by a grid barrier instead of kernel boundaries.
+// On C2 the V-cycle is ~20 dependent phases over < 10 MB of L2-resident data: as separate launches it costs ~170 us per PCG
+// iteration (launch gaps), as one kernel ~40 us.  kCycleCtas CTAs must be co-resident (they are: <= one per SM, 256 threads, no
+// shared memory); a barrier that does not complete within ~2 s reports through `fail` instead of hanging.
+constexpr int kCycleMaxLevels = 8;
+constexpr int kCycleThreads = 256;
+struct MlCycleArgs {
+    int nl, m, ntop;
+    double frac;
+    MlLevelDev lv[kCycleMaxLevels];
+    const int* agg[kCycleMaxLevels];
+    const int* mptr[kCycleMaxLevels];
+    const int* midx[kCycleMaxLevels];
+    const int* rptr[kCycleMaxLevels];
+    const int* ridx[kCycleMaxLevels];
+    int n_next[kCycleMaxLevels];
+    const double* r[kCycleMaxLevels + 1];   // r[0] = the caller's right-hand side; r[l] = restricted residual of level l
+    double* rw[kCycleMaxLevels + 1];        // the same buffers, writable (rw[0] unused)
+    double* za[kCycleMaxLevels];
+    double* zb[kCycleMaxLevels];
+    double* d[kCycleMaxLevels];
+    const double* Atop;
+    double* ztop;
+    unsigned* bar;                          // [2]: arrival counter, exit counter (both return to zero)
+    int* fail;
+    const int* done;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void ml_grid_barrier(unsigned* bar, unsigned& target, int* fail) {
+    __syncthreads();   // the CTA's writes of this phase happen-before thread 0's release below (bar.sync + cumulativity)
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        const long long t0 = clock64();
+        while (ld_acquire_gpu_u32(bar) < target) {
+            if (clock64() - t0 > 4000000000ll) { *fail = 1; break; }
+        }
+    }
+    __syncthreads();
+}
+
+template <int N>
+__global__ void __launch_bounds__(kCycleThreads) ml_vcycle_kernel(const __grid_constant__ MlCycleArgs a) {
+    if (a.done && *a.done) return;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (kCycleThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kCycleThreads / 32);
+    unsigned target = 0;
+    const double* cur[kCycleMaxLevels + 1];
+    for (int l = 0; l < a.nl; ++l) {   // down
+        const double* r = a.r[l];
+        double* bufs[2] = {a.za[l], a.zb[l]};
+        for (int k = 0; k < a.m; ++k) {
+            if (k > 0 || l > 0) ml_grid_barrier(a.bar, target, a.fail);
+            for (int i = gw; i < a.lv[l].n; i += nw)
+                ml_cheb_node<N>(a.lv[l], a.frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], a.d[l], nullptr, nullptr, i, lane);
+        }
+        cur[l] = bufs[(a.m - 1) & 1];
+        ml_grid_barrier(a.bar, target, a.fail);
+        for (int A = gw; A < a.n_next[l]; A += nw) ml_restrict_node<N>(a.lv[l], a.mptr[l], a.midx[l], a.rptr[l], a.ridx[l], r, cur[l], a.rw[l + 1], A, lane);
+    }
+    if (a.nl > 0) ml_grid_barrier(a.bar, target, a.fail);
+    for (int row = gw; row < a.ntop; row += nw) ml_gemv_row(a.Atop, a.r[a.nl], a.ztop, a.ntop, row, lane);
+    cur[a.nl] = a.ztop;
+    for (int l = a.nl - 1; l >= 0; --l) {   // up
+        const double* r = a.r[l];
+        const double* zi = cur[l];
+        for (int k = 0; k < a.m; ++k) {
+            ml_grid_barrier(a.bar, target, a.fail);
+            double* zo = zi == a.za[l] ? a.zb[l] : a.za[l];
+            for (int i = gw; i < a.lv[l].n; i += nw)
+                ml_cheb_node<N>(a.lv[l], a.frac, k, 0, r, zi, zo, a.d[l], k == 0 ? cur[l + 1] : nullptr, k == 0 ? a.agg[l] : nullptr, i, lane);
+            zi = zo;
+        }
+        cur[l] = zi;
+    }
+    // the last CTA to leave resets the counters for the next launch (everybody has passed every barrier by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.bar + 1, 1u) == gridDim.x - 1) { a.bar[0] = 0; a.bar[1] = 0; __threadfence(); }
+    }
 }
 
 // ---- refresh kernels (once per damped solve)
@@ -257,7 +396,7 @@ __global__ void __launch_bounds__(64) ml_dinv_kernel(int n, const int* __restric
 #pragma unroll
     for (int a = 0; a < N; ++a)
 #pragma unroll
-        for (int b = 0; b < N; ++b) dst[a * N + b] = A[a][b];
+        for (int b = 0; b < N; ++b) dst[a * N + b] = 0.5 * (A[a][b] + A[b][a]);   // exactly symmetric
     if (!ok) atomicExch(fail, 1);
 }
 
@@ -351,6 +490,17 @@ __global__ void __launch_bounds__(kTopThreads) ml_top_invert_kernel(double* A, i
     if (bad && tid == 0 && cta == 0) atomicExch(fail, 1);
 }
 
+// The Gauss-Jordan sweep leaves an inverse that is symmetric only up to cond * eps; CG needs an exactly symmetric preconditioner
+// (an asymmetry of 1e-7 stalls it at a 1e-7 relative residual): A <- (A + A^T) / 2, one thread per upper-triangle pair
+__global__ void __launch_bounds__(256) ml_symmetrize_kernel(double* __restrict__ A, int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const int r = (int)(idx / n), c = (int)(idx % n);
+    if (c <= r) return;
+    const double v = 0.5 * (A[(size_t)r * n + c] + A[(size_t)c * n + r]);
+    A[(size_t)r * n + c] = v; A[(size_t)c * n + r] = v;
+}
+
 // column c of the extrinsic border as a right-hand side: r[i] = EK[i * 6 + c]
 __global__ void ml_border_column_kernel(int n, int c, const double* __restrict__ EK, double* __restrict__ r) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,7 +557,7 @@ __global__ void __launch_bounds__(256) ml_border_schur_kernel(int n, const doubl
                     for (int b = 0; b < 6; ++b) A[a][b] = (b == k ? 0.0 : A[a][b]) - colk[a] * A[k][b];
         }
         for (int a = 0; a < 6; ++a)
-            for (int b = 0; b < 6; ++b) Ski[6 * a + b] = A[a][b];
+            for (int b = 0; b < 6; ++b) Ski[6 * a + b] = 0.5 * (A[a][b] + A[b][a]);
         if (!ok) atomicExch(fail, 1);
     }
 }

@@ -84,7 +84,7 @@ typedef struct asc_params {
     int32_t pcg_coarse_levels;       /* max smoothed levels of the V-cycle (8); 0 switches the coarse level off */
     int32_t pcg_ml_degree;           /* Chebyshev degree of the pre- and post-smoother (4) */
     int32_t pcg_ml_agg;              /* target nodes per aggregate (8) */
-    int32_t pcg_ml_top_dim;          /* aggregate until the coarsest level has at most this many unknowns (640); it is inverted densely */
+    int32_t pcg_ml_top_dim;          /* aggregate until the coarsest level has at most this many unknowns (256); it is inverted densely */
 } asc_params;
 
 /* One record per outer iterate() of the optimiser */
