@@ -672,9 +672,28 @@ struct Engine {
             }
             for (int l = 0; l <= nl; ++l) { a.r[l] = l == 0 ? rin : h->ml[l].r; a.rw[l] = l == 0 ? nullptr : h->ml[l].r; }
             a.Atop = h->Atop; a.ztop = h->ztop; a.bar = h->mlbar; a.fail = h->flags + 9; a.done = done;
-            const int ctas = ctas_env > 0 ? std::min(ctas_env, 148) : 128;
-            ml_vcycle_kernel<N><<<ctas, kCycleThreads, 0, st>>>(a);
-            CUDA_TRY(cudaGetLastError());
+            static const int dbg_env = getenv("ASC_ML_DBG") ? atoi(getenv("ASC_ML_DBG")) : 2;
+            a.dbg = dbg_env;
+            a.first_cluster_level = nl + 1;
+            for (int l = nl; l >= 0; --l) {
+                const int nodes = l == nl ? h->ntop / N : h->ml[l].n;
+                if (nodes <= kClusterLevelNodes) a.first_cluster_level = l; else break;
+            }
+            // Measured on C2 (scripts/vc_probe.py, 17 phases): all phases grid-wide 183 us, coarse levels on cluster 0 only 228 us (the
+            // hardware cluster barrier of cooperative groups carries a GPU-scope fence and costs as much as the grid barrier, and eight
+            // CTAs are slower than 128 on the 146-node level), one launch per phase 190 us.  So cluster mode is opt-in.
+            static const bool cluster_levels = getenv("ASC_ML_CLUSTER") != nullptr;
+            if (!cluster_levels) a.first_cluster_level = nl + 1;
+            int ctas = ctas_env > 0 ? std::min(ctas_env, 144) : 128;
+            ctas = std::max(kCycleCluster, ctas / kCycleCluster * kCycleCluster);
+            if (a.first_cluster_level == 0) ctas = kCycleCluster;   // the whole hierarchy fits one cluster
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(kCycleThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = kCycleCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, ml_vcycle_kernel<N>, a));
             h->launches += 1;
             const double* out = h->ztop;
             if (nl > 0) {   // output buffer of level 0: pre-smoothing ends in bufs[(m-1)&1], post-smoothing flips m more times
@@ -883,9 +902,7 @@ struct Engine {
                 coarse_restrict_y_kernel<<<cdiv(h->nC, 4), 128, 0, h->stream2>>>(h->nC, N, h->cl_ptr, h->ybuf, h->ryc, h->flags);
                 CUDA_TRY(cudaGetLastError());
                 h->launches += 1;
-                prof_start(h, 8);
                 rc = vcycle(h, h->ryc, h->flags, h->stream2);
-                prof_stop(h, 8);
                 if (rc) return rc;
                 CUDA_TRY(cudaEventRecord(h->ev_q, h->stream2));
             }
@@ -918,7 +935,9 @@ struct Engine {
                     CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_q, 0));
                     end.border = border_args(h, h->ybuf + PN, h->scal);
                 } else if (h->use_coarse) {   // zc = B rc recomputed from the new residual
+                    prof_start(h, 8);
                     int rc3 = vcycle(h, h->rc, h->flags, h->stream);
+                    prof_stop(h, 8);
                     if (rc3) return rc3;
                     end.border = border_args(h, h->rc + h->n1, nullptr);
                 }

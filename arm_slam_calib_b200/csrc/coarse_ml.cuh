@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128) ml_dense_gemv_kernel(const double* __rest
 constexpr int kCycleMaxLevels = 8;
 constexpr int kCycleThreads = 256;
 struct MlCycleArgs {
-    int nl, m, ntop;
+    int nl, m, ntop, first_cluster_level, dbg;
     double frac;
     MlLevelDev lv[kCycleMaxLevels];
     const int* agg[kCycleMaxLevels];
@@ -228,49 +228,92 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
     return v;
 }
 
-__device__ __forceinline__ void ml_grid_barrier(unsigned* bar, unsigned& target, int* fail) {
+__device__ __forceinline__ void ml_grid_barrier(unsigned* bar, unsigned& target, int* fail, int variant = 0) {
     __syncthreads();   // the CTA's writes of this phase happen-before thread 0's release below (bar.sync + cumulativity)
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-        const long long t0 = clock64();
-        while (ld_acquire_gpu_u32(bar) < target) {
-            if (clock64() - t0 > 4000000000ll) { *fail = 1; break; }
+        if (variant == 0) {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_u32(bar) < target) {
+                if (clock64() - t0 > 4000000000ll) { *fail = 1; break; }
+            }
+        } else {   // one fence on each side, plain polling in between (an acquire load invalidates L1 on EVERY poll: CCTL.IVALL)
+            __threadfence();
+            atomicAdd(bar, 1u);
+            const long long t0 = clock64();
+            while (*((volatile unsigned*)bar) < target) {
+                if (clock64() - t0 > 4000000000ll) { *fail = 1; break; }
+            }
+            __threadfence();
         }
     }
     __syncthreads();
 }
 
+// Phases of the FINE levels span the whole grid and are separated by the grid barrier (~8 us per phase on a B200: three dependent L2
+// round trips plus the barrier).  Levels with at most kClusterLevelNodes nodes (and everything below them, top level included) are
+// handled by thread-block cluster 0 alone, with the hardware cluster barrier between phases (~2.5 us per phase); the other
+// clusters wait at the next grid barrier.  a.first_cluster_level = first such level (nl + 1: none).
+constexpr int kCycleCluster = 8;
+constexpr int kClusterLevelNodes = 640;
+
 template <int N>
 __global__ void __launch_bounds__(kCycleThreads) ml_vcycle_kernel(const __grid_constant__ MlCycleArgs a) {
     if (a.done && *a.done) return;
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * (kCycleThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kCycleThreads / 32);
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, wpc = kCycleThreads / 32;
+    const int gw = blockIdx.x * wpc + (threadIdx.x >> 5), ngw = gridDim.x * wpc;
+    const bool c0 = blockIdx.x < kCycleCluster;                                   // member of cluster 0
+    const int cw = (blockIdx.x % kCycleCluster) * wpc + (threadIdx.x >> 5), ncw = kCycleCluster * wpc;
+    const int fc = a.first_cluster_level;
     unsigned target = 0;
     const double* cur[kCycleMaxLevels + 1];
+    // which output buffer every level ends its sweeps in is static: every CTA tracks it, whether or not it does the work
     for (int l = 0; l < a.nl; ++l) {   // down
+        const bool cl = l >= fc;
         const double* r = a.r[l];
         double* bufs[2] = {a.za[l], a.zb[l]};
+        const int w0 = cl ? cw : gw, nw = cl ? ncw : ngw;
         for (int k = 0; k < a.m; ++k) {
-            if (k > 0 || l > 0) ml_grid_barrier(a.bar, target, a.fail);
-            for (int i = gw; i < a.lv[l].n; i += nw)
-                ml_cheb_node<N>(a.lv[l], a.frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], a.d[l], nullptr, nullptr, i, lane);
+            if (k > 0 || l > 0) {
+                if (!cl || l == fc && k == 0) ml_grid_barrier(a.bar, target, a.fail, a.dbg >> 1);   // (entering cluster mode: the restriction above was a grid phase)
+                else if (c0) cluster.sync();
+            }
+            if ((!cl || c0) && !(a.dbg & 1))
+                for (int i = w0; i < a.lv[l].n; i += nw)
+                    ml_cheb_node<N>(a.lv[l], a.frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], a.d[l], nullptr, nullptr, i, lane);
         }
         cur[l] = bufs[(a.m - 1) & 1];
-        ml_grid_barrier(a.bar, target, a.fail);
-        for (int A = gw; A < a.n_next[l]; A += nw) ml_restrict_node<N>(a.lv[l], a.mptr[l], a.midx[l], a.rptr[l], a.ridx[l], r, cur[l], a.rw[l + 1], A, lane);
+        if (!cl) ml_grid_barrier(a.bar, target, a.fail, a.dbg >> 1);
+        else if (c0) cluster.sync();
+        if ((!cl || c0) && !(a.dbg & 1))
+            for (int A = w0; A < a.n_next[l]; A += nw) ml_restrict_node<N>(a.lv[l], a.mptr[l], a.midx[l], a.rptr[l], a.ridx[l], r, cur[l], a.rw[l + 1], A, lane);
     }
-    if (a.nl > 0) ml_grid_barrier(a.bar, target, a.fail);
-    for (int row = gw; row < a.ntop; row += nw) ml_gemv_row(a.Atop, a.r[a.nl], a.ztop, a.ntop, row, lane);
-    cur[a.nl] = a.ztop;
+    {   // top level
+        const bool cl = a.nl >= fc;
+        if (a.nl > 0) {
+            if (!cl || a.nl == fc) ml_grid_barrier(a.bar, target, a.fail, a.dbg >> 1);
+            else if (c0) cluster.sync();
+        }
+        const int w0 = cl ? cw : gw, nw = cl ? ncw : ngw;
+        if ((!cl || c0) && !(a.dbg & 1))
+            for (int row = w0; row < a.ntop; row += nw) ml_gemv_row(a.Atop, a.r[a.nl], a.ztop, a.ntop, row, lane);
+        cur[a.nl] = a.ztop;
+    }
     for (int l = a.nl - 1; l >= 0; --l) {   // up
+        const bool cl = l >= fc;
         const double* r = a.r[l];
         const double* zi = cur[l];
+        const int w0 = cl ? cw : gw, nw = cl ? ncw : ngw;
         for (int k = 0; k < a.m; ++k) {
-            ml_grid_barrier(a.bar, target, a.fail);
+            if (!cl) ml_grid_barrier(a.bar, target, a.fail, a.dbg >> 1);   // also the hand-over from cluster 0's coarse section
+            else if (c0) cluster.sync();
             double* zo = zi == a.za[l] ? a.zb[l] : a.za[l];
-            for (int i = gw; i < a.lv[l].n; i += nw)
-                ml_cheb_node<N>(a.lv[l], a.frac, k, 0, r, zi, zo, a.d[l], k == 0 ? cur[l + 1] : nullptr, k == 0 ? a.agg[l] : nullptr, i, lane);
+            if ((!cl || c0) && !(a.dbg & 1))
+                for (int i = w0; i < a.lv[l].n; i += nw)
+                    ml_cheb_node<N>(a.lv[l], a.frac, k, 0, r, zi, zo, a.d[l], k == 0 ? cur[l + 1] : nullptr, k == 0 ? a.agg[l] : nullptr, i, lane);
             zi = zo;
         }
         cur[l] = zi;

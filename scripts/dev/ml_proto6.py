@@ -85,11 +85,14 @@ def main():
                 z = z + d; rho = rho_n
             return z
 
-        for m, frac in ((3, 8), (4, 10), (6, 20)):
+        FR = {1: 4, 2: 4, 3: 8, 4: 10, 5: 15, 6: 20, 8: 30}
+        for mm in ((4, 4), (2, 4), (2, 6), (2, 8), (3, 6), (1, 6), (1, 8)):
             def V(li, r):
                 if li == len(levels):
                     return sla.cho_solve(cf, r)
                 E, Dinv, Pm, lmax = levels[li]
+                m = mm[0] if li == 0 else mm[1]
+                frac = FR[m]
                 hi = 1.2 * lmax; lo = hi / frac
                 z = cheb(E, Dinv, r, None, m, lo, hi)
                 z = z + Pm @ V(li + 1, Pm.T @ (r - E @ z))
@@ -104,7 +107,7 @@ def main():
                 zK = Ski @ (r[PN:] - E1K.T @ t)
                 z = t - Y @ zK
                 return M_cl(r) + np.concatenate([Z1 @ z, zK])
-            run("bordered K: gs=%d levels=%d cheb m=%d lo=hi/%d" % (gs, len(levels), m, frac), M)
+            run("bordered K: gs=%d levels=%d cheb m=%s" % (gs, len(levels), mm), M)
 
 
 if __name__ == "__main__":
