@@ -5,7 +5,7 @@ reference's optimiser surface for tests and bench.py; it contains no CPU fallbac
 """
 from ._ctypes_defs import (ASC_BATCH_DOGLEG, ASC_BATCH_LM, ASC_ERR_CUDA, ASC_ERR_INDETERMINATE, ASC_ERR_INVALID, ASC_OK,
                            AscIterLog, AscLinearStats, AscParams, AscSimConfig)
-from .capi import (AscError, BatchOptimizer, IndeterminantLinearSystemException, Problem, default_params, lib,
+from .capi import (AscError, BatchOptimizer, IndeterminantLinearSystemException, Problem, default_params, hostlib, lib,
                    optimization_mode_from_string, shard_by_landmark)
 from .sim import chain_generate, chain_mico, make_sim_problem, with_drift, with_velocity
 

@@ -88,6 +88,28 @@ def lib():
     return _lib
 
 
+_HOST_LIB_PATH = os.path.join(_HERE, "libasc_host.so")
+_hostlib = None
+HOST_SYMBOLS = ("asc_default_params", "asc_last_error", "asc_version", "asc_sim_default_config", "asc_chain_mico", "asc_chain_generate",
+                "asc_sim_create", "asc_sim_destroy", "asc_sim_sizes", "asc_sim_export", "asc_chain_fk", "asc_srand")
+
+
+def hostlib():
+    """libasc_host.so: the generator and the default parameters without any CUDA code (never maps the product library)."""
+    global _hostlib
+    if _hostlib is None:
+        if not os.path.exists(_HOST_LIB_PATH):
+            raise RuntimeError("libasc_host.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(_HOST_LIB_PATH)
+        for name in HOST_SYMBOLS:
+            res, args = SIGNATURES[name]
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _hostlib = L
+    return _hostlib
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
 
@@ -111,7 +133,7 @@ class IndeterminantLinearSystemException(AscError):
 
 def default_params():
     p = D.AscParams()
-    lib().asc_default_params(C.byref(p))
+    hostlib().asc_default_params(C.byref(p))
     return p
 
 

@@ -4,7 +4,8 @@ import ctypes as C
 import numpy as np
 
 from . import _ctypes_defs as D
-from .capi import Problem, _ptr, _vp, lib
+from .capi import Problem, _ptr, _vp
+from .capi import hostlib as lib   # generator calls go to the host-only library
 
 
 def chain_mico():
