@@ -51,6 +51,7 @@ SIGNATURES = {
     "asc_launch_count": (C.c_int64, [_vp]),
     "asc_solver_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "asc_coarse_info": (C.c_int, [_vp, C.POINTER(C.c_int32), _vp, _vp, C.c_int32, C.POINTER(C.c_int32)]),
+    "asc_debug_ml_trace": (C.c_int, [_vp, _vp, C.c_int32]),
     "asc_timer_start": (C.c_int, [_vp]),
     "asc_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "asc_profile_begin": (C.c_int, [_vp, C.c_int32, C.c_int32]),

@@ -136,7 +136,6 @@ struct MlHostLevel {
     std::vector<double> w;                     // static edge weight per block (shared-landmark pair count, summed on coarsening)
     std::vector<int> agg, mptr, midx;          // aggregation to the next level
     std::vector<int> cptr, cidx;               // children of each block of the NEXT level among this level's blocks
-    std::vector<int> rptr, ridx;               // blocks of the rows of each aggregate, flattened (restriction kernel)
     int n_next = 0;
 };
 
@@ -206,12 +205,6 @@ void ml_coarsen_pattern(MlHostLevel& L, MlHostLevel& C) {
     L.midx.assign(L.n, 0);
     std::vector<int> fill(L.mptr.begin(), L.mptr.end() - 1);
     for (int i = 0; i < L.n; ++i) L.midx[fill[L.agg[i]]++] = i;
-    L.rptr.assign(na + 1, 0); L.ridx.clear();
-    for (int a = 0; a < na; ++a) {
-        for (int q = L.mptr[a]; q < L.mptr[a + 1]; ++q)
-            for (int k = L.row_ptr[L.midx[q]]; k < L.row_ptr[L.midx[q] + 1]; ++k) L.ridx.push_back(k);
-        L.rptr[a + 1] = (int)L.ridx.size();
-    }
 }
 
 }  // namespace
@@ -309,17 +302,19 @@ struct asc_handle {
     struct MlLevel {                // one level of the hierarchy; the last one is the dense top level
         int n = 0, nnzb = 0, n_next = 0;
         int *row_ptr = nullptr, *col = nullptr, *diag_pos = nullptr;          // BSR pattern (both triangles)
+        int2* bpos = nullptr;                                                 // where each block's elements live (transposed rows, coarse_ml.cuh)
         int *agg = nullptr, *mptr = nullptr, *midx = nullptr;                 // node -> aggregate; members of each aggregate
         int *cptr = nullptr, *cidx = nullptr;                                 // blocks of THIS level that sum into each block of the next
-        int *rptr = nullptr, *ridx = nullptr;                                 // blocks of the rows of each aggregate (restriction)
         double *Eb = nullptr, *Dinv = nullptr, *lmax = nullptr;
-        double *r = nullptr, *za = nullptr, *zb = nullptr, *d = nullptr;      // V-cycle vectors (r of level 0 is the caller's)
+        double *r = nullptr, *za = nullptr, *zb = nullptr, *d = nullptr, *rs = nullptr;   // V-cycle vectors (r of level 0 is the caller's)
     };
     std::vector<MlLevel> ml;
     double *mlblk = nullptr;        // [Eb of level 0 | EK]: one all-reduce in a multi-GPU run
     double *EK = nullptr, *Yb = nullptr, *Ski = nullptr;   // extrinsic border of level 1, Y = V E_cK, S_k^-1
     double *Atop = nullptr, *ztop = nullptr, *mlpart = nullptr, *mlcol = nullptr;
-    unsigned* mlbar = nullptr;      // grid-barrier counters of the persistent V-cycle kernel
+    unsigned* mlbar = nullptr;      // grid-barrier counters of the persistent V-cycle kernel ([0..1]) and of the top-level inversion ([2..3])
+    double* mlpiv = nullptr;        // pivot-row broadcast buffer of the top-level inversion
+    unsigned long long* ml_trace = nullptr;   // ASC_ML_TRACE: barrier timestamps of the last V-cycle launch (debugging)
     int ntop = 0, ml_degree = 4;
     double ml_frac = 10.0;
     const double* ml_out = nullptr;  // where the V-cycle leaves its result (static for a given hierarchy and degree)
@@ -651,98 +646,40 @@ struct Engine {
     // ---- multilevel coarse solve (coarse_ml.cuh)
     static MlLevelDev level_dev(const asc_handle::MlLevel& L) {
         MlLevelDev d;
-        d.n = L.n; d.row_ptr = L.row_ptr; d.col = L.col; d.Eb = L.Eb; d.Dinv = L.Dinv; d.lmax = L.lmax;
+        d.n = L.n; d.row_ptr = L.row_ptr; d.col = L.col; d.Eb = L.Eb; d.bpos = L.bpos; d.Dinv = L.Dinv; d.lmax = L.lmax;
         return d;
     }
 
-    // t = V rin : one symmetric V-cycle on the cluster part of the coarse operator.  The result is left at h->ml_out (the
-    // buffer sequence is static for a given hierarchy and degree).  Kernels only: capturable, runs on any stream.
+    // t = V rin : one symmetric V-cycle on the cluster part of the coarse operator, ONE persistent kernel (coarse_ml.cuh).  The
+    // result is left at h->ml_out (the buffer sequence is static for a given hierarchy and degree).  Capturable, runs on any stream.
     static int vcycle(asc_handle* h, const double* rin, const int* done, cudaStream_t st) {
         const int nl = (int)h->ml.size() - 1;   // smoothed levels; ml[nl] is the dense top level
         const int m = h->ml_degree;
-        static const bool split = getenv("ASC_ML_SPLIT") != nullptr;   // one launch per phase (debugging / comparison)
-        if (!split && nl <= kCycleMaxLevels) {   // the whole cycle in one persistent kernel
-            static const int ctas_env = getenv("ASC_ML_CTAS") ? atoi(getenv("ASC_ML_CTAS")) : 0;
-            MlCycleArgs a{};
-            a.nl = nl; a.m = m; a.ntop = h->ntop; a.frac = h->ml_frac;
-            for (int l = 0; l < nl; ++l) {
-                asc_handle::MlLevel& L = h->ml[l];
-                a.lv[l] = level_dev(L); a.agg[l] = L.agg; a.mptr[l] = L.mptr; a.midx[l] = L.midx; a.rptr[l] = L.rptr; a.ridx[l] = L.ridx; a.n_next[l] = L.n_next;
-                a.za[l] = L.za; a.zb[l] = L.zb; a.d[l] = L.d;
-            }
-            for (int l = 0; l <= nl; ++l) { a.r[l] = l == 0 ? rin : h->ml[l].r; a.rw[l] = l == 0 ? nullptr : h->ml[l].r; }
-            a.Atop = h->Atop; a.ztop = h->ztop; a.bar = h->mlbar; a.fail = h->flags + 9; a.done = done;
-            static const int dbg_env = getenv("ASC_ML_DBG") ? atoi(getenv("ASC_ML_DBG")) : 2;
-            a.dbg = dbg_env;
-            a.first_cluster_level = nl + 1;
-            for (int l = nl; l >= 0; --l) {
-                const int nodes = l == nl ? h->ntop / N : h->ml[l].n;
-                if (nodes <= kClusterLevelNodes) a.first_cluster_level = l; else break;
-            }
-            // Measured on C2 (scripts/vc_probe.py, 17 phases): all phases grid-wide 183 us, coarse levels on cluster 0 only 228 us (the
-            // hardware cluster barrier of cooperative groups carries a GPU-scope fence and costs as much as the grid barrier, and eight
-            // CTAs are slower than 128 on the 146-node level), one launch per phase 190 us.  So cluster mode is opt-in.
-            static const bool cluster_levels = getenv("ASC_ML_CLUSTER") != nullptr;
-            if (!cluster_levels) a.first_cluster_level = nl + 1;
-            int ctas = ctas_env > 0 ? std::min(ctas_env, 144) : 128;
-            ctas = std::max(kCycleCluster, ctas / kCycleCluster * kCycleCluster);
-            if (a.first_cluster_level == 0) ctas = kCycleCluster;   // the whole hierarchy fits one cluster
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(kCycleThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = kCycleCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, ml_vcycle_kernel<N>, a));
-            h->launches += 1;
-            const double* out = h->ztop;
-            if (nl > 0) {   // output buffer of level 0: pre-smoothing ends in bufs[(m-1)&1], post-smoothing flips m more times
-                const double* zi = ((m - 1) & 1) ? h->ml[0].zb : h->ml[0].za;
-                for (int k = 0; k < m; ++k) zi = zi == h->ml[0].za ? h->ml[0].zb : h->ml[0].za;
-                out = zi;
-            }
-            if (h->ml_out && h->ml_out != out) return fail(ASC_ERR_INVALID, "internal: V-cycle output buffer moved");
-            h->ml_out = out;
-            return ASC_OK;
-        }
-        std::vector<const double*> cur(nl + 1, nullptr);
-        for (int l = 0; l < nl; ++l) {   // down: pre-smooth from zero, restrict the residual
+        if (nl > kCycleMaxLevels) return fail(ASC_ERR_INVALID, "internal: too many coarse levels");
+        static const int ctas_env = getenv("ASC_ML_CTAS") ? atoi(getenv("ASC_ML_CTAS")) : 0;
+        MlCycleArgs a{};
+        a.nl = nl; a.m = m; a.ntop = h->ntop; a.frac = h->ml_frac;
+        for (int l = 0; l < nl; ++l) {
             asc_handle::MlLevel& L = h->ml[l];
-            const MlLevelDev ld = level_dev(L);
-            const double* r = l == 0 ? rin : L.r;
-            const int grid = cdiv(L.n, 4);
-            double* bufs[2] = {L.za, L.zb};
-            for (int k = 0; k < m; ++k)   // step k writes bufs[k & 1]; step 0 starts from zero and reads no z
-                ml_cheb_step_kernel<N><<<grid, 128, 0, st>>>(ld, h->ml_frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], L.d, nullptr, nullptr, done);
-            cur[l] = bufs[(m - 1) & 1];
-            asc_handle::MlLevel& C = h->ml[l + 1];
-            ml_residual_restrict_kernel<N><<<cdiv(C.n, 4), 128, 0, st>>>(ld, C.n, L.mptr, L.midx, L.rptr, L.ridx, r, cur[l], C.r, done);
-            h->launches += m + 1;
+            a.lv[l] = level_dev(L); a.agg[l] = L.agg; a.mptr[l] = L.mptr; a.midx[l] = L.midx; a.n_next[l] = L.n_next;
+            a.za[l] = L.za; a.zb[l] = L.zb; a.d[l] = L.d; a.rs[l] = L.rs;
         }
-        {   // top: explicit dense inverse
-            asc_handle::MlLevel& T = h->ml[nl];
-            const double* r = nl == 0 ? rin : T.r;
-            ml_dense_gemv_kernel<<<cdiv(h->ntop, 4), 128, 0, st>>>(h->Atop, r, h->ztop, h->ntop, done);
-            cur[nl] = h->ztop;
-            h->launches += 1;
-        }
-        for (int l = nl - 1; l >= 0; --l) {   // up: prolong (inside the first step), post-smooth
-            asc_handle::MlLevel& L = h->ml[l];
-            const MlLevelDev ld = level_dev(L);
-            const double* r = l == 0 ? rin : L.r;
-            const int grid = cdiv(L.n, 4);
-            const double* zi = cur[l];
-            for (int k = 0; k < m; ++k) {
-                double* zo = zi == L.za ? L.zb : L.za;
-                ml_cheb_step_kernel<N><<<grid, 128, 0, st>>>(ld, h->ml_frac, k, 0, r, zi, zo, L.d, k == 0 ? cur[l + 1] : nullptr, k == 0 ? L.agg : nullptr, done);
-                zi = zo;
-            }
-            cur[l] = zi;
-            h->launches += m;
-        }
+        a.r0 = rin;
+        for (int l = 1; l <= nl; ++l) a.r[l] = h->ml[l].r;
+        a.Atop = h->Atop; a.ztop = h->ztop; a.bar = h->mlbar; a.fail = h->flags + 9; a.done = done;
+        a.trace = h->ml_trace;
+        const int ctas = ctas_env > 0 ? std::min(ctas_env, 148) : 128;
+        ml_vcycle_kernel<N><<<ctas, kCycleThreads, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
-        if (h->ml_out && h->ml_out != cur[0]) return fail(ASC_ERR_INVALID, "internal: V-cycle output buffer moved");
-        h->ml_out = cur[0];
+        h->launches += 1;
+        const double* out = h->ztop;
+        if (nl > 0) {   // output buffer of level 0: pre-smoothing ends in bufs[(m-1)&1], post-smoothing flips m more times
+            const double* zi = ((m - 1) & 1) ? h->ml[0].zb : h->ml[0].za;
+            for (int k = 0; k < m; ++k) zi = zi == h->ml[0].za ? h->ml[0].zb : h->ml[0].za;
+            out = zi;
+        }
+        if (h->ml_out && h->ml_out != out) return fail(ASC_ERR_INVALID, "internal: V-cycle output buffer moved");
+        h->ml_out = out;
         return ASC_OK;
     }
 
@@ -752,11 +689,12 @@ struct Engine {
         const int nl = (int)h->ml.size() - 1;
         asc_handle::MlLevel& L0 = h->ml[0];
         CUDA_TRY(cudaMemsetAsync(h->mlbar, 0, sizeof(unsigned) * 4, h->stream));
+        if (getenv("ASC_ML_TRACE") && !h->ml_trace) CUDA_TRY(cudaMalloc((void**)&h->ml_trace, sizeof(unsigned long long) * 64 * 148 * 2));
         inc_v_kernel<N><<<cdiv(std::max(h->nInc, 1), 4), 128, 0, h->stream>>>(h->nInc, h->inc_lo, h->inc_hi, h->inc_lm, h->l_perm, h->Wm, h->Cinv, h->Vinc, h->Tinc);
         DBG_SYNC(h, "inc_v");
-        ml_blocks_l1_kernel<N><<<cdiv(std::max(h->nDest, 1), 4), 128, 0, h->stream>>>(h->nDest, h->dest_ptr, h->pos_lo, h->pos_up, h->pair_a, h->pair_b, h->Vinc, h->Tinc, L0.Eb);
+        ml_blocks_l1_kernel<N><<<cdiv(std::max(h->nDest, 1), 4), 128, 0, h->stream>>>(h->nDest, h->dest_ptr, h->pos_lo, h->pos_up, h->pair_a, h->pair_b, h->Vinc, h->Tinc, L0.bpos, L0.Eb);
         DBG_SYNC(h, "ml_blocks_l1");
-        if (h->rank == 0) ml_diag_l1_kernel<<<cdiv((int64_t)h->nC * N * N, 256), 256, 0, h->stream>>>(h->nC, N, lambda, h->cl_ptr, h->Bpp, L0.diag_pos, L0.Eb);
+        if (h->rank == 0) ml_diag_l1_kernel<<<cdiv((int64_t)h->nC * N * N, 256), 256, 0, h->stream>>>(h->nC, N, lambda, h->cl_ptr, h->Bpp, L0.diag_pos, L0.bpos, L0.Eb);
         ml_border_l1_kernel<<<cdiv((int64_t)h->nC * N * 6, 256), 256, 0, h->stream>>>(h->nC, N, h->rank == 0 ? 1 : 0, h->cl_ptr, h->cl_inc_ptr, h->cl_inc, h->inc_lm, h->Tinc,
                                                                                    h->WK, h->BpK, h->EK);
         CUDA_TRY(cudaGetLastError());
@@ -769,7 +707,7 @@ struct Engine {
         for (int l = 0; l < nl; ++l) {
             asc_handle::MlLevel& L = h->ml[l];
             asc_handle::MlLevel& C = h->ml[l + 1];
-            ml_dinv_kernel<N><<<cdiv(L.n, 64), 64, 0, h->stream>>>(L.n, L.diag_pos, L.Eb, L.Dinv, h->flags + 4);
+            ml_dinv_kernel<N><<<cdiv(L.n, 64), 64, 0, h->stream>>>(L.n, L.diag_pos, L.bpos, L.Eb, L.Dinv, h->flags + 4);
             // lambda_max(D^-1 E): 16 power steps from a fixed start vector, estimate = |w_16| / |w_15|
             const int grid = cdiv(L.n, 4);
             ml_power_init_kernel<<<cdiv(L.n * N, 256), 256, 0, h->stream>>>(L.n * N, L.za);
@@ -780,8 +718,8 @@ struct Engine {
                 ml_power_step_kernel<N><<<grid, 128, 0, h->stream>>>(L.n, L.row_ptr, L.col, L.Eb, L.Dinv, v, w, part);
                 std::swap(v, w);
             }
-            ml_power_finish_kernel<<<1, 256, 0, h->stream>>>(h->mlpart, h->mlpart + grid, grid, L.lmax);
-            ml_coarsen_kernel<<<C.nnzb, N * N, 0, h->stream>>>(C.nnzb, N * N, L.cptr, L.cidx, L.Eb, C.Eb);
+            ml_power_finish_kernel<<<1, 256, 0, h->stream>>>(h->mlpart, h->mlpart + grid, grid, L.lmax, h->ml_frac, h->ml_degree);
+            ml_coarsen_kernel<<<C.nnzb, N * N, 0, h->stream>>>(C.nnzb, N * N, L.cptr, L.cidx, L.bpos, L.Eb, C.bpos, C.Eb);
             CUDA_TRY(cudaGetLastError());
             DBG_SYNC(h, "ml level set-up");
             h->launches += kPowerSteps + 4;
@@ -789,14 +727,10 @@ struct Engine {
         {   // dense top level
             asc_handle::MlLevel& T = h->ml[nl];
             CUDA_TRY(cudaMemsetAsync(h->Atop, 0, sizeof(double) * (size_t)h->ntop * h->ntop, h->stream));
-            ml_top_assemble_kernel<<<T.n, N * N, 0, h->stream>>>(T.n, N, T.row_ptr, T.col, T.Eb, h->Atop);
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(kTopCtas); cfg.blockDim = dim3(kTopThreads); cfg.dynamicSmemBytes = sizeof(double) * (size_t)h->ntop; cfg.stream = h->stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = kTopCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, ml_top_invert_kernel, h->Atop, h->ntop, h->flags + 4));
+            ml_top_assemble_kernel<<<T.n, N * N, 0, h->stream>>>(T.n, N, T.row_ptr, T.col, T.bpos, T.Eb, h->Atop);
+            const int top_ctas = cdiv(h->ntop, kTopThreads / 32);
+            ml_top_invert_kernel<<<top_ctas, kTopThreads, sizeof(double) * (size_t)h->ntop * (kTopThreads / 32 + 1), h->stream>>>(h->Atop, h->ntop, h->mlpiv, h->mlbar + 2,
+                                                                                                                              h->flags + 4);
             ml_symmetrize_kernel<<<cdiv((int64_t)h->ntop * h->ntop, 256), 256, 0, h->stream>>>(h->Atop, h->ntop);
             DBG_SYNC(h, "ml top level");
             h->launches += 3;
@@ -1843,7 +1777,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             for (size_t i = 0; i < inc_cl.size(); ++i) cl_inc[f[inc_cl[i]]++] = (int)i;
         }
         if (h->use_coarse) {   // ---- multilevel hierarchy (coarse_ml.cuh)
-            const int gs = std::max(2, pr.pcg_ml_agg), top_dim = std::max(6 * N, pr.pcg_ml_top_dim), max_levels = std::max(1, pr.pcg_coarse_levels);
+            const int gs = std::max(2, pr.pcg_ml_agg), top_dim = std::min(kTopMaxDim, std::max(6 * N, pr.pcg_ml_top_dim)), max_levels = std::max(1, pr.pcg_coarse_levels);
             hl.clear();
             hl.emplace_back();
             MlHostLevel& L0 = hl[0];
@@ -1880,7 +1814,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 ml_coarsen_pattern(hl[hl.size() - 2], hl.back());
             }
             h->ntop = hl.back().n * N;
-            if (h->ntop > 4096) {   // the graph did not coarsen (e.g. no couplings between clusters): cluster-Jacobi alone
+            if (h->ntop > kTopMaxDim) {   // the graph did not coarsen far enough (e.g. no couplings between clusters): cluster-Jacobi alone
                 h->use_coarse = false;
                 hl.clear();
             }
@@ -1938,6 +1872,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             reqs.push_back(ArenaReq{(void**)&D.row_ptr, sizeof(int) * (size_t)(H.n + 1)});
             reqs.push_back(ArenaReq{(void**)&D.col, sizeof(int) * std::max<size_t>(H.col.size(), 1)});
             reqs.push_back(ArenaReq{(void**)&D.diag_pos, sizeof(int) * (size_t)H.n});
+            reqs.push_back(ArenaReq{(void**)&D.bpos, sizeof(int2) * std::max<size_t>(H.col.size(), 1)});
             if (l > 0) reqs.push_back(ArenaReq{(void**)&D.Eb, sizeof(double) * H.col.size() * NN});
             reqs.push_back(ArenaReq{(void**)&D.r, sizeof(double) * (size_t)H.n * N});
             if (!top) {
@@ -1946,18 +1881,17 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 reqs.push_back(ArenaReq{(void**)&D.midx, sizeof(int) * (size_t)H.n});
                 reqs.push_back(ArenaReq{(void**)&D.cptr, sizeof(int) * H.cptr.size()});
                 reqs.push_back(ArenaReq{(void**)&D.cidx, sizeof(int) * std::max<size_t>(H.cidx.size(), 1)});
-                reqs.push_back(ArenaReq{(void**)&D.rptr, sizeof(int) * (size_t)(H.n_next + 1)});
-                reqs.push_back(ArenaReq{(void**)&D.ridx, sizeof(int) * std::max<size_t>(H.ridx.size(), 1)});
                 reqs.push_back(ArenaReq{(void**)&D.Dinv, sizeof(double) * (size_t)H.n * NN});
-                reqs.push_back(ArenaReq{(void**)&D.lmax, sizeof(double) * 4});
+                reqs.push_back(ArenaReq{(void**)&D.lmax, sizeof(double) * 32});   // [lmax | pad | c1_k, c2_k per Chebyshev step]
                 reqs.push_back(ArenaReq{(void**)&D.za, sizeof(double) * (size_t)H.n * N});
                 reqs.push_back(ArenaReq{(void**)&D.zb, sizeof(double) * (size_t)H.n * N});
                 reqs.push_back(ArenaReq{(void**)&D.d, sizeof(double) * (size_t)H.n * N});
+                reqs.push_back(ArenaReq{(void**)&D.rs, sizeof(double) * (size_t)H.n * N});
                 max_grid = std::max<size_t>(max_grid, (size_t)cdiv(H.n, 4));
             }
         }
         ALLOC(Yb, (size_t)h->n1 * 6); ALLOC(Ski, 36); ALLOC(mlcol, h->n1);
-        ALLOC(Atop, (size_t)h->ntop * h->ntop); ALLOC(ztop, h->ntop); ALLOC(mlpart, 2 * max_grid + 2); ALLOC(mlbar, 4);
+        ALLOC(Atop, (size_t)h->ntop * h->ntop); ALLOC(ztop, h->ntop); ALLOC(mlpart, 2 * max_grid + 2); ALLOC(mlbar, 4); ALLOC(mlpiv, 2 * (size_t)h->ntop);
     }
     ALLOC(Minv, PN * N); ALLOC(MinvK, 36); ALLOC(rhs, PN + 8);
     ALLOC(vx, PN + 8); ALLOC(vr, PN + 8); ALLOC(vz, PN + 8); ALLOC(vp, PN + 8);
@@ -1978,8 +1912,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
     if (h->use_coarse) {
         h->ml[0].Eb = h->mlblk;
         h->EK = h->mlblk + hl[0].col.size() * (size_t)N * N;
-        if ((size_t)h->ntop * sizeof(double) > 200 * 1024) return fail(ASC_ERR_INVALID, "pcg_ml_top_dim too large for the top-level kernel");
-        CUDA_TRY(cudaFuncSetAttribute(ml_top_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(ml_top_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTopMaxDim * (kTopThreads / 32 + 1))));
     }
     lap("cudaMalloc + memset");
 #define UP(dst, src, bytes) CUDA_TRY(cudaMemcpyAsync(h->dst, src, (bytes), cudaMemcpyHostToDevice, h->stream))
@@ -2001,6 +1934,7 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             UP(cl_inc, cl_inc.data(), sizeof(int) * h->nInc);
         }
     }
+    std::vector<std::vector<int2>> bpos_stage(hl.size());   // alive until the stream synchronises below
     if (h->use_coarse) {
         UP(pose_agg, pose_cluster.data(), sizeof(int) * P);
         UP(dest_ptr, dest_ptr.data(), sizeof(int) * (h->nDest + 1)); UP(pos_lo, pos_lo.data(), sizeof(int) * h->nDest); UP(pos_up, pos_up.data(), sizeof(int) * h->nDest);
@@ -2011,14 +1945,18 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             CUDA_TRY(cudaMemcpyAsync(D.row_ptr, H.row_ptr.data(), sizeof(int) * (H.n + 1), cudaMemcpyHostToDevice, h->stream));
             if (!H.col.empty()) CUDA_TRY(cudaMemcpyAsync(D.col, H.col.data(), sizeof(int) * H.col.size(), cudaMemcpyHostToDevice, h->stream));
             CUDA_TRY(cudaMemcpyAsync(D.diag_pos, H.diag_pos.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
+            {   // element positions of the transposed block rows
+                bpos_stage[l].resize(H.col.size());
+                for (int i = 0; i < H.n; ++i)
+                    for (int k = H.row_ptr[i]; k < H.row_ptr[i + 1]; ++k) bpos_stage[l][k] = make_int2(H.row_ptr[i] * N * N + (k - H.row_ptr[i]), H.row_ptr[i + 1] - H.row_ptr[i]);
+                if (!H.col.empty()) CUDA_TRY(cudaMemcpyAsync(D.bpos, bpos_stage[l].data(), sizeof(int2) * H.col.size(), cudaMemcpyHostToDevice, h->stream));
+            }
             if (l + 1 < hl.size()) {
                 CUDA_TRY(cudaMemcpyAsync(D.agg, H.agg.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
                 CUDA_TRY(cudaMemcpyAsync(D.mptr, H.mptr.data(), sizeof(int) * (H.n_next + 1), cudaMemcpyHostToDevice, h->stream));
                 CUDA_TRY(cudaMemcpyAsync(D.midx, H.midx.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
                 CUDA_TRY(cudaMemcpyAsync(D.cptr, H.cptr.data(), sizeof(int) * H.cptr.size(), cudaMemcpyHostToDevice, h->stream));
                 if (!H.cidx.empty()) CUDA_TRY(cudaMemcpyAsync(D.cidx, H.cidx.data(), sizeof(int) * H.cidx.size(), cudaMemcpyHostToDevice, h->stream));
-                CUDA_TRY(cudaMemcpyAsync(D.rptr, H.rptr.data(), sizeof(int) * (H.n_next + 1), cudaMemcpyHostToDevice, h->stream));
-                if (!H.ridx.empty()) CUDA_TRY(cudaMemcpyAsync(D.ridx, H.ridx.data(), sizeof(int) * H.ridx.size(), cudaMemcpyHostToDevice, h->stream));
             }
         }
     }
@@ -2275,6 +2213,13 @@ int asc_solver_info(asc_handle* h, int32_t* n_clusters, int32_t* coarse_dim, int
     if (n_clusters) *n_clusters = h->nC;
     if (coarse_dim) *coarse_dim = h->use_coarse ? h->nz : 0;
     if (cluster_block_doubles) *cluster_block_doubles = (int64_t)h->scTotal;
+    return ASC_OK;
+}
+
+int asc_debug_ml_trace(asc_handle* h, unsigned long long* out, int32_t capacity) {
+    if (!h || !h->ml_trace) return fail(ASC_ERR_INVALID, "no trace (set ASC_ML_TRACE=1)");
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(out, h->ml_trace, sizeof(unsigned long long) * std::min<size_t>((size_t)capacity, 64 * 148 * 2), cudaMemcpyDeviceToHost));
     return ASC_OK;
 }
 

@@ -8,7 +8,7 @@
 //   level l:   Chebyshev(m) smoother on D_l^-1 E_l (D_l = the N x N diagonal blocks), coarse space = one N-vector per
 //              AGGREGATE of ~8 strongly connected nodes (greedy heavy-edge aggregation on the shared-landmark counts, built on
 //              the host), E_{l+1} = P^T E_l P = block sums (no triple product: P is piecewise constant);
-//   top level: dense (<= pcg_ml_top_dim unknowns), explicit inverse by an in-place Gauss-Jordan sweep in a thread-block cluster.
+//   top level: dense (<= pcg_ml_top_dim <= 1024 unknowns), explicit inverse by an in-place Gauss-Jordan sweep (one persistent kernel).
 // The dense extrinsic border is eliminated exactly around V by bordering:
 //   Y = V E_cK (six V-cycles per refresh),  S_k = S_KK - E_Kc Y,
 //   B [r; r_K]:  t = V r,  z_K = S_k^-1 (r_K - E_Kc t),  z = t - Y z_K          ( = inverse of [V^-1 E_cK; E_Kc S_KK], SPD because V <= E_cc^-1 )
@@ -17,7 +17,6 @@
 // Reductions use fixed trees / fixed member orders: results are run-to-run identical and identical on every rank.
 #pragma once
 #include <cuda_runtime.h>
-#include <cooperative_groups.h>
 #include <stdint.h>
 
 namespace asck {
@@ -27,7 +26,10 @@ struct MlLevelDev {
     int n;                    // nodes (block rows)
     const int* row_ptr;       // [n + 1]
     const int* col;           // [nnzb]
-    const double* Eb;         // [nnzb][N*N] row-major blocks
+    const double* Eb;         // blocks, stored TRANSPOSED inside each block row: element e of block k lives at bpos[k].x + e * bpos[k].y
+                              // (.x = row_ptr[row] * N*N + position in the row, .y = blocks in the row), so that the lanes of a warp,
+                              // one block each, read consecutive addresses (the phases of the V-cycle are bound by L1 sector requests)
+    const int2* bpos;         // [nnzb]
     const double* Dinv;       // [n][N*N] inverses of the diagonal blocks
     const double* lmax;       // [1] power-iteration estimate of lambda_max(D^-1 E)
 };
@@ -39,29 +41,55 @@ constexpr double kMlSafety = 1.2;   // upper end of the Chebyshev interval = kMl
 // per PCG iteration).  The N partial results per lane are summed over the warp with a fixed butterfly; lane a < N returns entry a.
 // v_eff = v (+ vc[agg] when vc != null: prolongation on the fly).  Vectors are read through L2 (__ldcg).
 template <int N>
+__device__ __forceinline__ void ml_load_x(const double* v, const double* vc, const int* __restrict__ agg, int c, double (&x)[N]) {
+#pragma unroll
+    for (int b = 0; b < N; ++b) x[b] = 0.0;
+    if (c < 0) return;
+#pragma unroll
+    for (int b = 0; b < N; ++b) x[b] = __ldcg(v + (size_t)c * N + b);
+    if (vc) {
+        const double* cc = vc + (size_t)__ldg(agg + c) * N;
+#pragma unroll
+        for (int b = 0; b < N; ++b) x[b] += __ldcg(cc + b);
+    }
+}
+
+// All loads of a round are ISSUED BEFORE the first use (the compiler otherwise interleaves eight-byte loads and DFMAs with only a
+// handful of loads in flight: measured ~10 us per phase, seven L2 latencies back to back), and the column index / vector entries of
+// the next round are prefetched.  Blocks with N*N > 64 entries are processed in row chunks to bound the register count.
+template <int N>
 __device__ __forceinline__ double bsr_row_dot(const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ Eb,
                                               const double* v, const double* vc, const int* __restrict__ agg, int i, int lane) {
-    const int k0 = __ldg(row_ptr + i), k1 = __ldg(row_ptr + i + 1);
+    constexpr int RC = N * N <= 64 ? N : (48 / N > 0 ? 48 / N : 1);   // block rows per chunk
+    const int k0 = __ldg(row_ptr + i), k1 = __ldg(row_ptr + i + 1), nb = k1 - k0;
+    const double* rowbase = Eb + (size_t)k0 * N * N;
     double acc[N];
 #pragma unroll
     for (int a = 0; a < N; ++a) acc[a] = 0.0;
-    for (int k = k0 + lane; k < k1; k += 32) {
-        const int c = __ldg(col + k);
-        const double* blk = Eb + (size_t)k * N * N;
-        double x[N];
+    // a lane takes blocks lane, lane + 32, ...; the columns and vector entries of TWO rounds are fetched together (rows hold ~27
+    // blocks on average and at most ~60: one dependent row_ptr -> col -> vector chain per row instead of one per round)
+    for (int kl = lane; kl < nb; kl += 64) {
+        const int kn = kl + 32;
+        const int ca = __ldg(col + k0 + kl), cb = kn < nb ? __ldg(col + k0 + kn) : -1;
+        double xa[N], xb[N];
+        ml_load_x<N>(v, vc, agg, ca, xa);
+        ml_load_x<N>(v, vc, agg, cb, xb);
 #pragma unroll
-        for (int b = 0; b < N; ++b) x[b] = __ldcg(v + (size_t)c * N + b);
-        if (vc) {
-            const double* cc = vc + (size_t)__ldg(agg + c) * N;
+        for (int a0 = 0; a0 < N; a0 += RC) {
+            double e[RC * N], f[RC * N];
 #pragma unroll
-            for (int b = 0; b < N; ++b) x[b] += __ldcg(cc + b);
-        }
+            for (int q = 0; q < RC * N; ++q) e[q] = (a0 * N + q < N * N) ? __ldg(rowbase + (size_t)(a0 * N + q) * nb + kl) : 0.0;
 #pragma unroll
-        for (int a = 0; a < N; ++a) {
-            double t = 0.0;
+            for (int q = 0; q < RC * N; ++q) f[q] = (cb >= 0 && a0 * N + q < N * N) ? __ldg(rowbase + (size_t)(a0 * N + q) * nb + kn) : 0.0;
 #pragma unroll
-            for (int b = 0; b < N; ++b) t = fma(__ldg(blk + a * N + b), x[b], t);
-            acc[a] += t;
+            for (int a = 0; a < RC; ++a) {
+                if (a0 + a < N) {
+                    double t = 0.0, u = 0.0;
+#pragma unroll
+                    for (int b = 0; b < N; ++b) { t = fma(e[a * N + b], xa[b], t); u = fma(f[a * N + b], xb[b], u); }
+                    acc[a0 + a] += t + u;
+                }
+            }
         }
     }
     double mine = 0.0;
@@ -88,72 +116,60 @@ __device__ __forceinline__ double small_matvec(const double* __restrict__ D, dou
 // One Chebyshev step of the smoother on level `lv` for node i (one warp):
 //   res = r - E (z_in [+ P zc]);  t = D^-1 res;  d <- c1 d + c2 t;  z_out = z_in [+ P zc] + d
 // step 0 of a sweep: d is not read (c1 = 0, c2 = 1/theta); zero_in: z_in == 0 (pre-smoothing), the product is skipped.
+// gather (first pre-smoothing step of a coarse level): r[i] is the sum of the finer level's residual over the members of aggregate i
+// (restriction with a piecewise-constant prolongator); it is formed here and stored for the later steps.
 // Vectors are read through L2 (__ldcg): inside the persistent V-cycle kernel other CTAs rewrote them a phase ago.
 template <int N>
 __device__ __forceinline__ void ml_cheb_node(const MlLevelDev& lv, double frac, int step, int zero_in, const double* r, const double* z_in,
-                                             double* z_out, double* d, const double* zc, const int* agg, int i, int lane) {
-    const double hi = kMlSafety * *lv.lmax, lo = hi / frac;
-    const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
-    double c1 = 0.0, c2 = 1.0 / theta;
-    {
-        double rho = 1.0 / sigma;
-        for (int k = 1; k <= step; ++k) { const double rn = 1.0 / (2.0 * sigma - rho); c1 = rn * rho; c2 = 2.0 * rn / delta; rho = rn; }
-    }
-    double res = lane < N ? __ldcg(r + (size_t)i * N + lane) : 0.0;
+                                             double* z_out, double* d, const double* zc, const int* agg, const double* fine_res,
+                                             const int* __restrict__ mptr, const int* __restrict__ midx, double* r_store, int i, int lane) {
+    // loads that do not depend on the product first
+    double drow[N];
+#pragma unroll
+    for (int b = 0; b < N; ++b) drow[b] = lane < N ? __ldg(lv.Dinv + (size_t)i * N * N + lane * N + b) : 0.0;
+    const double dold = (step > 0 && lane < N) ? __ldcg(d + (size_t)i * N + lane) : 0.0;
+    double res = 0.0;
+    if (fine_res) {
+        const int m0 = __ldg(mptr + i), m1 = __ldg(mptr + i + 1);
+        if (lane < N)
+            for (int q = m0; q < m1; ++q) res += __ldcg(fine_res + (size_t)__ldg(midx + q) * N + lane);
+        if (lane < N) r_store[(size_t)i * N + lane] = res;
+    } else if (lane < N) res = __ldcg(r + (size_t)i * N + lane);
+    const double c1 = __ldg(lv.lmax + 2 + 2 * step), c2 = __ldg(lv.lmax + 3 + 2 * step);   // Chebyshev coefficients of this step (ml_power_finish_kernel)
     double zin = 0.0;
     if (!zero_in) {
-        const double p = bsr_row_dot<N>(lv.row_ptr, lv.col, lv.Eb, z_in, zc, agg, i, lane);
         if (lane < N) {
-            res -= p;
             zin = __ldcg(z_in + (size_t)i * N + lane);
-            if (zc) zin += __ldcg(zc + (size_t)agg[i] * N + lane);
+            if (zc) zin += __ldcg(zc + (size_t)__ldg(agg + i) * N + lane);
         }
+        const double p = bsr_row_dot<N>(lv.row_ptr, lv.col, lv.Eb, z_in, zc, agg, i, lane);
+        res -= p;
     }
-    const double t = small_matvec<N>(lv.Dinv + (size_t)i * N * N, res, lane);
+    double t = 0.0;
+#pragma unroll
+    for (int b = 0; b < N; ++b) t = fma(drow[b], __shfl_sync(kFull, res, b), t);
     if (lane < N) {
-        const double dn = (step > 0 ? c1 * __ldcg(d + (size_t)i * N + lane) : 0.0) + c2 * t;
+        const double dn = c1 * dold + c2 * t;
         d[(size_t)i * N + lane] = dn;
         z_out[(size_t)i * N + lane] = zin + dn;
     }
 }
 
-// r_c[A] = sum over the members i of aggregate A of (r - E z)[i].  The rows of one aggregate are summed anyway, so the warp walks
-// the flattened list of ALL blocks of the aggregate's rows (rptr / ridx, built on the host), one block per lane and round:
-// the loads of different rounds are independent, and one butterfly at the end finishes the sum.
+// residual of row i: out = r - E z
 template <int N>
-__device__ __forceinline__ void ml_restrict_node(const MlLevelDev& lv, const int* __restrict__ mptr, const int* __restrict__ midx,
-                                                 const int* __restrict__ rptr, const int* __restrict__ ridx, const double* r, const double* z,
-                                                 double* rc, int A, int lane) {
-    double acc[N];
-#pragma unroll
-    for (int a = 0; a < N; ++a) acc[a] = 0.0;
-    const int q0 = __ldg(rptr + A), q1 = __ldg(rptr + A + 1);
-    for (int q = q0 + lane; q < q1; q += 32) {
-        const int k = __ldg(ridx + q);
-        const int c = __ldg(lv.col + k);
-        const double* blk = lv.Eb + (size_t)k * N * N;
-        double x[N];
-#pragma unroll
-        for (int b = 0; b < N; ++b) x[b] = __ldcg(z + (size_t)c * N + b);
-#pragma unroll
-        for (int a = 0; a < N; ++a) {
-            double t = 0.0;
-#pragma unroll
-            for (int b = 0; b < N; ++b) t = fma(__ldg(blk + a * N + b), x[b], t);
-            acc[a] -= t;
-        }
-    }
-    const int m0 = __ldg(mptr + A), m1 = __ldg(mptr + A + 1);
-    for (int q = m0 + lane; q < m1; q += 32) {
-        const int i = __ldg(midx + q);
-#pragma unroll
-        for (int a = 0; a < N; ++a) acc[a] += __ldcg(r + (size_t)i * N + a);
-    }
-#pragma unroll
-    for (int a = 0; a < N; ++a) {
-        const double t = warp_sum(acc[a]);
-        if (lane == a) rc[(size_t)A * N + a] = t;
-    }
+__device__ __forceinline__ void ml_residual_node(const MlLevelDev& lv, const double* r, const double* z, double* out, int i, int lane) {
+    const double ri = lane < N ? __ldcg(r + (size_t)i * N + lane) : 0.0;
+    const double p = bsr_row_dot<N>(lv.row_ptr, lv.col, lv.Eb, z, nullptr, nullptr, i, lane);
+    if (lane < N) out[(size_t)i * N + lane] = ri - p;
+}
+
+// rc[A] = sum of the finer level's residual over the members of aggregate A (restriction onto the dense top level)
+template <int N>
+__device__ __forceinline__ void ml_sum_members_node(const int* __restrict__ mptr, const int* __restrict__ midx, const double* fine_res, double* rc, int A, int lane) {
+    if (lane >= N) return;
+    double acc = 0.0;
+    for (int q = __ldg(mptr + A); q < __ldg(mptr + A + 1); ++q) acc += __ldcg(fine_res + (size_t)__ldg(midx + q) * N + lane);
+    rc[(size_t)A * N + lane] = acc;
 }
 
 // row `row` of y = A x, dense row-major n x n (the explicit inverse of the top level); one warp
@@ -167,153 +183,96 @@ __device__ __forceinline__ void ml_gemv_row(const double* __restrict__ A, const 
     if (lane == 0) y[row] = t;
 }
 
-template <int N>
-__global__ void __launch_bounds__(128)
-ml_cheb_step_kernel(MlLevelDev lv, double frac, int step, int zero_in, const double* r, const double* z_in, double* z_out, double* d,
-                    const double* zc, const int* agg, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (i >= lv.n) return;
-    ml_cheb_node<N>(lv, frac, step, zero_in, r, z_in, z_out, d, zc, agg, i, lane);
-}
-
-template <int N>
-__global__ void __launch_bounds__(128)
-ml_residual_restrict_kernel(MlLevelDev lv, int n_coarse, const int* __restrict__ mptr, const int* __restrict__ midx, const int* __restrict__ rptr,
-                            const int* __restrict__ ridx, const double* r, const double* z, double* rc, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int A = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (A >= n_coarse) return;
-    ml_restrict_node<N>(lv, mptr, midx, rptr, ridx, r, z, rc, A, lane);
-}
-
-__global__ void __launch_bounds__(128) ml_dense_gemv_kernel(const double* __restrict__ A, const double* x, double* y, int n, const int* __restrict__ done) {
-    if (done && *done) return;
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= n) return;
-    ml_gemv_row(A, x, y, n, row, lane);
-}
-
-// ---- the whole V-cycle as ONE persistent kernel: the phases above separated by a grid barrier instead of kernel boundaries.
-// On C2 the V-cycle is ~20 dependent phases over < 10 MB of L2-resident data: as separate launches it costs ~170 us per PCG
-// iteration (launch gaps), as one kernel ~40 us.  kCycleCtas CTAs must be co-resident (they are: <= one per SM, 256 threads, no
-// shared memory); a barrier that does not complete within ~2 s reports through `fail` instead of hanging.
+// ---- the whole V-cycle as ONE persistent kernel: its phases are separated by a grid barrier instead of kernel boundaries.
+// On C2 the V-cycle is ~20 dependent phases over < 10 MB of L2-resident data.  kCycleCtas CTAs must be co-resident (they are:
+// <= one per SM, 256 threads, no shared memory); a barrier that does not complete within ~2 s reports through `fail` instead of
+// hanging.  Measured with the barrier trace (scripts/vc_trace.py): the barrier itself costs ~1.1 us; a phase is bound by the
+// dependent L2 accesses of one block row (row_ptr -> col -> vector), which is why every load of a round is issued up front.
 constexpr int kCycleMaxLevels = 8;
 constexpr int kCycleThreads = 256;
 struct MlCycleArgs {
-    int nl, m, ntop, first_cluster_level, dbg;
+    int nl, m, ntop;
     double frac;
     MlLevelDev lv[kCycleMaxLevels];
     const int* agg[kCycleMaxLevels];
     const int* mptr[kCycleMaxLevels];
     const int* midx[kCycleMaxLevels];
-    const int* rptr[kCycleMaxLevels];
-    const int* ridx[kCycleMaxLevels];
     int n_next[kCycleMaxLevels];
-    const double* r[kCycleMaxLevels + 1];   // r[0] = the caller's right-hand side; r[l] = restricted residual of level l
-    double* rw[kCycleMaxLevels + 1];        // the same buffers, writable (rw[0] unused)
+    const double* r0;                       // the caller's right-hand side (level 0)
+    double* r[kCycleMaxLevels + 1];         // r[l], l >= 1: restricted residual of level l (r[nl]: right-hand side of the top level)
+    double* rs[kCycleMaxLevels];            // residual r - E z of level l after pre-smoothing
     double* za[kCycleMaxLevels];
     double* zb[kCycleMaxLevels];
     double* d[kCycleMaxLevels];
     const double* Atop;
     double* ztop;
     unsigned* bar;                          // [2]: arrival counter, exit counter (both return to zero)
+    unsigned long long* trace;              // debugging: per CTA and barrier, globaltimer at arrival and at release (null: off)
     int* fail;
     const int* done;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ unsigned long long ml_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
-__device__ __forceinline__ void ml_grid_barrier(unsigned* bar, unsigned& target, int* fail, int variant = 0) {
-    __syncthreads();   // the CTA's writes of this phase happen-before thread 0's release below (bar.sync + cumulativity)
+// One fence on each side and plain polling in between (an acquire load would invalidate L1 on EVERY poll: CCTL.IVALL).
+__device__ __forceinline__ void ml_grid_barrier(unsigned* bar, unsigned& target, int* fail, unsigned long long* trace) {
+    __syncthreads();   // the CTA's writes of this phase happen-before thread 0's fence below (bar.sync + cumulativity)
     if (threadIdx.x == 0) {
+        if (trace) trace[(size_t)(target / gridDim.x) * gridDim.x * 2 + blockIdx.x * 2] = ml_globaltimer();
         target += gridDim.x;
-        if (variant == 0) {
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-            const long long t0 = clock64();
-            while (ld_acquire_gpu_u32(bar) < target) {
-                if (clock64() - t0 > 4000000000ll) { *fail = 1; break; }
-            }
-        } else {   // one fence on each side, plain polling in between (an acquire load invalidates L1 on EVERY poll: CCTL.IVALL)
-            __threadfence();
-            atomicAdd(bar, 1u);
-            const long long t0 = clock64();
-            while (*((volatile unsigned*)bar) < target) {
-                if (clock64() - t0 > 4000000000ll) { *fail = 1; break; }
-            }
-            __threadfence();
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const long long t0 = clock64();
+        while (*((volatile unsigned*)bar) < target) {
+            if (clock64() - t0 > 4000000000ll) { *fail = 1; break; }
         }
+        __threadfence();
+        if (trace) trace[(size_t)(target / gridDim.x - 1) * gridDim.x * 2 + blockIdx.x * 2 + 1] = ml_globaltimer();
     }
     __syncthreads();
 }
 
-// Phases of the FINE levels span the whole grid and are separated by the grid barrier (~8 us per phase on a B200: three dependent L2
-// round trips plus the barrier).  Levels with at most kClusterLevelNodes nodes (and everything below them, top level included) are
-// handled by thread-block cluster 0 alone, with the hardware cluster barrier between phases (~2.5 us per phase); the other
-// clusters wait at the next grid barrier.  a.first_cluster_level = first such level (nl + 1: none).
-constexpr int kCycleCluster = 8;
-constexpr int kClusterLevelNodes = 640;
-
 template <int N>
 __global__ void __launch_bounds__(kCycleThreads) ml_vcycle_kernel(const __grid_constant__ MlCycleArgs a) {
     if (a.done && *a.done) return;
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int lane = threadIdx.x & 31, wpc = kCycleThreads / 32;
-    const int gw = blockIdx.x * wpc + (threadIdx.x >> 5), ngw = gridDim.x * wpc;
-    const bool c0 = blockIdx.x < kCycleCluster;                                   // member of cluster 0
-    const int cw = (blockIdx.x % kCycleCluster) * wpc + (threadIdx.x >> 5), ncw = kCycleCluster * wpc;
-    const int fc = a.first_cluster_level;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (kCycleThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kCycleThreads / 32);
     unsigned target = 0;
     const double* cur[kCycleMaxLevels + 1];
-    // which output buffer every level ends its sweeps in is static: every CTA tracks it, whether or not it does the work
-    for (int l = 0; l < a.nl; ++l) {   // down
-        const bool cl = l >= fc;
-        const double* r = a.r[l];
+    for (int l = 0; l < a.nl; ++l) {   // down: pre-smooth from zero, residual
+        const double* r = l == 0 ? a.r0 : a.r[l];
         double* bufs[2] = {a.za[l], a.zb[l]};
-        const int w0 = cl ? cw : gw, nw = cl ? ncw : ngw;
         for (int k = 0; k < a.m; ++k) {
-            if (k > 0 || l > 0) {
-                if (!cl || l == fc && k == 0) ml_grid_barrier(a.bar, target, a.fail, a.dbg >> 1);   // (entering cluster mode: the restriction above was a grid phase)
-                else if (c0) cluster.sync();
-            }
-            if ((!cl || c0) && !(a.dbg & 1))
-                for (int i = w0; i < a.lv[l].n; i += nw)
-                    ml_cheb_node<N>(a.lv[l], a.frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], a.d[l], nullptr, nullptr, i, lane);
+            if (k > 0 || l > 0) ml_grid_barrier(a.bar, target, a.fail, a.trace);
+            const bool gather = k == 0 && l > 0;   // restriction of the finer residual, formed on the fly and stored in r[l]
+            for (int i = gw; i < a.lv[l].n; i += nw)
+                ml_cheb_node<N>(a.lv[l], a.frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], a.d[l], nullptr, nullptr,
+                                gather ? a.rs[l - 1] : nullptr, gather ? a.mptr[l - 1] : nullptr, gather ? a.midx[l - 1] : nullptr, a.r[l], i, lane);
         }
         cur[l] = bufs[(a.m - 1) & 1];
-        if (!cl) ml_grid_barrier(a.bar, target, a.fail, a.dbg >> 1);
-        else if (c0) cluster.sync();
-        if ((!cl || c0) && !(a.dbg & 1))
-            for (int A = w0; A < a.n_next[l]; A += nw) ml_restrict_node<N>(a.lv[l], a.mptr[l], a.midx[l], a.rptr[l], a.ridx[l], r, cur[l], a.rw[l + 1], A, lane);
+        ml_grid_barrier(a.bar, target, a.fail, a.trace);
+        for (int i = gw; i < a.lv[l].n; i += nw) ml_residual_node<N>(a.lv[l], r, cur[l], a.rs[l], i, lane);
     }
-    {   // top level
-        const bool cl = a.nl >= fc;
-        if (a.nl > 0) {
-            if (!cl || a.nl == fc) ml_grid_barrier(a.bar, target, a.fail, a.dbg >> 1);
-            else if (c0) cluster.sync();
-        }
-        const int w0 = cl ? cw : gw, nw = cl ? ncw : ngw;
-        if ((!cl || c0) && !(a.dbg & 1))
-            for (int row = w0; row < a.ntop; row += nw) ml_gemv_row(a.Atop, a.r[a.nl], a.ztop, a.ntop, row, lane);
-        cur[a.nl] = a.ztop;
+    if (a.nl > 0) {   // right-hand side of the top level
+        ml_grid_barrier(a.bar, target, a.fail, a.trace);
+        for (int A = gw; A < a.n_next[a.nl - 1]; A += nw) ml_sum_members_node<N>(a.mptr[a.nl - 1], a.midx[a.nl - 1], a.rs[a.nl - 1], a.r[a.nl], A, lane);
+        ml_grid_barrier(a.bar, target, a.fail, a.trace);
     }
-    for (int l = a.nl - 1; l >= 0; --l) {   // up
-        const bool cl = l >= fc;
-        const double* r = a.r[l];
+    for (int row = gw; row < a.ntop; row += nw) ml_gemv_row(a.Atop, a.nl == 0 ? a.r0 : a.r[a.nl], a.ztop, a.ntop, row, lane);
+    cur[a.nl] = a.ztop;
+    for (int l = a.nl - 1; l >= 0; --l) {   // up: prolong (inside the first step), post-smooth
+        const double* r = l == 0 ? a.r0 : a.r[l];
         const double* zi = cur[l];
-        const int w0 = cl ? cw : gw, nw = cl ? ncw : ngw;
         for (int k = 0; k < a.m; ++k) {
-            if (!cl) ml_grid_barrier(a.bar, target, a.fail, a.dbg >> 1);   // also the hand-over from cluster 0's coarse section
-            else if (c0) cluster.sync();
+            ml_grid_barrier(a.bar, target, a.fail, a.trace);
             double* zo = zi == a.za[l] ? a.zb[l] : a.za[l];
-            if ((!cl || c0) && !(a.dbg & 1))
-                for (int i = w0; i < a.lv[l].n; i += nw)
-                    ml_cheb_node<N>(a.lv[l], a.frac, k, 0, r, zi, zo, a.d[l], k == 0 ? cur[l + 1] : nullptr, k == 0 ? a.agg[l] : nullptr, i, lane);
+            for (int i = gw; i < a.lv[l].n; i += nw)
+                ml_cheb_node<N>(a.lv[l], a.frac, k, 0, r, zi, zo, a.d[l], k == 0 ? cur[l + 1] : nullptr, k == 0 ? a.agg[l] : nullptr, nullptr, nullptr, nullptr,
+                                nullptr, i, lane);
             zi = zo;
         }
         cur[l] = zi;
@@ -334,7 +293,7 @@ template <int N>
 __global__ void __launch_bounds__(128)
 ml_blocks_l1_kernel(int nDest, const int* __restrict__ dest_ptr, const int* __restrict__ pos_lo, const int* __restrict__ pos_up,
                     const int* __restrict__ pair_a, const int* __restrict__ pair_b, const double* __restrict__ V, const double* __restrict__ T,
-                    double* __restrict__ Eb) {
+                    const int2* __restrict__ bpos, double* __restrict__ Eb) {
     constexpr int NE = (N * N + 31) / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int d = blockIdx.x * 4 + warp;
@@ -355,26 +314,28 @@ ml_blocks_l1_kernel(int nDest, const int* __restrict__ dest_ptr, const int* __re
         }
     }
     const int plo = pos_lo[d], pup = pos_up[d];
+    const int2 blo = bpos[plo], bup = bpos[pup];
 #pragma unroll
     for (int i = 0; i < NE; ++i) {
         const int e = lane + 32 * i;
         if (e < N * N) {
-            Eb[(size_t)plo * N * N + e] = -acc[i];
-            if (pup != plo) Eb[(size_t)pup * N * N + (e % N) * N + e / N] = -acc[i];
+            Eb[blo.x + (size_t)e * blo.y] = -acc[i];
+            if (pup != plo) Eb[bup.x + (size_t)((e % N) * N + e / N) * bup.y] = -acc[i];
         }
     }
 }
 
 // diagonal blocks += sum_{p in cluster} (B_pp + lambda I)   (rank 0 only in a multi-GPU run); thread per (c, a, b)
 __global__ void ml_diag_l1_kernel(int nC, int N, double lambda, const int* __restrict__ cl_ptr, const double* __restrict__ Bpp,
-                                  const int* __restrict__ diag_pos, double* __restrict__ Eb) {
+                                  const int* __restrict__ diag_pos, const int2* __restrict__ bpos, double* __restrict__ Eb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nC * N * N) return;
     const int c = i / (N * N), a = (i / N) % N, b = i % N;
     double s = 0.0;
     for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) s += Bpp[(size_t)p * N * N + a * N + b];
     if (a == b) s += lambda * (cl_ptr[c + 1] - cl_ptr[c]);
-    Eb[(size_t)diag_pos[c] * N * N + a * N + b] += s;
+    const int2 bp = bpos[diag_pos[c]];
+    Eb[bp.x + (size_t)(a * N + b) * bp.y] += s;
 }
 
 // extrinsic border of level 1: EK[(c N + a) 6 + r] = sum_{p in c} B_pK[a][r] - sum over the cluster's incidences of (T W_Kj^T)[a][r]
@@ -397,27 +358,28 @@ __global__ void ml_border_l1_kernel(int nC, int N, int add_diag, const int* __re
 }
 
 // Galerkin coarsening with a piecewise-constant prolongator = block sums: coarse block k = sum of its child blocks (list order)
-__global__ void ml_coarsen_kernel(int nnzb_c, int NN, const int* __restrict__ cptr, const int* __restrict__ cidx, const double* __restrict__ Ef,
-                                  double* __restrict__ Ec) {
+__global__ void ml_coarsen_kernel(int nnzb_c, int NN, const int* __restrict__ cptr, const int* __restrict__ cidx, const int2* __restrict__ bpos_f,
+                                  const double* __restrict__ Ef, const int2* __restrict__ bpos_c, double* __restrict__ Ec) {
     const int k = blockIdx.x, e = threadIdx.x;
     if (k >= nnzb_c || e >= NN) return;
     double s = 0.0;
-    for (int q = cptr[k]; q < cptr[k + 1]; ++q) s += Ef[(size_t)cidx[q] * NN + e];
-    Ec[(size_t)k * NN + e] = s;
+    for (int q = cptr[k]; q < cptr[k + 1]; ++q) { const int2 bp = bpos_f[cidx[q]]; s += Ef[bp.x + (size_t)e * bp.y]; }
+    const int2 bc = bpos_c[k];
+    Ec[bc.x + (size_t)e * bc.y] = s;
 }
 
 // Dinv[i] = inverse of the N x N diagonal block (SPD): Gauss-Jordan without pivoting, one thread per node
 template <int N>
-__global__ void __launch_bounds__(64) ml_dinv_kernel(int n, const int* __restrict__ diag_pos, const double* __restrict__ Eb, double* __restrict__ Dinv,
-                                                     int* __restrict__ fail) {
+__global__ void __launch_bounds__(64) ml_dinv_kernel(int n, const int* __restrict__ diag_pos, const int2* __restrict__ bpos, const double* __restrict__ Eb,
+                                                     double* __restrict__ Dinv, int* __restrict__ fail) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double A[N][N];
-    const double* src = Eb + (size_t)diag_pos[i] * N * N;
+    const int2 bp = bpos[diag_pos[i]];
 #pragma unroll
     for (int a = 0; a < N; ++a)
 #pragma unroll
-        for (int b = 0; b < N; ++b) A[a][b] = src[a * N + b];
+        for (int b = 0; b < N; ++b) A[a][b] = Eb[bp.x + (size_t)(a * N + b) * bp.y];
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -474,8 +436,10 @@ __global__ void ml_power_init_kernel(int n, double* __restrict__ v) {
 }
 
 // lmax = sqrt(sum partB / sum partA); one block
+// also tabulates the Chebyshev coefficients of the smoother for the interval [hi / frac, hi], hi = kMlSafety * lmax:
+//   lmax[2 + 2 k] = c1_k, lmax[3 + 2 k] = c2_k  (d <- c1_k d + c2_k D^-1 res; c1_0 = 0, c2_0 = 1 / theta)
 __global__ void __launch_bounds__(256) ml_power_finish_kernel(const double* __restrict__ partA, const double* __restrict__ partB, int nPart,
-                                                               double* __restrict__ lmax) {
+                                                               double* __restrict__ lmax, double frac, int degree) {
     __shared__ double sa[256], sb[256];
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < nPart; i += 256) { a += partA[i]; b += partB[i]; }
@@ -485,52 +449,77 @@ __global__ void __launch_bounds__(256) ml_power_finish_kernel(const double* __re
         if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *lmax = (sa[0] > 0.0 && sb[0] > 0.0) ? sqrt(sb[0] / sa[0]) : 1.0;
+    if (threadIdx.x == 0) {
+        const double lm = (sa[0] > 0.0 && sb[0] > 0.0) ? sqrt(sb[0] / sa[0]) : 1.0;
+        lmax[0] = lm;
+        const double hi = kMlSafety * lm, lo = hi / frac, theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+        double rho = 1.0 / sigma;
+        lmax[2] = 0.0; lmax[3] = 1.0 / theta;
+        for (int k = 1; k < degree; ++k) { const double rn = 1.0 / (2.0 * sigma - rho); lmax[2 + 2 * k] = rn * rho; lmax[3 + 2 * k] = 2.0 * rn / delta; rho = rn; }
+    }
 }
 
 // dense copy of the last level: A[n N][n N] row-major from its BSR blocks
-__global__ void ml_top_assemble_kernel(int n, int N, const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ Eb,
-                                       double* __restrict__ A) {
+__global__ void ml_top_assemble_kernel(int n, int N, const int* __restrict__ row_ptr, const int* __restrict__ col, const int2* __restrict__ bpos,
+                                       const double* __restrict__ Eb, double* __restrict__ A) {
     const int i = blockIdx.x, e = threadIdx.x;
     if (i >= n || e >= N * N) return;
     const int ld = n * N, a = e / N, b = e % N;
-    for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) A[(size_t)(i * N + a) * ld + col[k] * N + b] = Eb[(size_t)k * N * N + e];
+    for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) { const int2 bp = bpos[k]; A[(size_t)(i * N + a) * ld + col[k] * N + b] = Eb[bp.x + (size_t)e * bp.y]; }
 }
 
-// In-place inverse of the dense SPD top-level matrix (n <= ~1024) by a Gauss-Jordan sweep without pivoting; one thread-block
-// CLUSTER of kTopCtas CTAs shares the work of every pivot step (rows are dealt round-robin to the cluster's threads' CTAs) and
-// synchronises with the hardware cluster barrier twice per step.  The matrix stays in L2 (n = 600: 2.9 MB).
-constexpr int kTopCtas = 8;
-constexpr int kTopThreads = 512;
-__global__ void __launch_bounds__(kTopThreads) ml_top_invert_kernel(double* A, int n, int* __restrict__ fail) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ double colk[];   // [n] pivot column, per CTA
-    const int cta = (int)cluster.block_rank(), ncta = (int)cluster.num_blocks();
-    const int tid = threadIdx.x;
+// In-place inverse of the dense SPD top-level matrix (n <= kTopMaxDim) by a Gauss-Jordan sweep without pivoting, as ONE persistent
+// kernel: every warp of the grid owns one matrix row for the whole sweep and keeps it in shared memory; the pivot row of step k is
+// broadcast through a two-slot global buffer (written by its owner at the end of step k - 1), so a step costs one grid barrier
+// (~1.1 us) plus ~1 us of work.  n = 876 (C2 with a one-level hierarchy): ~2 ms instead of 25 ms with one cluster and three
+// cooperative-groups cluster barriers per step.
+constexpr int kTopMaxDim = 1024;
+constexpr int kTopThreads = 256;                       // 8 warps = 8 rows per CTA
+constexpr int kTopCtas = kTopMaxDim / (kTopThreads / 32);
+__global__ void __launch_bounds__(kTopThreads) ml_top_invert_kernel(double* A, int n, double* piv /*[2][n]*/, unsigned* bar, int* fail) {
+    extern __shared__ double sm_top[];
+    const int wpc = kTopThreads / 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* prow = sm_top;                               // [n] scaled pivot row of the step
+    double* myrow = sm_top + n + (size_t)warp * n;       // [n] this warp's row
+    const int r = blockIdx.x * wpc + warp;               // the row this warp owns (r >= n: idle, still takes part in the barriers)
+    unsigned target = 0;
     bool bad = false;
-    // rows are written by one CTA and read by the others in later steps: every access goes to L2 (.cg), never through L1
+    if (r < n)
+        for (int c = lane; c < n; c += 32) myrow[c] = __ldcg(A + (size_t)r * n + c);
+    if (r == 0)
+        for (int c = lane; c < n; c += 32) __stcg(piv + c, myrow[c]);
+    ml_grid_barrier(bar, target, fail, nullptr);
     for (int k = 0; k < n; ++k) {
-        const double piv = __ldcg(A + (size_t)k * n + k);
-        bad = bad || !(piv > 0.0);
-        const double ip = 1.0 / piv;
-        for (int i = tid; i < n; i += kTopThreads) colk[i] = __ldcg(A + (size_t)i * n + k);
-        cluster.sync();   // everybody holds column k and the pivot before row k changes
-        if (cta == 0)
-            for (int c = tid; c < n; c += kTopThreads) __stcg(A + (size_t)k * n + c, c == k ? ip : __ldcg(A + (size_t)k * n + c) * ip);
-        cluster.sync();
-        // rows r != k, dealt to the cluster's warps round-robin; a warp walks one row (coalesced)
-        const int warp = tid >> 5, lane = tid & 31, nw = kTopThreads / 32;
-        for (int r = cta * nw + warp; r < n; r += ncta * nw) {
-            if (r == k) continue;
-            const double f = colk[r];
-            double* row = A + (size_t)r * n;
-            const double* rk = A + (size_t)k * n;
-            for (int c = lane; c < n; c += 32) __stcg(row + c, (c == k ? 0.0 : __ldcg(row + c)) - f * __ldcg(rk + c));
+        const double* pk = piv + (size_t)(k & 1) * n;
+        const double pivot = __ldcg(pk + k);
+        bad = bad || !(pivot > 0.0);
+        const double ip = 1.0 / pivot;
+        for (int c = threadIdx.x; c < n; c += kTopThreads) prow[c] = c == k ? ip : __ldcg(pk + c) * ip;
+        __syncthreads();
+        if (r < n) {
+            if (r == k) {
+                for (int c = lane; c < n; c += 32) myrow[c] = prow[c];
+            } else {
+                const double f = myrow[k];
+                __syncwarp();
+                for (int c = lane; c < n; c += 32) myrow[c] = (c == k ? 0.0 : myrow[c]) - f * prow[c];
+            }
+            if (r == k + 1) {   // next pivot row: publish it
+                __syncwarp();
+                double* pn = piv + (size_t)((k + 1) & 1) * n;
+                for (int c = lane; c < n; c += 32) __stcg(pn + c, myrow[c]);
+            }
         }
-        cluster.sync();
+        ml_grid_barrier(bar, target, fail, nullptr);   // (also orders prow reuse inside the CTA)
     }
-    if (bad && tid == 0 && cta == 0) atomicExch(fail, 1);
+    if (r < n)
+        for (int c = lane; c < n; c += 32) A[(size_t)r * n + c] = myrow[c];
+    if (bad && threadIdx.x == 0 && blockIdx.x == 0) atomicExch(fail, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(bar + 1, 1u) == gridDim.x - 1) { bar[0] = 0; bar[1] = 0; __threadfence(); }
+    }
 }
 
 // The Gauss-Jordan sweep leaves an inverse that is symmetric only up to cond * eps; CG needs an exactly symmetric preconditioner

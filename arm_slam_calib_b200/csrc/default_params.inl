@@ -28,6 +28,6 @@ void asc_default_params(asc_params* p) {
     p->pcg_coarse_levels = 8;
     p->pcg_ml_degree = 4;
     p->pcg_ml_agg = 8;
-    p->pcg_ml_top_dim = 256;
+    p->pcg_ml_top_dim = 1024;
 }
 

@@ -84,7 +84,7 @@ typedef struct asc_params {
     int32_t pcg_coarse_levels;       /* max smoothed levels of the V-cycle (8); 0 switches the coarse level off */
     int32_t pcg_ml_degree;           /* Chebyshev degree of the pre- and post-smoother (4) */
     int32_t pcg_ml_agg;              /* target nodes per aggregate (8) */
-    int32_t pcg_ml_top_dim;          /* aggregate until the coarsest level has at most this many unknowns (256); it is inverted densely */
+    int32_t pcg_ml_top_dim;          /* aggregate until the coarsest level has at most this many unknowns (1024, the maximum); it is inverted densely */
 } asc_params;
 
 /* One record per outer iterate() of the optimiser */
@@ -218,6 +218,8 @@ int asc_solver_info(asc_handle* h, int32_t* n_clusters, int32_t* coarse_dim, int
 /* Hierarchy of the multilevel coarse solve: number of levels (the last one is the dense top level; 0 = no coarse level), nodes and
  * non-zero N x N blocks of each level (arrays of `capacity` entries), Chebyshev degree of the smoothers. */
 int asc_coarse_info(asc_handle* h, int32_t* n_levels, int32_t* level_nodes, int64_t* level_blocks, int32_t capacity, int32_t* degree);
+/* debugging: barrier timestamps (globaltimer ns; [barrier][CTA][arrive, release]) of the last V-cycle launch when ASC_ML_TRACE is set */
+int asc_debug_ml_trace(asc_handle* h, unsigned long long* out, int32_t capacity);
 /* CUDA-event stopwatch recorded on the stream this handle launches its kernels on */
 int asc_timer_start(asc_handle* h);
 int asc_timer_stop(asc_handle* h, double* elapsed_ms);
