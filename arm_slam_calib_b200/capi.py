@@ -35,6 +35,7 @@ SIGNATURES = {
     "asc_set_problem": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "asc_set_values": (C.c_int, [_vp, _vp, _vp, _vp]),
     "asc_get_values": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "asc_append": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "asc_error": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "asc_linearize": (C.c_int, [_vp, C.POINTER(D.AscLinearStats)]),
     "asc_optimize": (C.c_int, [_vp, C.c_int32, C.POINTER(D.AscIterLog), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
@@ -299,6 +300,21 @@ class BatchOptimizer:
         l = np.ascontiguousarray(l, dtype=np.float64)
         x = np.ascontiguousarray(x, dtype=np.float64)
         self._check(self.L.asc_set_values(self.h, _ptr(q), _ptr(l), _ptr(x)))
+
+    def append(self, pose_idx, lm_idx, uv, enc_new, lm_prior_new, q_new, l_new, has_enc_new=None):
+        """asc_append: grow the packed graph by new keyframes / landmarks / observations, keeping the current estimate (incremental mode,
+        sim_genrobot.cpp:97-104).  New observations index the grown pose / landmark sets."""
+        pi = np.ascontiguousarray(pose_idx, dtype=np.int32); li = np.ascontiguousarray(lm_idx, dtype=np.int32)
+        uvs = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        enc_new = np.ascontiguousarray(enc_new, dtype=np.float64).reshape(-1, self.N)
+        q_new = np.ascontiguousarray(q_new, dtype=np.float64).reshape(-1, self.N)
+        lp = np.ascontiguousarray(lm_prior_new, dtype=np.float64).reshape(-1, 3)
+        ln = np.ascontiguousarray(l_new, dtype=np.float64).reshape(-1, 3)
+        he = None if has_enc_new is None else np.ascontiguousarray(has_enc_new, dtype=np.uint8)
+        self._check(self.L.asc_append(self.h, enc_new.shape[0], lp.shape[0], pi.shape[0], _ptr(pi), _ptr(li), _ptr(uvs), _ptr(enc_new), _ptr(he),
+                                      _ptr(lp), _ptr(q_new), _ptr(ln)))
+        self.P += enc_new.shape[0]; self.Lm += lp.shape[0]; self.M += pi.shape[0]
+        self._error = None
 
     def values(self):
         q = np.empty((self.P, self.N)); l = np.empty((self.Lm, 3)); x = np.empty(12)

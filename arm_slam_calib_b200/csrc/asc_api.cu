@@ -814,7 +814,7 @@ struct Engine {
         // Coarse V-cycle off the critical path (single GPU): t = V (Z^T y) runs on a side branch of the graph beside pcg_mid and the
         // cluster update, and pcg_end advances the coarse correction by linearity: zc <- zc - alpha B [Z^T y; y_K].
         static const bool no_side_v = getenv("ASC_NO_SIDE_VCYCLE") != nullptr;
-        const bool side_v = !no_side_v && h->world == 1 && h->use_clusters && h->use_coarse;
+        const bool side_v = !no_side_v && (h->world == 1 || p2p) && h->use_clusters && h->use_coarse;
         // Residual replacement for the coarse correction: the first iteration of every chunk recomputes zc = B Z^T r from the residual
         // (V-cycle on the main stream), the others advance it by linearity.  The recursion alone accumulates rounding errors of
         // size eps * cond(B) * |zc_0| that do not shrink with the residual and stall CG on ill-conditioned coarse operators (small graphs,
@@ -830,16 +830,18 @@ struct Engine {
             mid.rcK = h->use_coarse ? h->rc + h->n1 : nullptr;
             int rc = schur_apply_launch(h, lambda, true, h->vp, h->flags, lam_dev, p2p);
             if (rc) return rc;
-            if (side_v) {   // fork: t = V (Z^T y) on the side stream
+            auto fork_vcycle = [&]() -> int {   // t = V (Z^T y) on the side stream
                 CUDA_TRY(cudaEventRecord(h->ev_c, h->stream));
                 CUDA_TRY(cudaStreamWaitEvent(h->stream2, h->ev_c, 0));
-                coarse_restrict_y_kernel<<<cdiv(h->nC, 4), 128, 0, h->stream2>>>(h->nC, N, h->cl_ptr, h->ybuf, h->ryc, h->flags);
+                coarse_restrict_y_kernel<<<cdiv(h->nC, 4), 128, 0, h->stream2>>>(h->nC, N, h->cl_ptr, h->ybuf, h->ryc, h->flags, p2p ? h->pcm : single);
                 CUDA_TRY(cudaGetLastError());
                 h->launches += 1;
-                rc = vcycle(h, h->ryc, h->flags, h->stream2);
-                if (rc) return rc;
+                int rcv = vcycle(h, h->ryc, h->flags, h->stream2);
+                if (rcv) return rcv;
                 CUDA_TRY(cudaEventRecord(h->ev_q, h->stream2));
-            }
+                return ASC_OK;
+            };
+            if (side_v && !p2p) { rc = fork_vcycle(); if (rc) return rc; }   // single GPU: right after pass C
             if (p2p) {
                 pcg_signal_kernel<<<1, 1024, 0, h->stream>>>(h->pcm, mid.partC, mid.nC, mid.partB, mid.nB, h->flags);
                 CUDA_TRY(cudaGetLastError());
@@ -856,6 +858,7 @@ struct Engine {
             pcg_mid_kernel<<<1, kReduceThreads, 0, h->stream>>>(mid, p2p ? h->pcm : single, rowC);
             CUDA_TRY(cudaGetLastError());
             h->launches += 1;
+            if (side_v && p2p) { rc = fork_vcycle(); if (rc) return rc; }    // multi-GPU: after pcg_mid has seen every peer's partial product
             EndArgs end{};
             end.P = h->P; end.N = N; end.part = h->partA; end.nPart = nUpd; end.tol2 = tol2; end.max_iters = h->prm.pcg_max_iters;
             end.p = h->vp; end.z = h->vz; end.scal = h->scal; end.done = h->flags; end.rc = h->use_coarse ? h->rc : nullptr; end.zc = h->zc;
@@ -2020,6 +2023,61 @@ int asc_set_values(asc_handle* h, const double* q, const double* l, const double
     h->values_set = true;
     h->linearized = false;
     return ASC_OK;
+}
+
+// Incremental mode: the drivers call OptimizeStep every one or two frames on a GROWING graph with the previous
+// estimate as the initial values (sim_genrobot.cpp:97-104, sim.cpp; ArmSlamCalib::SimulationStep adds the new configuration, its
+// encoder factor and the new projection factors, ArmSlamCalib.cpp:307-327).  asc_append grows the packed problem in place: the
+// existing observations (original order), encoder readings, landmark priors and the CURRENT ESTIMATE are taken from the device, the
+// new keyframes / landmarks / observations are appended, and the graph is re-packed -- so a following asc_optimize starts from the
+// previous solution (warm start) and the caller never re-sends what the library already holds.
+int asc_append(asc_handle* h, int32_t n_new_poses, int32_t n_new_landmarks, int64_t n_new_obs, const int32_t* pose_idx, const int32_t* lm_idx,
+               const double* uv, const double* enc_new, const uint8_t* has_enc_new, const double* lm_prior_new, const double* q_new, const double* l_new) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (n_new_poses < 0 || n_new_landmarks < 0 || n_new_obs < 0) return fail(ASC_ERR_INVALID, "bad sizes");
+    if ((n_new_obs > 0 && (!pose_idx || !lm_idx || !uv)) || (n_new_poses > 0 && (!enc_new || !q_new)) || (n_new_landmarks > 0 && (!lm_prior_new || !l_new)))
+        return fail(ASC_ERR_INVALID, "null argument");
+    const int N = h->N;
+    const size_t P0 = h->P, L0 = h->L, M0 = (size_t)h->M, P1 = P0 + n_new_poses, L1 = L0 + n_new_landmarks, M1 = M0 + (size_t)n_new_obs;
+    // what the device holds, back in the caller's order
+    std::vector<int> d_lm(M0), d_pose(M0), d_orig(M0);
+    std::vector<double> d_uv(2 * M0), enc(P1 * N), prior(3 * L1), q(P1 * N), l(3 * L1), x(12);
+    std::vector<uint8_t> has(P1, 1);
+    bool any_has = has_enc_new != nullptr || h->has_enc != nullptr;
+    if (M0) {
+        CUDA_TRY(cudaMemcpyAsync(d_lm.data(), h->p_lm, sizeof(int) * M0, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_pose.data(), h->p_pose, sizeof(int) * M0, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_orig.data(), h->p_orig, sizeof(int) * M0, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_uv.data(), h->p_uv, sizeof(double) * 2 * M0, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(enc.data(), h->enc, sizeof(double) * P0 * N, cudaMemcpyDeviceToHost, h->stream));
+    if (L0) CUDA_TRY(cudaMemcpyAsync(prior.data(), h->lm_prior, sizeof(double) * 3 * L0, cudaMemcpyDeviceToHost, h->stream));
+    if (h->has_enc) CUDA_TRY(cudaMemcpyAsync(has.data(), h->has_enc, P0, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    rc = asc_get_values(h, q.data(), L0 ? l.data() : nullptr, x.data());
+    if (rc) return rc;
+    std::vector<int32_t> pi(M1), li(M1);
+    std::vector<double> uvs(2 * M1);
+    for (size_t k = 0; k < M0; ++k) {
+        const size_t m = (size_t)d_orig[k];
+        pi[m] = d_pose[k]; li[m] = d_lm[k]; uvs[2 * m] = d_uv[2 * k]; uvs[2 * m + 1] = d_uv[2 * k + 1];
+    }
+    for (size_t m = 0; m < (size_t)n_new_obs; ++m) { pi[M0 + m] = pose_idx[m]; li[M0 + m] = lm_idx[m]; uvs[2 * (M0 + m)] = uv[2 * m]; uvs[2 * (M0 + m) + 1] = uv[2 * m + 1]; }
+    if (n_new_poses) {
+        std::memcpy(enc.data() + P0 * N, enc_new, sizeof(double) * (size_t)n_new_poses * N);
+        std::memcpy(q.data() + P0 * N, q_new, sizeof(double) * (size_t)n_new_poses * N);
+        for (int p = 0; p < n_new_poses; ++p) has[P0 + p] = has_enc_new ? has_enc_new[p] : 1;
+    }
+    if (n_new_landmarks) {
+        std::memcpy(prior.data() + 3 * L0, lm_prior_new, sizeof(double) * 3 * (size_t)n_new_landmarks);
+        std::memcpy(l.data() + 3 * L0, l_new, sizeof(double) * 3 * (size_t)n_new_landmarks);
+    }
+    double x_prior[12];
+    std::memcpy(x_prior, h->pc.x_prior, sizeof x_prior);
+    rc = asc_set_problem(h, (int32_t)P1, (int32_t)L1, (int64_t)M1, pi.data(), li.data(), uvs.data(), enc.data(), any_has ? has.data() : nullptr, prior.data(), x_prior);
+    if (rc) return rc;
+    return asc_set_values(h, q.data(), l.data(), x.data());
 }
 
 int asc_get_values(asc_handle* h, double* q, double* l, double* x) {

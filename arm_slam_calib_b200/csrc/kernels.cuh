@@ -1683,12 +1683,17 @@ pcg_update_kernel(int P, const double* __restrict__ p, const double* __restrict_
 // Z^T y over the keyframe rows: ry[c N + t] = sum of y[p N + t] over the keyframes p of cluster c (K entries of ry stay 0).
 // One warp per cluster; feeds the side-stream V-cycle t = V (Z^T y) while pcg_mid / the cluster update run on the main stream.
 __global__ void __launch_bounds__(128) coarse_restrict_y_kernel(int nC, int N, const int* __restrict__ cl_ptr, const double* __restrict__ y,
-                                                                 double* __restrict__ ry, const int* __restrict__ done) {
+                                                                 double* __restrict__ ry, const int* __restrict__ done, PeerComm pcm) {
     if (done && *done) return;
     const int c = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= nC || lane >= N) return;
     double a = 0.0;
-    for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) a += y[(size_t)p * N + lane];
+    if (pcm.world > 1) {   // multi-GPU: y = sum over ranks of the exchange slots (launched after pcg_mid, which waited for the peers)
+        const unsigned seq = *pcm.ctr;
+        for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) a += peer_sum(pcm, seq, (long long)p * N + lane);
+    } else {
+        for (int p = cl_ptr[c]; p < cl_ptr[c + 1]; ++p) a += y[(size_t)p * N + lane];
+    }
     ry[(size_t)c * N + lane] = a;
 }
 

@@ -167,6 +167,18 @@ int asc_set_values(asc_handle* h, const double* q /*[P][N]*/, const double* l /*
                    const double* x /*[12]*/);
 int asc_get_values(asc_handle* h, double* q, double* l, double* x);
 
+/*
+ * Incremental mode (the drivers call OptimizeStep every one or two frames on a growing graph, sim_genrobot.cpp:97-104; SimulationStep
+ * adds the configuration, its EncoderFactor and the new projection factors, ArmSlamCalib.cpp:307-327): append keyframes, landmarks and
+ * observations to the packed problem.  New observations index the GROWN sets (poses 0 .. P + n_new_poses - 1, landmarks 0 .. L +
+ * n_new_landmarks - 1) and are appended after the existing ones; the current estimate of the existing variables is kept (warm start),
+ * new variables start at q_new / l_new.  Link factors must be set again afterwards.
+ */
+int asc_append(asc_handle* h, int32_t n_new_poses, int32_t n_new_landmarks, int64_t n_new_obs, const int32_t* pose_idx,
+               const int32_t* lm_idx, const double* uv /*[n_new_obs][2]*/, const double* enc_new /*[n_new_poses][N]*/,
+               const uint8_t* has_enc_new /*[n_new_poses] or NULL*/, const double* lm_prior_new /*[n_new_landmarks][3]*/,
+               const double* q_new /*[n_new_poses][N]*/, const double* l_new /*[n_new_landmarks][3]*/);
+
 /* NonlinearFactorGraph::error(values) */
 int asc_error(asc_handle* h, double* error);
 
