@@ -1198,18 +1198,7 @@ pcg_cluster_update_kernel(int init, int N, const int* __restrict__ cl_ptr, const
     double zm = 0.0;
     if (t < n) {
         const double* Mcol = Mc + cl_off[c] + t;   // column t == row t (symmetric): coalesced across threads
-        // eight independent loads in flight per thread (the block is streamed once from HBM: 28 KB per cluster)
-        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
-        int col = 0;
-        for (; col + 7 < n; col += 8) {
-            const double m0 = __ldcs(Mcol + (size_t)col * n), m1 = __ldcs(Mcol + (size_t)(col + 1) * n), m2 = __ldcs(Mcol + (size_t)(col + 2) * n),
-                         m3 = __ldcs(Mcol + (size_t)(col + 3) * n), m4 = __ldcs(Mcol + (size_t)(col + 4) * n), m5 = __ldcs(Mcol + (size_t)(col + 5) * n),
-                         m6 = __ldcs(Mcol + (size_t)(col + 6) * n), m7 = __ldcs(Mcol + (size_t)(col + 7) * n);
-            z0 = fma(m0, rs[col], z0); z1 = fma(m1, rs[col + 1], z1); z2 = fma(m2, rs[col + 2], z2); z3 = fma(m3, rs[col + 3], z3);
-            z0 = fma(m4, rs[col + 4], z0); z1 = fma(m5, rs[col + 5], z1); z2 = fma(m6, rs[col + 6], z2); z3 = fma(m7, rs[col + 7], z3);
-        }
-        for (; col < n; ++col) z0 = fma(__ldcs(Mcol + (size_t)col * n), rs[col], z0);
-        zm = (z0 + z1) + (z2 + z3);
+        for (int col = 0; col < n; ++col) zm = fma(Mcol[(size_t)col * n], rs[col], zm);
         z[base + t] = zm;
         if (init) p[base + t] = zm;
     }
@@ -1571,20 +1560,12 @@ schur_pass_c_kernel(int P, int64_t M, double lambda_val, int add_diag, const int
     if (p < P) {
         double ut[6] = {0, 0, 0, 0, 0, 0};   // U = sum l x t | T = sum t over this lane's observations
         const int k0 = pose_ptr[p], k1 = pose_ptr[p + 1];
-        // Software pipeline over the keyframe's tiles: the landmark index of tile t+2 and the two gathered sectors (u, l) of tile
-        // t+1 are in flight while tile t is computed.  The kernel was bound by the dependent p_lm -> u4 / lml chain
-        // (long_scoreboard 27 warps per issue, 0.43 of the HBM roofline with one tile in flight).
-        int kq = k0 + lane;
-        int j_cur = kq < k1 ? __ldg(p_lm + kq) : 0;
-        int j_nxt = kq + 32 < k1 ? __ldg(p_lm + kq + 32) : 0;
-        d4 u_cur = ldg256(u4 + 4 * (size_t)j_cur), l_cur = ldg256(lml + 4 * (size_t)j_cur);
-        for (int k = kq; k < k1; k += 32) {
+        for (int k = k0 + lane; k < k1; k += 32) {
             double jl[6];
             load_jl<N>(J, M, k, jl);
-            const int j_nn = k + 64 < k1 ? __ldg(p_lm + k + 64) : 0;
-            const d4 u_n = ldg256(u4 + 4 * (size_t)j_nxt), l_n = ldg256(lml + 4 * (size_t)j_nxt);   // (index 0 past the end: a valid, unused sector)
-            const d4 u = u_cur, l = l_cur;
-            u_cur = u_n; l_cur = l_n; j_nxt = j_nn;
+            const int j = __ldg(p_lm + k);
+            const d4 u = ldg256(u4 + 4 * (size_t)j);
+            const d4 l = ldg256(lml + 4 * (size_t)j);
             const double e0 = jl[0] * u.x + jl[1] * u.y + jl[2] * u.z, e1 = jl[3] * u.x + jl[4] * u.y + jl[5] * u.z;
             const double t0 = jl[0] * e0 + jl[3] * e1, t1 = jl[1] * e0 + jl[4] * e1, t2 = jl[2] * e0 + jl[5] * e1;
             ut[0] += l.y * t2 - l.z * t1; ut[1] += l.z * t0 - l.x * t2; ut[2] += l.x * t1 - l.y * t0;
