@@ -1780,7 +1780,8 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             for (size_t i = 0; i < inc_cl.size(); ++i) cl_inc[f[inc_cl[i]]++] = (int)i;
         }
         if (h->use_coarse) {   // ---- multilevel hierarchy (coarse_ml.cuh)
-            const int gs = std::max(2, pr.pcg_ml_agg), top_dim = std::min(kTopMaxDim, std::max(6 * N, pr.pcg_ml_top_dim)), max_levels = std::max(1, pr.pcg_coarse_levels);
+            const bool fixed_gs = pr.pcg_ml_agg < 0;   // negative: exactly |pcg_ml_agg| nodes per aggregate, no enlargement (deep hierarchies for tests)
+            const int gs = std::max(2, std::abs(pr.pcg_ml_agg)), top_dim = std::min(kTopMaxDim, std::max(6 * N, pr.pcg_ml_top_dim)), max_levels = std::max(1, pr.pcg_coarse_levels);
             hl.clear();
             hl.emplace_back();
             MlHostLevel& L0 = hl[0];
@@ -1810,7 +1811,12 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
             while ((int)hl.size() <= max_levels && hl.back().n * N > top_dim) {
                 MlHostLevel& L = hl.back();
                 int na = 0;
-                ml_aggregate(L, gs, L.agg, na);
+                // Aggregates as large as it takes to reach the dense top level in ONE step when <= 64 nodes per aggregate can do it: the
+                // smoothed level-0 sweeps carry the convergence (prototype: 106 -> 111 -> 114 PCG iterations for aggregates of 8 / 16 /
+                // 32..64), while every extra level adds ~9 latency-bound phases to the V-cycle of each PCG iteration.
+                const long long need = (14LL * L.n * N + 10LL * top_dim - 1) / (10LL * top_dim);
+                const int gs_l = fixed_gs ? gs : (int)std::min<long long>(64, std::max<long long>(gs, need));
+                ml_aggregate(L, gs_l, L.agg, na);
                 if (na >= L.n) break;   // no coarsening possible (no couplings): stop here
                 L.n_next = na;
                 hl.emplace_back();

@@ -83,7 +83,8 @@ typedef struct asc_params {
        this library (csrc/coarse_ml.cuh) -- no size limit, no cuSOLVER/cuBLAS */
     int32_t pcg_coarse_levels;       /* max smoothed levels of the V-cycle (8); 0 switches the coarse level off */
     int32_t pcg_ml_degree;           /* Chebyshev degree of the pre- and post-smoother (4) */
-    int32_t pcg_ml_agg;              /* target nodes per aggregate (8) */
+    int32_t pcg_ml_agg;              /* nodes per aggregate (8); enlarged up to 64 when that reaches the dense top level in one step;
+                                        negative: exactly |value|, never enlarged */
     int32_t pcg_ml_top_dim;          /* aggregate until the coarsest level has at most this many unknowns (1024, the maximum); it is inverted densely */
 } asc_params;
 

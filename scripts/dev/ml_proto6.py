@@ -50,7 +50,7 @@ def main():
         return sp.bsr_matrix((np.linalg.inv(diag), np.arange(nn), np.arange(nn + 1)), shape=(nn * N, nn * N)).tocsr()
 
     # pair-count-like static weights: use block norms here
-    for gs in (8,):
+    for gs in (8, 16, 32, 64):
         levels = []
         E = E1; nn = nC
         while nn * N > top_dim:
@@ -86,7 +86,7 @@ def main():
             return z
 
         FR = {1: 4, 2: 4, 3: 8, 4: 10, 5: 15, 6: 20, 8: 30}
-        for mm in ((4, 4), (2, 4), (2, 6), (2, 8), (3, 6), (1, 6), (1, 8)):
+        for mm in ((4, 4),):
             def V(li, r):
                 if li == len(levels):
                     return sla.cho_solve(cf, r)

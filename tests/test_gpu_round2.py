@@ -170,7 +170,7 @@ def test_multilevel_coarse_solve_is_exact_preconditioning(asc, oracle_cls, c2):
     """The V-cycle only preconditions: the converged damped step at C2 size must not depend on the hierarchy (degree, aggregate
     size, depth) nor on having a coarse level at all.  Also reports the hierarchy and the iteration counts."""
     sols, its_all = [], {}
-    variants = {"default": {}, "degree2": dict(pcg_ml_degree=2), "deep": dict(pcg_ml_agg=4, pcg_ml_top_dim=120), "none": dict(pcg_coarse_levels=0)}
+    variants = {"default": {}, "degree2": dict(pcg_ml_degree=2), "deep": dict(pcg_ml_agg=-4, pcg_ml_top_dim=120), "none": dict(pcg_coarse_levels=0)}
     for name, kw in variants.items():
         prm = asc.default_params()
         for k, v in kw.items():

@@ -124,7 +124,7 @@ def test_preconditioner_variants_give_the_same_solution(asc, oracle_cls, c1_offs
     elif variant == "ml_degree_2":
         prm.pcg_ml_degree = 2
     else:                       # several smoothed levels even on this small graph
-        prm.pcg_ml_agg = 2
+        prm.pcg_ml_agg = -2
         prm.pcg_ml_top_dim = 36
     opt = asc.BatchOptimizer(pb, prm)
     vals = perturbed_values(pb)
