@@ -198,3 +198,22 @@ def test_two_ranks_match_one_gpu(asc):
            os.path.join(ROOT, "scripts", "mgpu_check.py"), "c1"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and "MGPU_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_packing_does_not_depend_on_the_openmp_team_size(asc, c1_offset_problem):
+    """asc_set_problem's parallel counting sorts and incidence builder must give the same packed graph whatever team OpenMP delivers
+    (slices were derived from the REQUESTED thread count): the optimiser's result under OMP_NUM_THREADS=1 and under
+    OMP_THREAD_LIMIT=3 / OMP_DYNAMIC is bitwise the one of the default run."""
+    import json
+    script = ("import sys, json; sys.path.insert(0, %r); import arm_slam_calib_b200 as asc\n"
+              "from arm_slam_calib_b200.sim import pose12\n"
+              "pb = asc.make_sim_problem(trajectory_size=250, seed=0, extrinsic_guess=pose12(t=[0.1, 0.1, 0.1]))\n"
+              "opt = asc.BatchOptimizer(pb, asc.default_params()); q, l, x = opt.optimize(0)\n"
+              "print(json.dumps([opt.error().hex(), float(q.sum()).hex(), float(l.sum()).hex(), opt.iterations()]))\n" % ROOT)
+    outs = []
+    for env in ({}, {"OMP_NUM_THREADS": "1"}, {"OMP_THREAD_LIMIT": "3", "OMP_DYNAMIC": "true"}, {"OMP_NUM_THREADS": "5"}):
+        e = dict(os.environ); e.update(env)
+        r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=e, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert all(o == outs[0] for o in outs[1:]), outs
