@@ -135,9 +135,6 @@ struct MlHostLevel {
     std::vector<int> row_ptr, col, diag_pos;   // BSR pattern, both triangles, columns ascending
     std::vector<double> w;                     // static edge weight per block (shared-landmark pair count, summed on coarsening)
     std::vector<int> agg, mptr, midx;          // aggregation to the next level
-    std::vector<int> sagg, smptr, smidx, dmap; // smoother blocks (<= kSmootherNodes nodes each): members, and the BSR block of every member pair
-    std::vector<long long> soff, dmoff;        // offsets of each block's dense inverse / of its pair map
-    int nsb = 0;
     std::vector<int> cptr, cidx;               // children of each block of the NEXT level among this level's blocks
     int n_next = 0;
 };
@@ -308,10 +305,7 @@ struct asc_handle {
         int2* bpos = nullptr;                                                 // where each block's elements live (transposed rows, coarse_ml.cuh)
         int *agg = nullptr, *mptr = nullptr, *midx = nullptr;                 // node -> aggregate; members of each aggregate
         int *cptr = nullptr, *cidx = nullptr;                                 // blocks of THIS level that sum into each block of the next
-        double *Eb = nullptr, *Dblk = nullptr, *lmax = nullptr;
-        int nsb = 0;
-        int *smptr = nullptr, *smidx = nullptr, *dmap = nullptr;             // smoother blocks
-        long long *soff = nullptr, *dmoff = nullptr;
+        double *Eb = nullptr, *Dinv = nullptr, *lmax = nullptr;
         double *r = nullptr, *za = nullptr, *zb = nullptr, *d = nullptr, *rs = nullptr;   // V-cycle vectors (r of level 0 is the caller's)
     };
     std::vector<MlLevel> ml;
@@ -469,7 +463,6 @@ struct Engine {
         CUDA_TRY(cudaFuncSetAttribute(cluster_schur_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(cluster_schur_cta_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(cluster_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(ml_dblk_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (kSmootherNodes * N) * ((kSmootherNodes * N) | 1))));
         done[dev] = true;
         return ASC_OK;
     }
@@ -653,8 +646,7 @@ struct Engine {
     // ---- multilevel coarse solve (coarse_ml.cuh)
     static MlLevelDev level_dev(const asc_handle::MlLevel& L) {
         MlLevelDev d;
-        d.n = L.n; d.row_ptr = L.row_ptr; d.col = L.col; d.Eb = L.Eb; d.bpos = L.bpos; d.lmax = L.lmax;
-        d.nsb = L.nsb; d.smptr = L.smptr; d.smidx = L.smidx; d.soff = L.soff; d.Dblk = L.Dblk;
+        d.n = L.n; d.row_ptr = L.row_ptr; d.col = L.col; d.Eb = L.Eb; d.bpos = L.bpos; d.Dinv = L.Dinv; d.lmax = L.lmax;
         return d;
     }
 
@@ -676,8 +668,7 @@ struct Engine {
         for (int l = 1; l <= nl; ++l) a.r[l] = h->ml[l].r;
         a.Atop = h->Atop; a.ztop = h->ztop; a.bar = h->mlbar; a.fail = h->flags + 9; a.done = done;
         a.trace = h->ml_trace;
-        // one CTA per smoother block of level 0 when they fit the machine (C2: 146 blocks); never more CTAs than SMs (grid barrier)
-        const int ctas = ctas_env > 0 ? std::min(ctas_env, 148) : std::max(64, std::min(nl > 0 ? h->ml[0].nsb : 64, 148));
+        const int ctas = ctas_env > 0 ? std::min(ctas_env, 148) : 128;
         ml_vcycle_kernel<N><<<ctas, kCycleThreads, 0, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         h->launches += 1;
@@ -716,20 +707,15 @@ struct Engine {
         for (int l = 0; l < nl; ++l) {
             asc_handle::MlLevel& L = h->ml[l];
             asc_handle::MlLevel& C = h->ml[l + 1];
-            {
-                const int nmax = kSmootherNodes * N;
-                ml_dblk_kernel<N><<<L.nsb, 256, sizeof(double) * (size_t)nmax * (nmax | 1), h->stream>>>(L.nsb, L.smptr, L.soff, L.dmoff, L.dmap, L.bpos, L.Eb, L.Dblk,
-                                                                                                       h->flags + 4);
-            }
+            ml_dinv_kernel<N><<<cdiv(L.n, 64), 64, 0, h->stream>>>(L.n, L.diag_pos, L.bpos, L.Eb, L.Dinv, h->flags + 4);
             // lambda_max(D^-1 E): 16 power steps from a fixed start vector, estimate = |w_16| / |w_15|
-            const int grid = std::min(L.nsb, 148);
+            const int grid = cdiv(L.n, 4);
             ml_power_init_kernel<<<cdiv(L.n * N, 256), 256, 0, h->stream>>>(L.n * N, L.za);
             double *v = L.za, *w = L.zb;
             constexpr int kPowerSteps = 16;
-            const MlLevelDev ldv = level_dev(L);
             for (int k = 0; k < kPowerSteps; ++k) {
                 double* part = k == kPowerSteps - 2 ? h->mlpart : (k == kPowerSteps - 1 ? h->mlpart + grid : nullptr);
-                ml_power_step_kernel<N><<<grid, kCycleThreads, 0, h->stream>>>(ldv, v, w, part);
+                ml_power_step_kernel<N><<<grid, 128, 0, h->stream>>>(L.n, L.row_ptr, L.col, L.Eb, L.Dinv, v, w, part);
                 std::swap(v, w);
             }
             ml_power_finish_kernel<<<1, 256, 0, h->stream>>>(h->mlpart, h->mlpart + grid, grid, L.lmax, h->ml_frac, h->ml_degree);
@@ -1836,30 +1822,6 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 hl.emplace_back();
                 ml_coarsen_pattern(hl[hl.size() - 2], hl.back());
             }
-            for (size_t l = 0; l + 1 < hl.size(); ++l) {   // smoother blocks of every smoothed level: their own aggregation into <= kSmootherNodes nodes
-                MlHostLevel& L = hl[l];
-                ml_aggregate(L, kSmootherNodes, L.sagg, L.nsb);
-                L.smptr.assign(L.nsb + 1, 0);
-                for (int i = 0; i < L.n; ++i) L.smptr[L.sagg[i] + 1]++;
-                for (int a = 0; a < L.nsb; ++a) L.smptr[a + 1] += L.smptr[a];
-                L.smidx.assign(L.n, 0);
-                std::vector<int> fill(L.smptr.begin(), L.smptr.end() - 1);
-                for (int i = 0; i < L.n; ++i) L.smidx[fill[L.sagg[i]]++] = i;
-                L.soff.assign(L.nsb + 1, 0); L.dmoff.assign(L.nsb + 1, 0); L.dmap.clear();
-                for (int a = 0; a < L.nsb; ++a) {
-                    const int ns = L.smptr[a + 1] - L.smptr[a];
-                    L.soff[a + 1] = L.soff[a] + (long long)ns * N * ns * N;
-                    L.dmoff[a + 1] = L.dmoff[a] + (long long)ns * ns;
-                    for (int il = 0; il < ns; ++il)
-                        for (int jl = 0; jl < ns; ++jl) {
-                            const int i = L.smidx[L.smptr[a] + il], j = L.smidx[L.smptr[a] + jl];
-                            const int* b0 = L.col.data() + L.row_ptr[i];
-                            const int* b1 = L.col.data() + L.row_ptr[i + 1];
-                            const int* it = std::lower_bound(b0, b1, j);
-                            L.dmap.push_back(it != b1 && *it == j ? (int)(it - L.col.data()) : -1);
-                        }
-                }
-            }
             h->ntop = hl.back().n * N;
             if (h->ntop > kTopMaxDim) {   // the graph did not coarsen far enough (e.g. no couplings between clusters): cluster-Jacobi alone
                 h->use_coarse = false;
@@ -1928,19 +1890,13 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 reqs.push_back(ArenaReq{(void**)&D.midx, sizeof(int) * (size_t)H.n});
                 reqs.push_back(ArenaReq{(void**)&D.cptr, sizeof(int) * H.cptr.size()});
                 reqs.push_back(ArenaReq{(void**)&D.cidx, sizeof(int) * std::max<size_t>(H.cidx.size(), 1)});
-                D.nsb = H.nsb;
-                reqs.push_back(ArenaReq{(void**)&D.Dblk, sizeof(double) * (size_t)std::max<long long>(H.soff.back(), 1)});
-                reqs.push_back(ArenaReq{(void**)&D.smptr, sizeof(int) * (size_t)(H.nsb + 1)});
-                reqs.push_back(ArenaReq{(void**)&D.smidx, sizeof(int) * (size_t)H.n});
-                reqs.push_back(ArenaReq{(void**)&D.dmap, sizeof(int) * std::max<size_t>(H.dmap.size(), 1)});
-                reqs.push_back(ArenaReq{(void**)&D.soff, sizeof(long long) * (size_t)(H.nsb + 1)});
-                reqs.push_back(ArenaReq{(void**)&D.dmoff, sizeof(long long) * (size_t)(H.nsb + 1)});
+                reqs.push_back(ArenaReq{(void**)&D.Dinv, sizeof(double) * (size_t)H.n * NN});
                 reqs.push_back(ArenaReq{(void**)&D.lmax, sizeof(double) * 32});   // [lmax | pad | c1_k, c2_k per Chebyshev step]
                 reqs.push_back(ArenaReq{(void**)&D.za, sizeof(double) * (size_t)H.n * N});
                 reqs.push_back(ArenaReq{(void**)&D.zb, sizeof(double) * (size_t)H.n * N});
                 reqs.push_back(ArenaReq{(void**)&D.d, sizeof(double) * (size_t)H.n * N});
                 reqs.push_back(ArenaReq{(void**)&D.rs, sizeof(double) * (size_t)H.n * N});
-                max_grid = std::max<size_t>(max_grid, 148);
+                max_grid = std::max<size_t>(max_grid, (size_t)cdiv(H.n, 4));
             }
         }
         ALLOC(Yb, (size_t)h->n1 * 6); ALLOC(Ski, 36); ALLOC(mlcol, h->n1);
@@ -2009,11 +1965,6 @@ int asc_set_problem(asc_handle* h, int32_t P, int32_t L, int64_t M, const int32_
                 CUDA_TRY(cudaMemcpyAsync(D.mptr, H.mptr.data(), sizeof(int) * (H.n_next + 1), cudaMemcpyHostToDevice, h->stream));
                 CUDA_TRY(cudaMemcpyAsync(D.midx, H.midx.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
                 CUDA_TRY(cudaMemcpyAsync(D.cptr, H.cptr.data(), sizeof(int) * H.cptr.size(), cudaMemcpyHostToDevice, h->stream));
-                CUDA_TRY(cudaMemcpyAsync(D.smptr, H.smptr.data(), sizeof(int) * (H.nsb + 1), cudaMemcpyHostToDevice, h->stream));
-                CUDA_TRY(cudaMemcpyAsync(D.smidx, H.smidx.data(), sizeof(int) * H.n, cudaMemcpyHostToDevice, h->stream));
-                if (!H.dmap.empty()) CUDA_TRY(cudaMemcpyAsync(D.dmap, H.dmap.data(), sizeof(int) * H.dmap.size(), cudaMemcpyHostToDevice, h->stream));
-                CUDA_TRY(cudaMemcpyAsync(D.soff, H.soff.data(), sizeof(long long) * (H.nsb + 1), cudaMemcpyHostToDevice, h->stream));
-                CUDA_TRY(cudaMemcpyAsync(D.dmoff, H.dmoff.data(), sizeof(long long) * (H.nsb + 1), cudaMemcpyHostToDevice, h->stream));
                 if (!H.cidx.empty()) CUDA_TRY(cudaMemcpyAsync(D.cidx, H.cidx.data(), sizeof(int) * H.cidx.size(), cudaMemcpyHostToDevice, h->stream));
             }
         }

@@ -12,7 +12,6 @@
 // The dense extrinsic border is eliminated exactly around V by bordering:
 //   Y = V E_cK (six V-cycles per refresh),  S_k = S_KK - E_Kc Y,
 //   B [r; r_K]:  t = V r,  z_K = S_k^-1 (r_K - E_Kc t),  z = t - Y z_K          ( = inverse of [V^-1 E_cK; E_Kc S_KK], SPD because V <= E_cc^-1 )
-//   smoother: Chebyshev(m) on D^-1 E with D = block diagonal of E over smoother blocks of <= 8 nodes (exact inverses, one CTA each).
 // Everything is a fixed linear SPD operator, so PCG stays exact; only the iteration count depends on it (measured on C2, first
 // solve: exact dense coarse solve 90 iterations, this V-cycle with m = 4: ~110; scripts/dev/ml_proto6.py is the numpy prototype).
 // Reductions use fixed trees / fixed member orders: results are run-to-run identical and identical on every rank.
@@ -31,14 +30,8 @@ struct MlLevelDev {
                               // (.x = row_ptr[row] * N*N + position in the row, .y = blocks in the row), so that the lanes of a warp,
                               // one block each, read consecutive addresses (the phases of the V-cycle are bound by L1 sector requests)
     const int2* bpos;         // [nnzb]
-    // block-Jacobi smoother: D = the diagonal blocks of E over SMOOTHER BLOCKS of <= kSmootherNodes strongly connected nodes
-    // (their own greedy aggregation); one CTA applies one dense inverse (<= 96 x 96 at N = 12)
-    int nsb;                  // smoother blocks
-    const int* smptr;         // [nsb + 1] members of each smoother block ...
-    const int* smidx;         // [n]       ... node ids
-    const long long* soff;    // [nsb + 1] offset of each block's inverse in Dblk ((members * N)^2 doubles each, row-major, symmetric)
-    const double* Dblk;
-    const double* lmax;       // [0] power-iteration estimate of lambda_max(D^-1 E); [2 + 2k], [3 + 2k] Chebyshev coefficients of step k
+    const double* Dinv;       // [n][N*N] inverses of the diagonal blocks
+    const double* lmax;       // [1] power-iteration estimate of lambda_max(D^-1 E)
 };
 
 constexpr double kMlSafety = 1.2;   // upper end of the Chebyshev interval = kMlSafety * estimate (the power iteration converges from below)
@@ -108,68 +101,58 @@ __device__ __forceinline__ double bsr_row_dot(const int* __restrict__ row_ptr, c
     return mine;
 }
 
-constexpr int kSmootherNodes = 8;                     // nodes per smoother block
-constexpr int kCycleThreads = 256;
-constexpr int kCycleWarps = kCycleThreads / 32;
+// y_a = sum_b D[a][b] x_b over the first N lanes
+template <int N>
+__device__ __forceinline__ double small_matvec(const double* __restrict__ D, double x, int lane) {
+    double y = 0.0;
+#pragma unroll
+    for (int b = 0; b < N; ++b) {
+        const double xb = __shfl_sync(kFull, x, b);
+        if (lane < N) y = fma(D[lane * N + b], xb, y);
+    }
+    return y;
+}
 
-// One Chebyshev step of the block-Jacobi smoother for smoother block A (one CTA):
-//   res = r - E (z_in [+ P zc]) on the block's rows (one warp per row);  t = D_A^-1 res (dense, whole CTA);
-//   d <- c1 d + c2 t;  z_out = z_in [+ P zc] + d
-// step 0 of a sweep: c1 = 0; zero_in: z_in == 0 (pre-smoothing), the product is skipped.
+// One Chebyshev step of the smoother on level `lv` for node i (one warp):
+//   res = r - E (z_in [+ P zc]);  t = D^-1 res;  d <- c1 d + c2 t;  z_out = z_in [+ P zc] + d
+// step 0 of a sweep: d is not read (c1 = 0, c2 = 1/theta); zero_in: z_in == 0 (pre-smoothing), the product is skipped.
 // gather (first pre-smoothing step of a coarse level): r[i] is the sum of the finer level's residual over the members of aggregate i
 // (restriction with a piecewise-constant prolongator); it is formed here and stored for the later steps.
-// power: power iteration of the set-up, w = D^-1 E v (z_in = v, z_out = w); returns this warp's part of |w|^2 (lane 0).
-// sm: [2 * kSmootherNodes * N] doubles of shared memory.  Vectors are read through L2 (__ldcg).
+// Vectors are read through L2 (__ldcg): inside the persistent V-cycle kernel other CTAs rewrote them a phase ago.
 template <int N>
-__device__ __forceinline__ double ml_cheb_block(const MlLevelDev& lv, int step, int zero_in, const double* r, const double* z_in, double* z_out, double* d,
-                                              const double* zc, const int* agg, const double* fine_res, const int* __restrict__ mptr,
-                                              const int* __restrict__ midx, double* r_store, int A, double* sm, bool power) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = __ldg(lv.smptr + A), ns = __ldg(lv.smptr + A + 1) - m0, nA = ns * N;
-    double* s_res = sm;
-    double* s_zin = sm + kSmootherNodes * N;
-    for (int il = warp; il < ns; il += kCycleWarps) {
-        const int i = __ldg(lv.smidx + m0 + il);
-        double res = 0.0, zin = 0.0;
-        if (power) {
-            res = bsr_row_dot<N>(lv.row_ptr, lv.col, lv.Eb, z_in, nullptr, nullptr, i, lane);
-        } else {
-            if (fine_res) {
-                if (lane < N) {
-                    for (int q = __ldg(mptr + i); q < __ldg(mptr + i + 1); ++q) res += __ldcg(fine_res + (size_t)__ldg(midx + q) * N + lane);
-                    r_store[(size_t)i * N + lane] = res;
-                }
-            } else if (lane < N) res = __ldcg(r + (size_t)i * N + lane);
-            if (!zero_in) {
-                if (lane < N) {
-                    zin = __ldcg(z_in + (size_t)i * N + lane);
-                    if (zc) zin += __ldcg(zc + (size_t)__ldg(agg + i) * N + lane);
-                }
-                res -= bsr_row_dot<N>(lv.row_ptr, lv.col, lv.Eb, z_in, zc, agg, i, lane);
-            }
+__device__ __forceinline__ void ml_cheb_node(const MlLevelDev& lv, double frac, int step, int zero_in, const double* r, const double* z_in,
+                                             double* z_out, double* d, const double* zc, const int* agg, const double* fine_res,
+                                             const int* __restrict__ mptr, const int* __restrict__ midx, double* r_store, int i, int lane) {
+    // loads that do not depend on the product first
+    double drow[N];
+#pragma unroll
+    for (int b = 0; b < N; ++b) drow[b] = lane < N ? __ldg(lv.Dinv + (size_t)i * N * N + lane * N + b) : 0.0;
+    const double dold = (step > 0 && lane < N) ? __ldcg(d + (size_t)i * N + lane) : 0.0;
+    double res = 0.0;
+    if (fine_res) {
+        const int m0 = __ldg(mptr + i), m1 = __ldg(mptr + i + 1);
+        if (lane < N)
+            for (int q = m0; q < m1; ++q) res += __ldcg(fine_res + (size_t)__ldg(midx + q) * N + lane);
+        if (lane < N) r_store[(size_t)i * N + lane] = res;
+    } else if (lane < N) res = __ldcg(r + (size_t)i * N + lane);
+    const double c1 = __ldg(lv.lmax + 2 + 2 * step), c2 = __ldg(lv.lmax + 3 + 2 * step);   // Chebyshev coefficients of this step (ml_power_finish_kernel)
+    double zin = 0.0;
+    if (!zero_in) {
+        if (lane < N) {
+            zin = __ldcg(z_in + (size_t)i * N + lane);
+            if (zc) zin += __ldcg(zc + (size_t)__ldg(agg + i) * N + lane);
         }
-        if (lane < N) { s_res[il * N + lane] = res; s_zin[il * N + lane] = zin; }
+        const double p = bsr_row_dot<N>(lv.row_ptr, lv.col, lv.Eb, z_in, zc, agg, i, lane);
+        res -= p;
     }
-    __syncthreads();
-    const double* Di = lv.Dblk + __ldg(lv.soff + A);
-    const double c1 = power ? 0.0 : __ldg(lv.lmax + 2 + 2 * step), c2 = power ? 1.0 : __ldg(lv.lmax + 3 + 2 * step);
-    double n2 = 0.0;
-    for (int a = warp; a < nA; a += kCycleWarps) {
-        double acc = 0.0;
-        for (int b = lane; b < nA; b += 32) acc = fma(__ldg(Di + (size_t)a * nA + b), s_res[b], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const size_t idx = (size_t)__ldg(lv.smidx + m0 + a / N) * N + a % N;
-            if (power) { z_out[idx] = acc; n2 += acc * acc; }
-            else {
-                const double dn = (step > 0 ? c1 * __ldcg(d + idx) : 0.0) + c2 * acc;
-                d[idx] = dn;
-                z_out[idx] = s_zin[a] + dn;
-            }
-        }
+    double t = 0.0;
+#pragma unroll
+    for (int b = 0; b < N; ++b) t = fma(drow[b], __shfl_sync(kFull, res, b), t);
+    if (lane < N) {
+        const double dn = c1 * dold + c2 * t;
+        d[(size_t)i * N + lane] = dn;
+        z_out[(size_t)i * N + lane] = zin + dn;
     }
-    __syncthreads();   // sm is reused by the CTA's next block
-    return n2;
 }
 
 // residual of row i: out = r - E z
@@ -206,6 +189,7 @@ __device__ __forceinline__ void ml_gemv_row(const double* __restrict__ A, const 
 // hanging.  Measured with the barrier trace (scripts/vc_trace.py): the barrier itself costs ~1.1 us; a phase is bound by the
 // dependent L2 accesses of one block row (row_ptr -> col -> vector), which is why every load of a round is issued up front.
 constexpr int kCycleMaxLevels = 8;
+constexpr int kCycleThreads = 256;
 struct MlCycleArgs {
     int nl, m, ntop;
     double frac;
@@ -255,7 +239,6 @@ __device__ __forceinline__ void ml_grid_barrier(unsigned* bar, unsigned& target,
 template <int N>
 __global__ void __launch_bounds__(kCycleThreads) ml_vcycle_kernel(const __grid_constant__ MlCycleArgs a) {
     if (a.done && *a.done) return;
-    __shared__ double sm_blk[2 * kSmootherNodes * N];
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (kCycleThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kCycleThreads / 32);
     unsigned target = 0;
@@ -266,9 +249,9 @@ __global__ void __launch_bounds__(kCycleThreads) ml_vcycle_kernel(const __grid_c
         for (int k = 0; k < a.m; ++k) {
             if (k > 0 || l > 0) ml_grid_barrier(a.bar, target, a.fail, a.trace);
             const bool gather = k == 0 && l > 0;   // restriction of the finer residual, formed on the fly and stored in r[l]
-            for (int A = blockIdx.x; A < a.lv[l].nsb; A += gridDim.x)
-                ml_cheb_block<N>(a.lv[l], k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], a.d[l], nullptr, nullptr,
-                                 gather ? a.rs[l - 1] : nullptr, gather ? a.mptr[l - 1] : nullptr, gather ? a.midx[l - 1] : nullptr, a.r[l], A, sm_blk, false);
+            for (int i = gw; i < a.lv[l].n; i += nw)
+                ml_cheb_node<N>(a.lv[l], a.frac, k, k == 0 ? 1 : 0, r, bufs[(k + 1) & 1], bufs[k & 1], a.d[l], nullptr, nullptr,
+                                gather ? a.rs[l - 1] : nullptr, gather ? a.mptr[l - 1] : nullptr, gather ? a.midx[l - 1] : nullptr, a.r[l], i, lane);
         }
         cur[l] = bufs[(a.m - 1) & 1];
         ml_grid_barrier(a.bar, target, a.fail, a.trace);
@@ -287,9 +270,9 @@ __global__ void __launch_bounds__(kCycleThreads) ml_vcycle_kernel(const __grid_c
         for (int k = 0; k < a.m; ++k) {
             ml_grid_barrier(a.bar, target, a.fail, a.trace);
             double* zo = zi == a.za[l] ? a.zb[l] : a.za[l];
-            for (int A = blockIdx.x; A < a.lv[l].nsb; A += gridDim.x)
-                ml_cheb_block<N>(a.lv[l], k, 0, r, zi, zo, a.d[l], k == 0 ? cur[l + 1] : nullptr, k == 0 ? a.agg[l] : nullptr, nullptr, nullptr, nullptr, nullptr,
-                                 A, sm_blk, false);
+            for (int i = gw; i < a.lv[l].n; i += nw)
+                ml_cheb_node<N>(a.lv[l], a.frac, k, 0, r, zi, zo, a.d[l], k == 0 ? cur[l + 1] : nullptr, k == 0 ? a.agg[l] : nullptr, nullptr, nullptr, nullptr,
+                                nullptr, i, lane);
             zi = zo;
         }
         cur[l] = zi;
@@ -385,62 +368,62 @@ __global__ void ml_coarsen_kernel(int nnzb_c, int NN, const int* __restrict__ cp
     Ec[bc.x + (size_t)e * bc.y] = s;
 }
 
-// Inverse of the diagonal block of E over smoother block A: gather (dmap = BSR block of every (member, member) pair, -1: none),
-// Gauss-Jordan without pivoting in shared memory, symmetrise, store.  One CTA per smoother block.
+// Dinv[i] = inverse of the N x N diagonal block (SPD): Gauss-Jordan without pivoting, one thread per node
 template <int N>
-__global__ void __launch_bounds__(256)
-ml_dblk_kernel(int nsb, const int* __restrict__ smptr, const long long* __restrict__ soff, const long long* __restrict__ dmoff, const int* __restrict__ dmap,
-               const int2* __restrict__ bpos, const double* __restrict__ Eb, double* __restrict__ Dblk, int* __restrict__ fail) {
-    extern __shared__ double A[];
-    __shared__ double colk[kSmootherNodes * N];
-    __shared__ int bad;
-    const int blk = blockIdx.x;
-    if (blk >= nsb) return;
-    const int ns = smptr[blk + 1] - smptr[blk], n = ns * N, ld = n | 1;
-    const int* map = dmap + dmoff[blk];
-    if (threadIdx.x == 0) bad = 0;
-    for (int e = threadIdx.x; e < n * n; e += 256) {
-        const int ra = e / n, cb = e % n, il = ra / N, a = ra % N, jl = cb / N, b = cb % N;
-        const int kb = map[il * ns + jl];
-        double v = 0.0;
-        if (kb >= 0) { const int2 bp = bpos[kb]; v = Eb[bp.x + (size_t)(a * N + b) * bp.y]; }
-        A[ra * ld + cb] = v;
-    }
-    __syncthreads();
-    for (int k = 0; k < n; ++k) {
-        const double piv = A[k * ld + k];
-        if (threadIdx.x == 0 && !(piv > 0)) bad = 1;
+__global__ void __launch_bounds__(64) ml_dinv_kernel(int n, const int* __restrict__ diag_pos, const int2* __restrict__ bpos, const double* __restrict__ Eb,
+                                                     double* __restrict__ Dinv, int* __restrict__ fail) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double A[N][N];
+    const int2 bp = bpos[diag_pos[i]];
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int b = 0; b < N; ++b) A[a][b] = Eb[bp.x + (size_t)(a * N + b) * bp.y];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double piv = A[k][k];
+        ok = ok && (piv > 0.0);
         const double ip = 1.0 / piv;
-        for (int i = threadIdx.x; i < n; i += 256) colk[i] = A[i * ld + k];
-        __syncthreads();
-        for (int cc = threadIdx.x; cc < n; cc += 256) A[k * ld + cc] = cc == k ? ip : A[k * ld + cc] * ip;
-        __syncthreads();
-        for (int i = threadIdx.x; i < n * n; i += 256) {
-            const int r = i / n, cc = i % n;
-            if (r != k) A[r * ld + cc] = (cc == k ? 0.0 : A[r * ld + cc]) - colk[r] * A[k * ld + cc];
-        }
-        __syncthreads();
+        double colk[N];
+#pragma unroll
+        for (int a = 0; a < N; ++a) colk[a] = A[a][k];
+#pragma unroll
+        for (int b = 0; b < N; ++b) A[k][b] = b == k ? ip : A[k][b] * ip;
+#pragma unroll
+        for (int a = 0; a < N; ++a)
+            if (a != k)
+#pragma unroll
+                for (int b = 0; b < N; ++b) A[a][b] = (b == k ? 0.0 : A[a][b]) - colk[a] * A[k][b];
     }
-    double* dst = Dblk + soff[blk];
-    for (int i = threadIdx.x; i < n * n; i += 256) { const int r = i / n, cc = i % n; dst[i] = 0.5 * (A[r * ld + cc] + A[cc * ld + r]); }   // exactly symmetric
-    if (threadIdx.x == 0 && bad) atomicExch(fail, 1);
+    double* dst = Dinv + (size_t)i * N * N;
+#pragma unroll
+    for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int b = 0; b < N; ++b) dst[a * N + b] = 0.5 * (A[a][b] + A[b][a]);   // exactly symmetric
+    if (!ok) atomicExch(fail, 1);
 }
 
 // power iteration on D^-1 E (no normalisation inside: 16 steps grow the vector by ~2^16): w = D^-1 E v; with `part`, also the
-// CTA partial of |w|^2 (for the estimate |w_k| / |w_{k-1}| of the last two steps).  One CTA per smoother block (grid-stride).
+// CTA partial of |w|^2 (for the estimate |w_k| / |w_{k-1}| of the last two steps)
 template <int N>
-__global__ void __launch_bounds__(kCycleThreads) ml_power_step_kernel(MlLevelDev lv, const double* v, double* w, double* __restrict__ part) {
-    __shared__ double sm_blk[2 * kSmootherNodes * N];
-    __shared__ double s_n2[kCycleWarps];
+__global__ void __launch_bounds__(128)
+ml_power_step_kernel(int n, const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ Eb, const double* __restrict__ Dinv,
+                     const double* __restrict__ v, double* __restrict__ w, double* __restrict__ part) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + warp;
+    __shared__ double s[4];
     double n2 = 0.0;
-    for (int A = blockIdx.x; A < lv.nsb; A += gridDim.x) n2 += ml_cheb_block<N>(lv, 0, 0, nullptr, v, w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, A, sm_blk, true);
-    if ((threadIdx.x & 31) == 0) s_n2[threadIdx.x >> 5] = n2;
-    __syncthreads();
-    if (part && threadIdx.x == 0) {
-        double t = 0.0;
-        for (int q = 0; q < kCycleWarps; ++q) t += s_n2[q];
-        part[blockIdx.x] = t;
+    if (i < n) {
+        const double p = bsr_row_dot<N>(row_ptr, col, Eb, v, nullptr, nullptr, i, lane);
+        const double t = small_matvec<N>(Dinv + (size_t)i * N * N, lane < N ? p : 0.0, lane);
+        if (lane < N) { w[(size_t)i * N + lane] = t; n2 = t * t; }
     }
+    n2 = warp_sum(n2);
+    if (lane == 0) s[warp] = n2;
+    __syncthreads();
+    if (part && threadIdx.x == 0) part[blockIdx.x] = (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 // deterministic start vector of the power iteration: a fixed hash of the index in [0.5, 1.5)
