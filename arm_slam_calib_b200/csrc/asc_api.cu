@@ -2165,23 +2165,32 @@ int asc_get_projection_blocks(asc_handle* h, double* b, double* jq, double* jl) 
     const size_t M = (size_t)h->M, N = h->N;
     double2* bdbg = nullptr;
     double *d_b = nullptr, *d_jq = nullptr, *d_jl = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&bdbg, std::max<size_t>(M, 1) * sizeof(double2)));
-    CUDA_TRY(cudaMalloc((void**)&d_b, std::max<size_t>(M, 1) * 2 * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&d_jq, std::max<size_t>(M, 1) * 2 * N * sizeof(double)));
-    CUDA_TRY(cudaMalloc((void**)&d_jl, std::max<size_t>(M, 1) * 6 * sizeof(double)));
+    auto release = [&]() { cudaFree(bdbg); cudaFree(d_b); cudaFree(d_jq); cudaFree(d_jl); };
+    auto checked = [&](cudaError_t e, const char* what) -> int {
+        if (e == cudaSuccess) return ASC_OK;
+        release();
+        return fail(ASC_ERR_CUDA, "asc_get_projection_blocks: %s: %s", what, cudaGetErrorString(e));
+    };
+    if ((rc = checked(cudaMalloc((void**)&bdbg, std::max<size_t>(M, 1) * sizeof(double2)), "cudaMalloc"))) return rc;
+    if ((rc = checked(cudaMalloc((void**)&d_b, std::max<size_t>(M, 1) * 2 * sizeof(double)), "cudaMalloc"))) return rc;
+    if ((rc = checked(cudaMalloc((void**)&d_jq, std::max<size_t>(M, 1) * 2 * N * sizeof(double)), "cudaMalloc"))) return rc;
+    if ((rc = checked(cudaMalloc((void**)&d_jl, std::max<size_t>(M, 1) * 6 * sizeof(double)), "cudaMalloc"))) return rc;
     double2* saved = h->b_dbg;
     h->b_dbg = bdbg;
     rc = dispatch_linearize(h, true, nullptr, nullptr);
     if (!rc && M) rc = dispatch_unpack(h, d_b, d_jq, d_jl);
     h->b_dbg = saved;
-    if (!rc) {
-        if (b) cudaMemcpyAsync(b, d_b, M * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-        if (jq) cudaMemcpyAsync(jq, d_jq, M * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-        if (jl) cudaMemcpyAsync(jl, d_jl, M * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (rc) {
+        cudaStreamSynchronize(h->stream);
+        release();
+        return rc;
     }
-    cudaStreamSynchronize(h->stream);
-    cudaFree(bdbg); cudaFree(d_b); cudaFree(d_jq); cudaFree(d_jl);
-    return rc;
+    if (b && M && (rc = checked(cudaMemcpyAsync(b, d_b, M * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "copy of b"))) return rc;
+    if (jq && M && (rc = checked(cudaMemcpyAsync(jq, d_jq, M * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "copy of J_q"))) return rc;
+    if (jl && M && (rc = checked(cudaMemcpyAsync(jl, d_jl, M * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "copy of J_l"))) return rc;
+    if ((rc = checked(cudaStreamSynchronize(h->stream), "synchronize"))) return rc;
+    release();
+    return ASC_OK;
 }
 
 int asc_get_landmark_blocks(asc_handle* h, double* c, double* gl, double* wk) {

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ASC_MAX_DOF 20 /* data/dof_experiments.py:17 sweeps 4..19 DOF */
+#define ASC_MAX_DOF 20 /* array bound of asc_params; kernels are instantiated for 2..12 DOF (asc_set_chain rejects the rest with ASC_ERR_INVALID); data/dof_experiments.py:17 sweeps 4..19 */
 
 typedef struct asc_handle asc_handle;
 
