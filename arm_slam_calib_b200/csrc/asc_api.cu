@@ -942,13 +942,13 @@ struct Engine {
 
     // Multi-GPU: the failure flags that steer the host (non-PD landmark block of ONE shard, a peer-exchange timeout seen by ONE
     // rank) are rank-local; every rank must take the same branch or the next collective deadlocks.  One small all-reduce makes
-    // the decision global: afterwards h_flags[1..5, 8] are "somebody failed" indicators on every rank (own index kept if it has one).
+    // the decision global: afterwards h_flags[1..5, 8, 9] are "somebody failed" indicators on every rank (own index kept if it has one).
     static int agree_on_failures(asc_handle* h) {
         if (h->world <= 1) return ASC_OK;
         const int big = 0x7fffffff;
         double* d = h->status + 48;
         double v[8] = {h->h_flags[1] != big ? 1.0 : 0.0, h->h_flags[2] != big ? 1.0 : 0.0, h->h_flags[3] != big ? 1.0 : 0.0,
-                       h->h_flags[4] != 0 ? 1.0 : 0.0, h->h_flags[5] != 0 ? 1.0 : 0.0, h->h_flags[8] != 0 ? 1.0 : 0.0, 0.0, 0.0};
+                       h->h_flags[4] != 0 ? 1.0 : 0.0, h->h_flags[5] != 0 ? 1.0 : 0.0, h->h_flags[8] != 0 ? 1.0 : 0.0, h->h_flags[9] != 0 ? 1.0 : 0.0, 0.0};
         CUDA_TRY(cudaMemcpyAsync(d, v, sizeof v, cudaMemcpyHostToDevice, h->stream));
         int rc = allreduce(h, d, 8);
         if (rc) return rc;
@@ -960,6 +960,7 @@ struct Engine {
         if (v[3] > 0) h->h_flags[4] = 1;
         if (v[4] > 0) h->h_flags[5] = 1;
         if (v[5] > 0) h->h_flags[8] = 1;
+        if (v[6] > 0) h->h_flags[9] = 1;   // a grid-barrier watchdog is timing-dependent: one rank may see it alone
         return ASC_OK;
     }
 
